@@ -1,0 +1,60 @@
+"""Synthetic phantom volumes: fp32, x fastest, numpy shape (Z, Y, X).
+
+``blob_phantom``  -- BASELINE.json config 1: constant background 50 + K Gaussian blobs.
+``brain_phantom`` -- configs 2-5: ellipsoid "head" of intensity 100 + K blobs masked by the head.
+
+Deterministic in (shape, seed, K): ``numpy.random.default_rng(seed)`` with scalar draws in the
+order cx, cy, cz, sigma, a per blob.
+"""
+import numpy as np
+
+
+def _add_blob(vol, cx, cy, cz, sigma, a, mask=None):
+    Z, Y, X = vol.shape
+    h = int(4 * sigma) + 1
+    x0, x1 = max(0, int(cx) - h), min(X, int(cx) + h + 1)
+    y0, y1 = max(0, int(cy) - h), min(Y, int(cy) + h + 1)
+    z0, z1 = max(0, int(cz) - h), min(Z, int(cz) + h + 1)
+    if x0 >= x1 or y0 >= y1 or z0 >= z1:
+        return
+    zz, yy, xx = np.meshgrid(np.arange(z0, z1), np.arange(y0, y1), np.arange(x0, x1), indexing="ij")
+    r2 = (xx - cx) ** 2 + (yy - cy) ** 2 + (zz - cz) ** 2
+    blob = a * np.exp(-r2 / (2.0 * sigma * sigma))
+    if mask is not None:
+        blob = blob * mask[z0:z1, y0:y1, x0:x1]
+    vol[z0:z1, y0:y1, x0:x1] += blob
+
+
+def blob_phantom(shape_xyz=(128, 128, 128), seed=2, nblobs=200):
+    """Config 1 phantom: background 50, centres U[12, dim-12], sigma U[1.5,6], a 60*U[-1,1]."""
+    X, Y, Z = shape_xyz
+    rng = np.random.default_rng(seed)
+    vol = np.full((Z, Y, X), 50.0, dtype=np.float64)
+    for _ in range(nblobs):
+        cx = rng.uniform(12, X - 12)
+        cy = rng.uniform(12, Y - 12)
+        cz = rng.uniform(12, Z - 12)
+        sigma = rng.uniform(1.5, 6.0)
+        a = 60.0 * rng.uniform(-1.0, 1.0)
+        _add_blob(vol, cx, cy, cz, sigma, a)
+    return np.ascontiguousarray(vol.astype(np.float32))
+
+
+def brain_phantom(shape_xyz=(182, 218, 182), seed=1, nblobs=400):
+    """Configs 2-5 phantom: ellipsoid head (semi-axes 70,90,70 at MNI size, scaled otherwise)."""
+    X, Y, Z = shape_xyz
+    rng = np.random.default_rng(seed)
+    cx0, cy0, cz0 = X / 2.0, Y / 2.0, Z / 2.0
+    ax, ay, az = 70.0 * X / 182.0, 90.0 * Y / 218.0, 70.0 * Z / 182.0
+    z, y, x = np.ogrid[0:Z, 0:Y, 0:X]
+    mask = (((x - cx0) / ax) ** 2 + ((y - cy0) / ay) ** 2 + ((z - cz0) / az) ** 2) <= 1.0
+    vol = np.where(mask, 100.0, 0.0).astype(np.float64)
+    m = 25.0 * min(X, Y, Z) / 182.0
+    for _ in range(nblobs):
+        cx = rng.uniform(m, X - m)
+        cy = rng.uniform(m, Y - m)
+        cz = rng.uniform(m, Z - m)
+        sigma = rng.uniform(1.5, 7.0)
+        a = 60.0 * rng.uniform(-1.0, 1.0)
+        _add_blob(vol, cx, cy, cz, sigma, a, mask)
+    return np.ascontiguousarray(vol.astype(np.float32))
