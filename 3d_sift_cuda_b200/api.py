@@ -1,0 +1,305 @@
+"""ctypes binding of the C-ABI in include/s3d.h (lib3dsift_b200.so).
+
+Mirrors the reference's interface for the featExtract path: one ``Engine`` per GPU (the reference's
+``-dN``), ``Engine.extract(volume, Params(...))`` = ``featExtract [-2+|-2-] [-b|-br|-bn]`` up to the
+feature file, and stage-level methods with the meaning of the reference's four CUDA launchers
+(SIFT_cuda_Tools.cuh:32-38, 69-76, 202-205, 213-217).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is usable the calls
+raise ``S3DError``.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+FEATURE_DTYPE = np.dtype([("flag", "<u4"), ("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("scale", "<f4"),
+                          ("ori", "<f4", (9,)), ("eigs", "<f4", (3,)), ("pc", "<f4", (64,))])
+CAND_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("z", "<i4"), ("value", "<f4")])
+KEYPOINT_DTYPE = np.dtype([("octave", "<i4"), ("level", "<i4"), ("is_max", "<i4"),
+                           ("ix", "<i4"), ("iy", "<i4"), ("iz", "<i4"),
+                           ("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("scale", "<f4")])
+
+DESC_SIFT, DESC_BRIEF, DESC_RRIEF, DESC_NRRIEF = 0, 1, 2, 3
+_STATUS = {0: "ok", 1: "invalid argument", 2: "CUDA error", 3: "out of memory", 4: "capacity exceeded", 5: "unsupported"}
+
+EXPORTS = [
+    "s3d_ctx_create", "s3d_ctx_create_on_stream", "s3d_ctx_destroy", "s3d_last_error", "s3d_device_count",
+    "s3d_sync", "s3d_stream", "s3d_gaussian_taps", "s3d_blur3d", "s3d_dog", "s3d_subsample2", "s3d_detect",
+    "s3d_double_size", "s3d_halve_size", "s3d_extract", "s3d_extract_device", "s3d_extract_host_async",
+    "s3d_fetch_features", "s3d_fetch_counts", "s3d_result_device", "s3d_free", "s3d_num_octaves",
+    "s3d_get_level", "s3d_get_keypoints", "s3d_get_patches", "s3d_last_launch_count", "s3d_write_features_text",
+]
+
+
+class S3DError(RuntimeError):
+    pass
+
+
+class _Params(C.Structure):
+    _fields_ = [("double_mode", C.c_int), ("descriptor", C.c_int), ("eig_thres", C.c_float),
+                ("max_keypoints", C.c_int), ("max_features", C.c_int), ("keep_patches", C.c_int)]
+
+
+class Params:
+    """featExtract's options (featExtract.cpp:299-350 plus the README's -b/-br/-bn)."""
+
+    def __init__(self, double_mode=0, descriptor=DESC_SIFT, eig_thres=140.0, max_keypoints=0, max_features=0,
+                 keep_patches=False):
+        self.c = _Params(double_mode, descriptor, eig_thres, max_keypoints, max_features, 1 if keep_patches else 0)
+
+
+def library_path():
+    return os.path.join(_HERE, "lib3dsift_b200.so")
+
+
+def build_library(verbose=False):
+    """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "all"], check=True, stdout=out)
+    return library_path()
+
+
+def load_library():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise S3DError("%s is missing: build it with __graft_entry__.build() "
+                       "(make -C 3d_sift_cuda_b200/csrc); there is no CPU fallback" % path)
+    L = C.CDLL(path)
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    L.s3d_ctx_create.argtypes = [i, C.POINTER(vp)]
+    L.s3d_ctx_create_on_stream.argtypes = [i, vp, C.POINTER(vp)]
+    L.s3d_ctx_destroy.argtypes = [vp]
+    L.s3d_ctx_destroy.restype = None
+    L.s3d_last_error.argtypes = [vp]
+    L.s3d_last_error.restype = C.c_char_p
+    L.s3d_sync.argtypes = [vp]
+    L.s3d_stream.argtypes = [vp]
+    L.s3d_stream.restype = vp
+    L.s3d_gaussian_taps.argtypes = [f, vp, i]
+    L.s3d_blur3d.argtypes = [vp, vp, vp, vp, i, i, i, i, vp, i, vp]
+    L.s3d_dog.argtypes = [vp, vp, vp, vp, i, i, i, i]
+    for fn in (L.s3d_subsample2, L.s3d_double_size, L.s3d_halve_size):
+        fn.argtypes = [vp, vp, i, i, i, i, vp, i]
+    L.s3d_detect.argtypes = [vp, vp, vp, i, i, i, i, vp, vp, vp, vp, i]
+    L.s3d_extract.argtypes = [vp, vp, i, i, i, vp, C.POINTER(vp), C.POINTER(i)]
+    L.s3d_extract_device.argtypes = [vp, vp, i, i, i, vp]
+    L.s3d_extract_host_async.argtypes = [vp, vp, i, i, i, vp]
+    L.s3d_fetch_features.argtypes = [vp, C.POINTER(vp), C.POINTER(i)]
+    L.s3d_fetch_counts.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
+    L.s3d_result_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.s3d_free.argtypes = [vp]
+    L.s3d_free.restype = None
+    L.s3d_num_octaves.argtypes = [vp]
+    L.s3d_get_level.argtypes = [vp, i, i, i, vp, C.POINTER(i * 3)]
+    L.s3d_get_keypoints.argtypes = [vp, C.POINTER(vp), C.POINTER(i)]
+    L.s3d_get_patches.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i)]
+    L.s3d_last_launch_count.argtypes = [vp]
+    L.s3d_write_features_text.argtypes = [C.c_char_p, vp, i, f, i, C.POINTER(C.c_char_p)]
+    _LIB = L
+    return L
+
+
+def gaussian_taps(sigma):
+    """Normalised taps for one blur (host arithmetic, GaussianMask.cpp:12-57, 241-265)."""
+    L = load_library()
+    buf = np.zeros(129, np.float32)
+    n = L.s3d_gaussian_taps(sigma, buf.ctypes.data_as(C.c_void_p), 129)
+    if n <= 0:
+        raise S3DError("sigma %g needs %d taps" % (sigma, -n))
+    return buf[:n].copy()
+
+
+def _copy_out(ptr, count, dtype, free):
+    if not ptr or count == 0:
+        if ptr:
+            free(ptr)
+        return np.zeros(0, dtype)
+    nbytes = count * np.dtype(dtype).itemsize
+    out = np.frombuffer(C.string_at(ptr, nbytes), dtype=dtype).copy()
+    free(ptr)
+    return out
+
+
+def _dptr(t):
+    """Device pointer of a torch CUDA tensor (float32 / int32, contiguous)."""
+    assert t.is_cuda and t.is_contiguous()
+    return C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """One GPU's extraction context (reference: FEATUREIO.device / -dN)."""
+
+    def __init__(self, device=0, stream=None):
+        self.L = load_library()
+        self.ctx = C.c_void_p()
+        if stream is None:
+            st = self.L.s3d_ctx_create(device, C.byref(self.ctx))
+        else:
+            st = self.L.s3d_ctx_create_on_stream(device, C.c_void_p(stream), C.byref(self.ctx))
+        if st != 0:
+            msg = self.L.s3d_last_error(self.ctx).decode() if self.ctx else "no usable CUDA device"
+            if self.ctx:
+                self.L.s3d_ctx_destroy(self.ctx)
+                self.ctx = C.c_void_p()
+            raise S3DError("s3d_ctx_create(%d): %s (%s)" % (device, _STATUS.get(st, st), msg))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.s3d_ctx_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st, what):
+        if st != 0:
+            raise S3DError("%s: %s (%s)" % (what, _STATUS.get(st, st), self.L.s3d_last_error(self.ctx).decode()))
+
+    @property
+    def stream(self):
+        return self.L.s3d_stream(self.ctx)
+
+    def sync(self):
+        self._ck(self.L.s3d_sync(self.ctx), "s3d_sync")
+
+    # ---- pipeline level ----------------------------------------------------------------------------
+    def extract(self, volume, params=None):
+        """Host volume (numpy (Z, Y, X) float32) -> structured array of feature rows."""
+        params = params or Params()
+        v = np.ascontiguousarray(volume, dtype=np.float32)
+        Z, Y, X = v.shape
+        out, n = C.c_void_p(), C.c_int()
+        self._ck(self.L.s3d_extract(self.ctx, v.ctypes.data_as(C.c_void_p), X, Y, Z, C.byref(params.c),
+                                    C.byref(out), C.byref(n)), "s3d_extract")
+        return _copy_out(out, n.value, FEATURE_DTYPE, self.L.s3d_free)
+
+    def extract_device(self, d_volume, shape_xyz, params=None):
+        """Dense device volume (torch tensor or raw pointer); enqueues only."""
+        params = params or Params()
+        self._last_params = params
+        X, Y, Z = shape_xyz
+        p = _dptr(d_volume) if hasattr(d_volume, "data_ptr") else C.c_void_p(d_volume)
+        self._ck(self.L.s3d_extract_device(self.ctx, p, X, Y, Z, C.byref(params.c)), "s3d_extract_device")
+
+    def extract_host_async(self, h_volume, params=None):
+        """Host volume (numpy array or pinned torch tensor, (Z, Y, X) float32); enqueues H2D + the path."""
+        params = params or Params()
+        self._last_params = params
+        if hasattr(h_volume, "data_ptr"):
+            Z, Y, X = h_volume.shape
+            p = C.c_void_p(h_volume.data_ptr())
+        else:
+            assert h_volume.dtype == np.float32 and h_volume.flags["C_CONTIGUOUS"]
+            Z, Y, X = h_volume.shape
+            p = h_volume.ctypes.data_as(C.c_void_p)
+        self._ck(self.L.s3d_extract_host_async(self.ctx, p, X, Y, Z, C.byref(params.c)), "s3d_extract_host_async")
+
+    def fetch_features(self):
+        out, n = C.c_void_p(), C.c_int()
+        self._ck(self.L.s3d_fetch_features(self.ctx, C.byref(out), C.byref(n)), "s3d_fetch_features")
+        return _copy_out(out, n.value, FEATURE_DTYPE, self.L.s3d_free)
+
+    def fetch_counts(self):
+        nk, nf = C.c_int(), C.c_int()
+        self._ck(self.L.s3d_fetch_counts(self.ctx, C.byref(nk), C.byref(nf)), "s3d_fetch_counts")
+        return nk.value, nf.value
+
+    def num_octaves(self):
+        return self.L.s3d_num_octaves(self.ctx)
+
+    def level(self, octave, level, dog=False):
+        dims = (C.c_int * 3)()
+        self._ck(self.L.s3d_get_level(self.ctx, octave, 1 if dog else 0, level, None, C.byref(dims)), "s3d_get_level")
+        X, Y, Z = dims[0], dims[1], dims[2]
+        out = np.empty((Z, Y, X), np.float32)
+        self._ck(self.L.s3d_get_level(self.ctx, octave, 1 if dog else 0, level, out.ctypes.data_as(C.c_void_p),
+                                      C.byref(dims)), "s3d_get_level")
+        return out
+
+    def keypoints(self):
+        out, n = C.c_void_p(), C.c_int()
+        self._ck(self.L.s3d_get_keypoints(self.ctx, C.byref(out), C.byref(n)), "s3d_get_keypoints")
+        return _copy_out(out, n.value, KEYPOINT_DTYPE, self.L.s3d_free)
+
+    def patches(self):
+        pa, pr, n = C.c_void_p(), C.c_void_p(), C.c_int()
+        self._ck(self.L.s3d_get_patches(self.ctx, C.byref(pa), C.byref(pr), C.byref(n)), "s3d_get_patches")
+        nn = n.value
+        a = _copy_out(pa, nn * 1331, np.float32, self.L.s3d_free).reshape(nn, 11, 11, 11)
+        b = _copy_out(pr, nn * 64, np.float32, self.L.s3d_free).reshape(nn, 64)
+        return a, b
+
+    def launch_count(self):
+        return self.L.s3d_last_launch_count(self.ctx)
+
+    # ---- stage level (torch CUDA tensors shaped (Z, Y, pitch), float32) ------------------------------
+    def blur3d(self, d_in, d_tmp, d_out, X, taps, d_dog=None):
+        Z, Y, pitch = d_in.shape
+        t = np.ascontiguousarray(taps, np.float32)
+        self._ck(self.L.s3d_blur3d(self.ctx, _dptr(d_in), _dptr(d_tmp), _dptr(d_out), X, Y, Z, pitch,
+                                   t.ctypes.data_as(C.c_void_p), len(t), _dptr(d_dog) if d_dog is not None else None),
+                 "s3d_blur3d")
+
+    def dog(self, d_a, d_b, d_out, X):
+        Z, Y, pitch = d_a.shape
+        self._ck(self.L.s3d_dog(self.ctx, _dptr(d_a), _dptr(d_b), _dptr(d_out), X, Y, Z, pitch), "s3d_dog")
+
+    def _resize(self, fn, name, d_in, X, d_out):
+        Z, Y, pitch = d_in.shape
+        self._ck(fn(self.ctx, _dptr(d_in), X, Y, Z, pitch, _dptr(d_out), d_out.shape[2]), name)
+
+    def subsample2(self, d_in, X, d_out):
+        self._resize(self.L.s3d_subsample2, "s3d_subsample2", d_in, X, d_out)
+
+    def double_size(self, d_in, X, d_out):
+        self._resize(self.L.s3d_double_size, "s3d_double_size", d_in, X, d_out)
+
+    def halve_size(self, d_in, X, d_out):
+        self._resize(self.L.s3d_halve_size, "s3d_halve_size", d_in, X, d_out)
+
+    def detect(self, d_finer, d_centre, X, cap=1 << 16):
+        """Returns (minima, maxima) as CAND_DTYPE arrays in raster order."""
+        import torch
+        Z, Y, pitch = d_centre.shape
+        dev = d_centre.device
+        mins = torch.zeros(cap * 4, dtype=torch.int32, device=dev)
+        maxs = torch.zeros(cap * 4, dtype=torch.int32, device=dev)
+        cnt = torch.zeros(2, dtype=torch.int32, device=dev)
+        self._ck(self.L.s3d_detect(self.ctx, _dptr(d_finer), _dptr(d_centre), X, Y, Z, pitch,
+                                   _dptr(mins), C.c_void_p(cnt.data_ptr()), _dptr(maxs), C.c_void_p(cnt.data_ptr() + 4), cap),
+                 "s3d_detect")
+        self.sync()
+        n = cnt.cpu().numpy()
+        if n[0] > cap or n[1] > cap:
+            raise S3DError("s3d_detect: %d/%d candidates exceed cap %d" % (n[0], n[1], cap))
+        a = mins.cpu().numpy().view(CAND_DTYPE)[:n[0]].copy()
+        b = maxs.cpu().numpy().view(CAND_DTYPE)[:n[1]].copy()
+        return a, b
+
+
+def write_features_text(path, feats, shape_xyz, eig_thres=140.0, comments=None):
+    """The reference's text feature file (MultiScale.h:386-474, featExtract.cpp:542-575)."""
+    L = load_library()
+    f = np.ascontiguousarray(feats, dtype=FEATURE_DTYPE)
+    if comments is None:
+        comments = [
+            "Extraction Voxel Resolution (ijk) : %d %d %d" % tuple(shape_xyz),
+            "Extraction Voxel Size (mm)  (ijk) : %f %f %f" % (1.0, 1.0, 1.0),
+            "Feature Coordinate Space: voxels: 1.0 0.0 0.0 0.0 0.0 1.0 0.0 0.0 0.0 0.0 1.0 0.0 0.0 0.0 0.0 1.0",
+        ]
+    arr = (C.c_char_p * len(comments))(*[c.encode() for c in comments])
+    st = L.s3d_write_features_text(path.encode(), f.ctypes.data_as(C.c_void_p), len(f), eig_thres, len(comments), arr)
+    if st != 0:
+        raise S3DError("s3d_write_features_text(%s): %s" % (path, _STATUS.get(st, st)))

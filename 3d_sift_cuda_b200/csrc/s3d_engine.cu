@@ -1,0 +1,867 @@
+// s3d_engine.cu -- context, pyramid plan, stream/graph orchestration and the C-ABI of include/s3d.h.
+//
+// One context = one device + one stream + one resident pyramid plan.  The whole extraction (pre-step,
+// pyramid, DoG, detection, refinement, orientation, descriptors) is enqueued on the stream without any
+// host round trip -- every data-dependent count (candidates, keypoints, feature rows) stays in device
+// memory and the kernels size their own work from it -- and is replayed as one CUDA graph per
+// (shape, options).  The reference instead crosses PCIe ~17 times per octave with blocking
+// cudaMemcpy.  There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/s3d.h"
+#include "s3d_voxel.cuh"
+#include "s3d_keypoint.cuh"
+
+using namespace s3d;
+
+// ---------------------------------------------------------------------------------------------------
+// host-side parameter arithmetic (kept on the host, as in the reference)
+// ---------------------------------------------------------------------------------------------------
+
+// calculate_gaussian_filter_size (reference GaussianMask.cpp:12-57).  The reference is C++: exp() on a
+// float argument is the float overload, i.e. expf.
+static int filter_size(float fSigma, float fMinValue)
+{
+    float fPower = 0.0f;
+    float fValue = expf(fPower);
+    float fCurVolume = 1, fNewVolume = 1;
+    int i = 0;
+    if (fSigma == 0) return 1;
+    do {
+        i++;
+        fCurVolume = fNewVolume;
+        fPower = ((float)(i * i)) / ((float)-2.0 * fSigma * fSigma);
+        fNewVolume = fCurVolume + 2 * expf(fPower);
+    } while (fNewVolume - fCurVolume > 0.00001f);
+    for (i = 1; fValue <= fCurVolume * (1.0f - fMinValue); i++) {
+        fPower = ((float)(i * i)) / ((float)-2.0 * fSigma * fSigma);
+        fValue += 2 * expf(fPower);
+    }
+    i--;
+    return 2 * i + 1;
+}
+
+extern "C" int s3d_gaussian_taps(float sigma, float *taps, int cap)
+{
+    const double PI_ = 3.1415926535897932384626433832795;
+    int n = filter_size(sigma, 0.01f);
+    if (n > cap) return -n;
+    if (sigma > 0.0f) {
+        float fMeanCol = (float)(n / 2);
+        float fSigmaColSqr = sigma * sigma;
+        float fScale = (float)(1.0 / (sigma * sqrt(2.0 * PI_)));
+        for (int j = 0; j < n; j++) {
+            float fColPos = ((float)j - fMeanCol);
+            float fPower = ((fColPos * fColPos) / fSigmaColSqr) / (float)(-2.0f);
+            taps[j] = fScale * expf(fPower);
+        }
+    } else {
+        taps[0] = 1;
+    }
+    float fSum = 0;
+    for (int c = 0; c < n; c++) fSum += taps[c];
+    for (int c = 0; c < n; c++) taps[c] /= fSum;
+    return n;
+}
+
+// BRIEF pair table, method 2 (reference MultiScale.cpp:805-807), x,y,z triples.
+static const unsigned char kBriefA[192] = { 5,4,4,4,4,2,6,5,5,4,4,4,3,8,5,5,6,3,5,5,5,5,6,5,4,6,6,6,3,4,4,4,5,3,4,5,4,5,5,4,2,7,7,5,3,5,4,5,3,5,7,3,5,5,2,3,5,5,6,6,4,6,5,4,4,6,5,3,5,6,4,3,6,4,4,5,3,3,3,6,6,5,2,4,4,6,3,6,3,2,3,5,4,5,3,4,3,6,5,4,3,6,4,5,2,4,3,7,2,3,6,5,2,6,3,3,5,6,3,6,3,5,3,6,5,7,4,2,5,5,5,2,5,7,4,2,5,3,4,3,3,7,4,4,7,6,4,4,2,8,7,6,5,4,7,3,6,6,5,2,4,5,3,2,5,5,1,6,3,6,3,6,2,5,4,4,7,2,6,3,2,2,4,3,3,2,3,4,2,5,6,7 };
+static const unsigned char kBriefB[192] = { 6,5,3,4,5,3,7,4,6,4,3,2,4,7,5,3,5,1,5,4,7,6,8,4,4,5,6,5,2,5,4,6,4,0,4,3,3,4,4,2,1,7,8,6,4,4,1,6,1,3,7,2,3,3,1,3,6,1,6,6,4,7,6,4,3,5,4,2,3,6,4,5,6,3,3,5,1,3,1,6,7,4,1,4,3,5,2,4,2,1,2,5,4,5,2,3,3,3,3,4,2,6,3,4,3,3,3,6,1,2,5,4,2,4,1,4,6,7,3,6,2,4,3,6,5,6,4,0,6,6,5,1,4,7,2,1,5,3,4,2,2,7,3,3,6,4,2,4,1,9,7,7,5,2,7,1,7,5,5,1,5,4,1,3,3,4,0,5,1,6,3,5,3,2,3,3,7,2,5,1,1,0,4,1,3,1,0,3,1,6,5,9 };
+
+static void build_tables(KpTables &t)
+{
+    memset(&t, 0, sizeof(t));
+    // sphere voxels in raster order (reference MultiScale.cpp:2575-2583)
+    float fRadiusSqr = (float)((PD / 2) * (PD / 2));
+    int n = 0;
+    for (int z = 0; z < PD; z++)
+        for (int y = 0; y < PD; y++)
+            for (int x = 0; x < PD; x++) {
+                float dz = (float)(z - PD / 2), dy = (float)(y - PD / 2), dx = (float)(x - PD / 2);
+                if (dz * dz + dy * dy + dx * dx < fRadiusSqr) t.sphere[n++] = (unsigned short)((z * PD + y) * PD + x);
+            }
+    t.n_sphere = n;
+    t.n_hist_taps = s3d_gaussian_taps(0.5f, t.hist_taps, 9);    // fBlurGradOriHist
+    t.n_brief_taps = s3d_gaussian_taps(0.95f, t.brief_taps, 9); // gb3d_blur3d(..., 0.95, 0.01, ...)
+    // spatial-bin coordinate of each patch index (reference MultiScale.cpp:627-660) and its lower-bin
+    // weight (_fioDetermineInterpCoord with dim 2, reference FeatureIO.cpp:757-782)
+    float fBinSize = PD / (float)2;
+    for (int q = 0; q < PD; q++) {
+        float c = (int)(q / fBinSize) + 0.5f;
+        if ((int)((q + 0) / fBinSize) != (int)((q + 1) / fBinSize)) {
+            float fP0 = ((q + 0) / fBinSize);
+            float fP1 = ((q + 1) / fBinSize);
+            c = (fP0 + fP1) / 2.0f;
+        }
+        float w;
+        if (c < 0.5f) w = 1.0f;
+        else if (c >= 2.0f - 0.5f) w = 0.0f;
+        else { float mh = c - 0.5f; int i = (int)floorf(mh); w = 1.0f - (mh - (float)i); }
+        t.desc_w[q] = w;
+    }
+    for (int i = 0; i < 64; i++) {
+        int ax = kBriefA[3 * i], ay = kBriefA[3 * i + 1], az = kBriefA[3 * i + 2];
+        int bx = kBriefB[3 * i], by = kBriefB[3 * i + 1], bz = kBriefB[3 * i + 2];
+        t.brief_a[i] = (unsigned short)(ax + ay * PD + az * PD * PD);
+        t.brief_b[i] = (unsigned short)(bx + by * PD + bz * PD * PD);
+        float fdx = (float)(ax - bx), fdy = (float)(ay - by), fdz = (float)(az - bz);
+        t.brief_dist[i] = (float)(int)sqrtf(fdx * fdx + fdy * fdy + fdz * fdz);   // euclidean_distance_3d :1051-1056
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+struct Vol {
+    float *p = nullptr;
+    int X = 0, Y = 0, Z = 0, pitch = 0;
+    size_t elems() const { return (size_t)pitch * Y * Z; }
+};
+
+struct Plan {
+    int X = 0, Y = 0, Z = 0, double_mode = 0;      // input dims and pre-step
+    int kp_cap = 0, row_cap = 0, cand_cap = 0, keep_patches = 0;
+    int n_oct = 0;
+    Vol stage;                   // dense copy of the input (pitch == X)
+    Vol img0;                    // pre-stepped, pitched input of the pyramid
+    std::vector<Vol> g, d;       // [oct*6 + level], [oct*5 + level]
+    float *tmp1 = nullptr, *tmp2 = nullptr;
+    s3d_cand *cand_raw = nullptr, *cand_sorted = nullptr;   // [list][cand_cap], list = (oct*3 + (c-1))*2 + is_max
+    int *counts = nullptr;       // [n_lists] candidate counts, then kp_count, n_features, err
+    int n_lists = 0;
+    s3d_keypoint *kps = nullptr;
+    int *nrows = nullptr, *row_off = nullptr;
+    float *kp_eigs = nullptr, *kp_ori0 = nullptr, *kp_rots = nullptr, *kp_patch0 = nullptr;
+    s3d_feature *feats = nullptr;
+    float *dbg_patches = nullptr, *dbg_prerank = nullptr;
+    PyramidDesc pyr;
+    float init_taps[kMaxTaps]; int n_init_taps = 0;
+    float lvl_taps[5][kMaxTaps]; int n_lvl_taps[5];
+    cudaGraphExec_t graph = nullptr;
+    int graph_descriptor = -1; float graph_eig = 0;
+    std::vector<void *> allocs;
+};
+
+struct s3d_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    Plan *plan = nullptr;
+    int launches = 0;
+    int last_launches = 0;
+    bool use_graph = true;
+    int sm_count = 148;
+    int march_target = 0;
+    bool has_result = false;
+    int *h_counts = nullptr;     // pinned: kp_count, n_features, err
+};
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            char b_[512];                                                                            \
+            snprintf(b_, sizeof(b_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            ctx->err = b_;                                                                           \
+            return S3D_ERR_CUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+static s3d_status fail(s3d_ctx *ctx, s3d_status st, const char *msg)
+{
+    if (ctx) ctx->err = msg;
+    return st;
+}
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+extern "C" int s3d_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **out)
+{
+    if (!out) return S3D_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        fprintf(stderr, "s3d: no usable CUDA device (%s); this engine has no CPU fallback\n",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return S3D_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) return S3D_ERR_INVALID;
+    s3d_ctx *ctx = new s3d_ctx();
+    ctx->device = device;
+    *out = ctx;   // handed back even on failure so the caller can read the error text
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    if (borrow) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    KpTables t;
+    build_tables(t);
+    CK(cudaMemcpyToSymbol(c_tab, &t, sizeof(t)));
+    CK(cudaFuncSetAttribute(orient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrientSmem)));
+    CK(cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DescribeSmem)));
+    CK(cudaMallocHost((void **)&ctx->h_counts, 4 * sizeof(int)));
+    const char *g = getenv("S3D_NO_GRAPH");
+    if (g && g[0] == '1') ctx->use_graph = false;
+    const char *mt = getenv("S3D_MARCH_TARGET");
+    ctx->march_target = mt ? atoi(mt) : 0;
+    return S3D_OK;
+}
+
+extern "C" s3d_status s3d_ctx_create(int device, s3d_ctx **ctx) { return ctx_create(device, nullptr, false, ctx); }
+extern "C" s3d_status s3d_ctx_create_on_stream(int device, void *stream, s3d_ctx **ctx) { return ctx_create(device, stream, true, ctx); }
+
+static void plan_free(s3d_ctx *ctx)
+{
+    Plan *p = ctx->plan;
+    if (!p) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (p->graph) cudaGraphExecDestroy(p->graph);
+    for (void *a : p->allocs) cudaFree(a);
+    delete p;
+    ctx->plan = nullptr;
+    ctx->has_result = false;
+}
+
+extern "C" void s3d_ctx_destroy(s3d_ctx *ctx)
+{
+    if (!ctx) return;
+    plan_free(ctx);
+    if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *s3d_last_error(const s3d_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" void *s3d_stream(s3d_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" s3d_status s3d_sync(s3d_ctx *ctx)
+{
+    if (!ctx) return S3D_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return S3D_OK;
+}
+extern "C" void s3d_free(void *p) { free(p); }
+extern "C" int s3d_last_launch_count(s3d_ctx *ctx) { return ctx ? ctx->last_launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------
+// stage launchers
+// ---------------------------------------------------------------------------------------------------
+static bool fast_layout(const void *a, const void *b, const void *c, int pitch)
+{
+    return pitch % 8 == 0 && ((uintptr_t)a % 32) == 0 && ((uintptr_t)b % 32) == 0 && ((uintptr_t)c % 32) == 0;
+}
+
+// Split the blur axis into segments so that about `target` threads are in flight; each segment
+// re-reads 2R halo inputs, so segments are kept >= 16 long.
+static void march_segments(int target, long long cols, int len, int &seg_len, int &n_seg)
+{
+    n_seg = (int)((target + cols - 1) / cols);
+    if (n_seg < 1) n_seg = 1;
+    int max_seg = (len + 15) / 16;
+    if (n_seg > max_seg) n_seg = max_seg;
+    seg_len = (len + n_seg - 1) / n_seg;
+    n_seg = (len + seg_len - 1) / seg_len;
+}
+
+template <int R>
+static void launch_blur_fast(s3d_ctx *ctx, const float *in, float *tmp, float *out, int X, int Y, int Z, int pitch,
+                             const float *taps, float *dog)
+{
+    TapsSmall t;
+    memset(&t, 0, sizeof(t));
+    for (int j = 0; j < 2 * R + 1; j++) t.w[j] = taps[j];
+    long long plane = (long long)pitch * Y;
+    long long n_chunks = plane * Z / 8;
+    // x: in -> out
+    blur_x_kernel<R><<<(unsigned)((n_chunks + 255) / 256), 256, 0, ctx->stream>>>(in, out, pitch, X, n_chunks, t);
+    // y: out -> tmp
+    int target = ctx->march_target > 0 ? ctx->march_target : ctx->sm_count * 1024;
+    {
+        long long cols = (long long)pitch * Z;
+        int seg_len, n_seg;
+        march_segments(target, cols, Y, seg_len, n_seg);
+        dim3 grid((unsigned)((cols + 127) / 128), (unsigned)n_seg);
+        blur_march_kernel<R, false><<<grid, 128, 0, ctx->stream>>>(out, tmp, nullptr, nullptr, cols, pitch, plane, pitch, Y, seg_len, t);
+    }
+    // z: tmp -> out (+ DoG)
+    {
+        long long cols = plane;
+        int seg_len, n_seg;
+        march_segments(target, cols, Z, seg_len, n_seg);
+        dim3 grid((unsigned)((cols + 127) / 128), (unsigned)n_seg);
+        if (dog) blur_march_kernel<R, true><<<grid, 128, 0, ctx->stream>>>(tmp, out, in, dog, cols, plane, 0, plane, Z, seg_len, t);
+        else blur_march_kernel<R, false><<<grid, 128, 0, ctx->stream>>>(tmp, out, nullptr, nullptr, cols, plane, 0, plane, Z, seg_len, t);
+    }
+    ctx->launches += 3;
+}
+
+static void launch_blur_generic(s3d_ctx *ctx, const float *in, float *tmp, float *out, int X, int Y, int Z, int pitch,
+                                const float *taps, int ntaps, float *dog)
+{
+    TapsAny t;
+    memset(&t, 0, sizeof(t));
+    t.n = ntaps;
+    for (int j = 0; j < ntaps; j++) t.w[j] = taps[j];
+    long long plane = (long long)pitch * Y;
+    long long n = plane * Z;
+    blur_x_generic_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(in, out, pitch, X, n, t);
+    {
+        long long cols = (long long)pitch * Z;
+        dim3 grid((unsigned)((cols + 127) / 128), (unsigned)(Y < 32 ? Y : 32));
+        blur_march_generic_kernel<false><<<grid, 128, 0, ctx->stream>>>(out, tmp, nullptr, nullptr, cols, pitch, plane, pitch, Y, t);
+    }
+    {
+        dim3 grid((unsigned)((plane + 127) / 128), (unsigned)(Z < 32 ? Z : 32));
+        if (dog) blur_march_generic_kernel<true><<<grid, 128, 0, ctx->stream>>>(tmp, out, in, dog, plane, plane, 0, plane, Z, t);
+        else blur_march_generic_kernel<false><<<grid, 128, 0, ctx->stream>>>(tmp, out, nullptr, nullptr, plane, plane, 0, plane, Z, t);
+    }
+    ctx->launches += 3;
+}
+
+static s3d_status blur3d(s3d_ctx *ctx, const float *in, float *tmp, float *out, int X, int Y, int Z, int pitch,
+                         const float *taps, int ntaps, float *dog)
+{
+    if (!in || !tmp || !out || !taps || X <= 0 || Y <= 0 || Z <= 0 || pitch < X || ntaps < 1 || (ntaps & 1) == 0 || ntaps > kMaxTaps)
+        return fail(ctx, S3D_ERR_INVALID, "s3d_blur3d: bad argument");
+    if (in == out || in == tmp || tmp == out) return fail(ctx, S3D_ERR_INVALID, "s3d_blur3d: in/tmp/out must be distinct");
+    int R = ntaps / 2;
+    bool fast = fast_layout(in, tmp, out, pitch) && (!dog || ((uintptr_t)dog % 32) == 0) && R >= 1 && R <= kMaxFastR;
+    if (fast) {
+        switch (R) {
+        case 1: launch_blur_fast<1>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog); break;
+        case 2: launch_blur_fast<2>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog); break;
+        case 3: launch_blur_fast<3>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog); break;
+        case 4: launch_blur_fast<4>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog); break;
+        case 5: launch_blur_fast<5>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog); break;
+        case 6: launch_blur_fast<6>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog); break;
+        case 7: launch_blur_fast<7>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog); break;
+        default: launch_blur_fast<8>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog); break;
+        }
+    } else {
+        launch_blur_generic(ctx, in, tmp, out, X, Y, Z, pitch, taps, ntaps, dog);
+    }
+    CK(cudaGetLastError());
+    return S3D_OK;
+}
+
+extern "C" s3d_status s3d_blur3d(s3d_ctx *ctx, const float *d_in, float *d_tmp, float *d_out,
+                                 int X, int Y, int Z, int pitch, const float *h_taps, int ntaps, float *d_dog)
+{
+    if (!ctx) return S3D_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    return blur3d(ctx, d_in, d_tmp, d_out, X, Y, Z, pitch, h_taps, ntaps, d_dog);
+}
+
+extern "C" s3d_status s3d_dog(s3d_ctx *ctx, const float *d_a, const float *d_b, float *d_out, int X, int Y, int Z, int pitch)
+{
+    if (!ctx) return S3D_ERR_INVALID;
+    if (!d_a || !d_b || !d_out || X <= 0 || Y <= 0 || Z <= 0 || pitch < X) return fail(ctx, S3D_ERR_INVALID, "s3d_dog: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    long long n = (long long)pitch * Y * Z;
+    dog_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_a, d_b, d_out, n);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return S3D_OK;
+}
+
+static s3d_status resize_launch(s3d_ctx *ctx, int kind, const float *in, int X, int Y, int Z, int pitch, float *out, int opitch)
+{
+    if (!in || !out || X <= 1 || Y <= 1 || Z <= 1 || pitch < X) return fail(ctx, S3D_ERR_INVALID, "resize: bad argument");
+    int ox = kind == 2 ? 2 * X : X / 2, oy = kind == 2 ? 2 * Y : Y / 2, oz = kind == 2 ? 2 * Z : Z / 2;
+    if (ox < 1 || oy < 1 || oz < 1 || opitch < ox) return fail(ctx, S3D_ERR_INVALID, "resize: bad output shape");
+    dim3 block(32, 8), grid((opitch + 31) / 32, (oy + 7) / 8, oz);
+    if (kind == 0) subsample_kernel<<<grid, block, 0, ctx->stream>>>(in, X, Y, Z, pitch, out, ox, oy, oz, opitch);
+    else if (kind == 1) halve_kernel<<<grid, block, 0, ctx->stream>>>(in, X, Y, Z, pitch, out, ox, oy, oz, opitch);
+    else double_kernel<<<grid, block, 0, ctx->stream>>>(in, X, Y, Z, pitch, out, opitch);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return S3D_OK;
+}
+
+extern "C" s3d_status s3d_subsample2(s3d_ctx *ctx, const float *d_in, int X, int Y, int Z, int pitch, float *d_out, int out_pitch)
+{
+    if (!ctx) return S3D_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    return resize_launch(ctx, 0, d_in, X, Y, Z, pitch, d_out, out_pitch);
+}
+extern "C" s3d_status s3d_halve_size(s3d_ctx *ctx, const float *d_in, int X, int Y, int Z, int pitch, float *d_out, int out_pitch)
+{
+    if (!ctx) return S3D_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    return resize_launch(ctx, 1, d_in, X, Y, Z, pitch, d_out, out_pitch);
+}
+extern "C" s3d_status s3d_double_size(s3d_ctx *ctx, const float *d_in, int X, int Y, int Z, int pitch, float *d_out, int out_pitch)
+{
+    if (!ctx) return S3D_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    return resize_launch(ctx, 2, d_in, X, Y, Z, pitch, d_out, out_pitch);
+}
+
+// detection + ordering; raw lists are scratch owned by the caller (engine) or allocated here (stage API)
+static s3d_status detect_launch(s3d_ctx *ctx, const float *finer, const float *centre, int X, int Y, int Z, int pitch,
+                                s3d_cand *raw_min, s3d_cand *raw_max, s3d_cand *out_min, int *n_min,
+                                s3d_cand *out_max, int *n_max, int cap)
+{
+    if (X < 3 || Y < 3 || Z < 3) return S3D_OK;   // no interior voxel
+    dim3 block(32, 8), grid((X - 2 + 31) / 32, (Y - 2 + 7) / 8, Z - 2);
+    CandList lmin{ raw_min, n_min }, lmax{ raw_max, n_max };
+    detect_kernel<<<grid, block, 0, ctx->stream>>>(finer, centre, X, Y, Z, pitch, lmin, lmax, cap);
+    int blocks = (cap + 255) / 256;
+    order_candidates_kernel<<<blocks, 256, 0, ctx->stream>>>(raw_min, n_min, out_min, X, Y, cap);
+    order_candidates_kernel<<<blocks, 256, 0, ctx->stream>>>(raw_max, n_max, out_max, X, Y, cap);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    return S3D_OK;
+}
+
+extern "C" s3d_status s3d_detect(s3d_ctx *ctx, const float *d_finer, const float *d_centre, int X, int Y, int Z, int pitch,
+                                 s3d_cand *d_min, int *d_n_min, s3d_cand *d_max, int *d_n_max, int cap)
+{
+    if (!ctx) return S3D_ERR_INVALID;
+    if (!d_finer || !d_centre || !d_min || !d_max || !d_n_min || !d_n_max || cap <= 0 || pitch < X)
+        return fail(ctx, S3D_ERR_INVALID, "s3d_detect: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    s3d_cand *raw = nullptr;
+    CK(cudaMallocAsync((void **)&raw, sizeof(s3d_cand) * 2 * (size_t)cap, ctx->stream));
+    CK(cudaMemsetAsync(d_n_min, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(d_n_max, 0, sizeof(int), ctx->stream));
+    s3d_status st = detect_launch(ctx, d_finer, d_centre, X, Y, Z, pitch, raw, raw + cap, d_min, d_n_min, d_max, d_n_max, cap);
+    CK(cudaFreeAsync(raw, ctx->stream));
+    return st;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// plan: every buffer of the pyramid for one input shape
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t plan_alloc(Plan *p, T **ptr, size_t count)
+{
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+    if (e != cudaSuccess) return e;
+    p->allocs.push_back(q);
+    *ptr = (T *)q;
+    return cudaSuccess;
+}
+
+static s3d_status plan_build(s3d_ctx *ctx, int X, int Y, int Z, const s3d_params *prm)
+{
+    int kp_cap = prm->max_keypoints > 0 ? prm->max_keypoints : 16384;
+    int row_cap = prm->max_features > 0 ? prm->max_features : 8 * kp_cap;
+    Plan *old = ctx->plan;
+    if (old && old->X == X && old->Y == Y && old->Z == Z && old->double_mode == prm->double_mode &&
+        old->kp_cap == kp_cap && old->row_cap == row_cap && old->keep_patches == (prm->keep_patches ? 1 : 0))
+        return S3D_OK;
+    plan_free(ctx);
+    Plan *p = new Plan();
+    ctx->plan = p;
+    p->X = X; p->Y = Y; p->Z = Z; p->double_mode = prm->double_mode;
+    p->kp_cap = kp_cap; p->row_cap = row_cap; p->keep_patches = prm->keep_patches ? 1 : 0;
+
+    int X0 = X, Y0 = Y, Z0 = Z;
+    if (prm->double_mode == 1) { X0 *= 2; Y0 *= 2; Z0 *= 2; }
+    else if (prm->double_mode == -1) { X0 /= 2; Y0 /= 2; Z0 /= 2; }
+    if (X0 < 1 || Y0 < 1 || Z0 < 1) return fail(ctx, S3D_ERR_INVALID, "volume too small");
+
+    cudaError_t e;
+#define PA(ptr, count)                                                          \
+    do {                                                                        \
+        e = plan_alloc(p, ptr, (size_t)(count));                                \
+        if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e); cudaGetLastError(); return S3D_ERR_NOMEM; } \
+    } while (0)
+
+    p->stage.X = X; p->stage.Y = Y; p->stage.Z = Z; p->stage.pitch = X;
+    PA(&p->stage.p, p->stage.elems());
+    p->img0.X = X0; p->img0.Y = Y0; p->img0.Z = Z0; p->img0.pitch = round_up(X0, 8);
+    PA(&p->img0.p, p->img0.elems());
+    PA(&p->tmp1, p->img0.elems());
+
+    // octaves (reference MultiScale.cpp:359: stop when any dimension <= 2)
+    int ox = X0, oy = Y0, oz = Z0, n_oct = 0;
+    memset(&p->pyr, 0, sizeof(p->pyr));
+    while (!(ox <= 2 || oy <= 2 || oz <= 2) && n_oct < kMaxOct) {
+        OctaveDesc &od = p->pyr.oct[n_oct];
+        od.X = ox; od.Y = oy; od.Z = oz; od.pitch = round_up(ox, 8);
+        for (int j = 0; j < 6; j++) {
+            Vol v; v.X = ox; v.Y = oy; v.Z = oz; v.pitch = od.pitch;
+            PA(&v.p, v.elems());
+            p->g.push_back(v);
+            od.g[j] = v.p;
+        }
+        for (int j = 0; j < 5; j++) {
+            Vol v; v.X = ox; v.Y = oy; v.Z = oz; v.pitch = od.pitch;
+            PA(&v.p, v.elems());
+            p->d.push_back(v);
+            od.d[j] = v.p;
+        }
+        n_oct++;
+        ox /= 2; oy /= 2; oz /= 2;
+    }
+    p->n_oct = n_oct;
+    p->pyr.n_oct = n_oct;
+
+    // schedule (reference MultiScale.cpp:288-294, 337-371, 526-527)
+    {
+        float fInitialImageScale = prm->double_mode == 1 ? 0.5f : 1.0f;
+        float fSigmaInit = 0.5f;
+        if (fInitialImageScale > 0) fSigmaInit /= fInitialImageScale;
+        float fSigma = 1.6f;
+        float fSigmaExtra = sqrtf(fSigma * fSigma - fSigmaInit * fSigmaInit);
+        p->n_init_taps = s3d_gaussian_taps(fSigmaExtra, p->init_taps, kMaxTaps);
+        float fSigmaFactor = (float)pow(2.0, 1.0 / (double)3);
+        float sig[6];
+        sig[0] = fSigma;
+        for (int j = 1; j < 6; j++) {
+            float ex = fSigma * sqrtf(fSigmaFactor * fSigmaFactor - 1.0f);
+            p->n_lvl_taps[j - 1] = s3d_gaussian_taps(ex, p->lvl_taps[j - 1], kMaxTaps);
+            fSigma *= fSigmaFactor;
+            sig[j] = fSigma;
+        }
+        for (int o = 0; o < n_oct; o++) for (int j = 0; j < 6; j++) p->pyr.oct[o].sigma[j] = sig[j];
+        if (p->n_init_taps < 0) return fail(ctx, S3D_ERR_UNSUPPORTED, "initial blur too wide");
+    }
+
+    // candidate lists: capacity X0*Y0 per list like the reference (MultiScale.cpp:255-267), bounded
+    long long cc = (long long)X0 * Y0;
+    if (cc > (1 << 20)) cc = 1 << 20;
+    if (cc < 1024) cc = 1024;
+    p->cand_cap = (int)cc;
+    p->n_lists = n_oct * 3 * 2;
+    if (p->n_lists > 0) {
+        PA(&p->cand_raw, (size_t)2 * p->cand_cap);                 // scratch shared by all lists
+        PA(&p->cand_sorted, (size_t)p->n_lists * p->cand_cap);
+    }
+    PA(&p->counts, p->n_lists + 8);
+    PA(&p->kps, kp_cap);
+    PA(&p->nrows, kp_cap);
+    PA(&p->row_off, kp_cap);
+    PA(&p->kp_eigs, (size_t)kp_cap * 3);
+    PA(&p->kp_ori0, (size_t)kp_cap * 9);
+    PA(&p->kp_rots, (size_t)kp_cap * kMaxRowsPerKp * 9);
+    PA(&p->kp_patch0, (size_t)kp_cap * PV);
+    PA(&p->feats, row_cap);
+    if (p->keep_patches) {
+        PA(&p->dbg_patches, (size_t)row_cap * PV);
+        PA(&p->dbg_prerank, (size_t)row_cap * 64);
+    }
+#undef PA
+    // padding columns must be zero everywhere once; stages keep them zero afterwards
+    CK(cudaMemsetAsync(p->img0.p, 0, p->img0.elems() * sizeof(float), ctx->stream));
+    CK(cudaMemsetAsync(p->tmp1, 0, p->img0.elems() * sizeof(float), ctx->stream));
+    for (auto &v : p->g) CK(cudaMemsetAsync(v.p, 0, v.elems() * sizeof(float), ctx->stream));
+    for (auto &v : p->d) CK(cudaMemsetAsync(v.p, 0, v.elems() * sizeof(float), ctx->stream));
+    return S3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the whole path, enqueued on the stream (input already in plan->stage)
+// ---------------------------------------------------------------------------------------------------
+static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
+{
+    Plan *p = ctx->plan;
+    cudaStream_t st = ctx->stream;
+    int *kp_count = p->counts + p->n_lists, *n_features = kp_count + 1, *err = kp_count + 2;
+    CK(cudaMemsetAsync(p->counts, 0, sizeof(int) * (p->n_lists + 8), st));
+
+    // pre-step: -2+ / -2- / plain copy into the pitched pyramid input
+    if (p->double_mode == 1) {
+        s3d_status s = resize_launch(ctx, 2, p->stage.p, p->X, p->Y, p->Z, p->X, p->img0.p, p->img0.pitch);
+        if (s != S3D_OK) return s;
+    } else if (p->double_mode == -1) {
+        s3d_status s = resize_launch(ctx, 1, p->stage.p, p->X, p->Y, p->Z, p->X, p->img0.p, p->img0.pitch);
+        if (s != S3D_OK) return s;
+    } else {
+        long long rows = (long long)p->Y * p->Z, n = rows * p->img0.pitch;
+        pad_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->stage.p, p->X, rows, p->img0.p, p->img0.pitch);
+        ctx->launches++;
+    }
+    if (p->n_oct == 0) {
+        ctx->has_result = true;
+        return S3D_OK;
+    }
+    // initial blur (MultiScale.cpp:298)
+    {
+        Vol &g0 = p->g[0];
+        s3d_status s = blur3d(ctx, p->img0.p, p->tmp1, g0.p, g0.X, g0.Y, g0.Z, g0.pitch, p->init_taps, p->n_init_taps, nullptr);
+        if (s != S3D_OK) return s;
+    }
+    for (int o = 0; o < p->n_oct; o++) {
+        const OctaveDesc &od = p->pyr.oct[o];
+        for (int j = 1; j < 6; j++) {
+            Vol &a = p->g[o * 6 + j - 1], &b = p->g[o * 6 + j], &dd = p->d[o * 5 + j - 1];
+            s3d_status s = blur3d(ctx, a.p, p->tmp1, b.p, od.X, od.Y, od.Z, od.pitch, p->lvl_taps[j - 1], p->n_lvl_taps[j - 1], dd.p);
+            if (s != S3D_OK) return s;
+            if (j == 3 && o + 1 < p->n_oct) {
+                const OctaveDesc &nx = p->pyr.oct[o + 1];
+                s = resize_launch(ctx, 0, b.p, od.X, od.Y, od.Z, od.pitch, p->g[(o + 1) * 6].p, nx.pitch);
+                if (s != S3D_OK) return s;
+            }
+        }
+        for (int c = 1; c <= 3; c++) {
+            int l0 = (o * 3 + (c - 1)) * 2;
+            s3d_cand *smin = p->cand_sorted + (size_t)l0 * p->cand_cap, *smax = p->cand_sorted + (size_t)(l0 + 1) * p->cand_cap;
+            s3d_status s = detect_launch(ctx, od.d[c - 1], od.d[c], od.X, od.Y, od.Z, od.pitch,
+                                         p->cand_raw, p->cand_raw + p->cand_cap, smin, p->counts + l0, smax, p->counts + l0 + 1, p->cand_cap);
+            if (s != S3D_OK) return s;
+            if (od.X < 3 || od.Y < 3 || od.Z < 3) continue;
+            refine_kernel<<<1, 256, 0, st>>>(p->pyr, o, c, 0, smin, p->counts + l0, p->cand_cap, p->kps, kp_count, p->kp_cap, err);
+            refine_kernel<<<1, 256, 0, st>>>(p->pyr, o, c, 1, smax, p->counts + l0 + 1, p->cand_cap, p->kps, kp_count, p->kp_cap, err);
+            ctx->launches += 2;
+        }
+    }
+    float eig = prm->eig_thres;
+    int grid_o = ctx->sm_count * 3;
+    orient_kernel<<<grid_o, 256, sizeof(OrientSmem), st>>>(p->pyr, p->kps, kp_count, eig, p->nrows, p->kp_eigs, p->kp_ori0, p->kp_rots, p->kp_patch0);
+    row_offsets_kernel<<<1, 1024, 0, st>>>(p->nrows, kp_count, p->row_off, n_features, p->row_cap, err);
+    float size_factor = 1.0f;
+    if (p->double_mode > 0) size_factor /= 2; else if (p->double_mode < 0) size_factor *= 2;
+    int grid_d = ctx->sm_count * 8;
+    describe_kernel<<<grid_d, 128, sizeof(DescribeSmem), st>>>(p->pyr, p->kps, kp_count, p->nrows, p->row_off, p->kp_eigs, p->kp_ori0,
+                                                              p->kp_rots, p->kp_patch0, prm->descriptor, size_factor, p->row_cap,
+                                                              p->feats, p->dbg_patches, p->dbg_prerank);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    return S3D_OK;
+}
+
+static s3d_status check_params(s3d_ctx *ctx, const float *vol, int X, int Y, int Z, const s3d_params *prm)
+{
+    if (!ctx) return S3D_ERR_INVALID;
+    if (!vol || !prm) return fail(ctx, S3D_ERR_INVALID, "null volume or params");
+    if (X < 1 || Y < 1 || Z < 1) return fail(ctx, S3D_ERR_INVALID, "bad dimensions");
+    if (prm->double_mode < -1 || prm->double_mode > 1) return fail(ctx, S3D_ERR_INVALID, "double_mode must be -1, 0 or +1");
+    if (prm->descriptor < 0 || prm->descriptor > 3) return fail(ctx, S3D_ERR_INVALID, "unknown descriptor");
+    if (prm->double_mode != 0 && (X < 2 || Y < 2 || Z < 2)) return fail(ctx, S3D_ERR_INVALID, "volume too small for -2+/-2-");
+    return S3D_OK;
+}
+
+// run the pipeline on plan->stage (already filled, stream-ordered): direct launches or graph replay
+static s3d_status run_pipeline(s3d_ctx *ctx, const s3d_params *prm)
+{
+    Plan *p = ctx->plan;
+    ctx->has_result = false;
+    if (!ctx->use_graph) {
+        ctx->launches = 0;
+        s3d_status s = enqueue_pipeline(ctx, prm);
+        ctx->last_launches = ctx->launches;
+        if (s == S3D_OK) ctx->has_result = true;
+        return s;
+    }
+    if (!p->graph || p->graph_descriptor != prm->descriptor || p->graph_eig != prm->eig_thres) {
+        if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        ctx->launches = 0;
+        s3d_status s = enqueue_pipeline(ctx, prm);
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+        if (s != S3D_OK) { if (g) cudaGraphDestroy(g); return s; }
+        if (e != cudaSuccess) { ctx->err = std::string("graph capture failed: ") + cudaGetErrorString(e); return S3D_ERR_CUDA; }
+        e = cudaGraphInstantiate(&p->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { ctx->err = std::string("graph instantiate failed: ") + cudaGetErrorString(e); p->graph = nullptr; return S3D_ERR_CUDA; }
+        p->graph_descriptor = prm->descriptor;
+        p->graph_eig = prm->eig_thres;
+        ctx->last_launches = ctx->launches;
+    }
+    CK(cudaGraphLaunch(p->graph, ctx->stream));
+    ctx->has_result = true;
+    return S3D_OK;
+}
+
+extern "C" s3d_status s3d_extract_device(s3d_ctx *ctx, const float *d_volume, int X, int Y, int Z, const s3d_params *prm)
+{
+    s3d_status s = check_params(ctx, d_volume, X, Y, Z, prm);
+    if (s != S3D_OK) return s;
+    CK(cudaSetDevice(ctx->device));
+    s = plan_build(ctx, X, Y, Z, prm);
+    if (s != S3D_OK) return s;
+    CK(cudaMemcpyAsync(ctx->plan->stage.p, d_volume, sizeof(float) * (size_t)X * Y * Z, cudaMemcpyDeviceToDevice, ctx->stream));
+    return run_pipeline(ctx, prm);
+}
+
+extern "C" s3d_status s3d_extract_host_async(s3d_ctx *ctx, const float *h_volume, int X, int Y, int Z, const s3d_params *prm)
+{
+    s3d_status s = check_params(ctx, h_volume, X, Y, Z, prm);
+    if (s != S3D_OK) return s;
+    CK(cudaSetDevice(ctx->device));
+    s = plan_build(ctx, X, Y, Z, prm);
+    if (s != S3D_OK) return s;
+    CK(cudaMemcpyAsync(ctx->plan->stage.p, h_volume, sizeof(float) * (size_t)X * Y * Z, cudaMemcpyHostToDevice, ctx->stream));
+    return run_pipeline(ctx, prm);
+}
+
+static s3d_status fetch_counts(s3d_ctx *ctx)
+{
+    if (!ctx->plan || !ctx->has_result) return fail(ctx, S3D_ERR_INVALID, "no extraction has been run");
+    Plan *p = ctx->plan;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->h_counts, p->counts + p->n_lists, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int err = ctx->h_counts[2];
+    if (err) {
+        char b[256];
+        snprintf(b, sizeof(b), "capacity exceeded:%s%s%s (raise s3d_params.max_keypoints / max_features)",
+                 (err & ERR_CAND_OVERFLOW) ? " candidate list" : "", (err & ERR_KP_OVERFLOW) ? " keypoints" : "",
+                 (err & ERR_ROW_OVERFLOW) ? " feature rows" : "");
+        ctx->err = b;
+        return S3D_ERR_CAPACITY;
+    }
+    return S3D_OK;
+}
+
+extern "C" s3d_status s3d_fetch_counts(s3d_ctx *ctx, int *n_keypoints, int *n_features)
+{
+    if (!ctx) return S3D_ERR_INVALID;
+    s3d_status s = fetch_counts(ctx);
+    if (s != S3D_OK) return s;
+    if (n_keypoints) *n_keypoints = ctx->h_counts[0];
+    if (n_features) *n_features = ctx->h_counts[1];
+    return S3D_OK;
+}
+
+extern "C" s3d_status s3d_fetch_features(s3d_ctx *ctx, s3d_feature **out, int *n_out)
+{
+    if (!ctx || !out || !n_out) return S3D_ERR_INVALID;
+    *out = nullptr; *n_out = 0;
+    s3d_status s = fetch_counts(ctx);
+    if (s != S3D_OK) return s;
+    int n = ctx->h_counts[1];
+    s3d_feature *h = (s3d_feature *)malloc(sizeof(s3d_feature) * (size_t)(n > 0 ? n : 1));
+    if (!h) return fail(ctx, S3D_ERR_NOMEM, "host allocation failed");
+    if (n > 0) {
+        cudaError_t e = cudaMemcpyAsync(h, ctx->plan->feats, sizeof(s3d_feature) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { free(h); ctx->err = cudaGetErrorString(e); return S3D_ERR_CUDA; }
+    }
+    *out = h; *n_out = n;
+    return S3D_OK;
+}
+
+extern "C" s3d_status s3d_result_device(s3d_ctx *ctx, const s3d_feature **d_features, const int **d_n_features)
+{
+    if (!ctx || !ctx->plan || !ctx->has_result) return S3D_ERR_INVALID;
+    if (d_features) *d_features = ctx->plan->feats;
+    if (d_n_features) *d_n_features = ctx->plan->counts + ctx->plan->n_lists + 1;
+    return S3D_OK;
+}
+
+extern "C" s3d_status s3d_extract(s3d_ctx *ctx, const float *h_volume, int X, int Y, int Z, const s3d_params *prm,
+                                  s3d_feature **out, int *n_out)
+{
+    if (!out || !n_out) return S3D_ERR_INVALID;
+    s3d_status s = s3d_extract_host_async(ctx, h_volume, X, Y, Z, prm);
+    if (s != S3D_OK) return s;
+    return s3d_fetch_features(ctx, out, n_out);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// introspection
+// ---------------------------------------------------------------------------------------------------
+extern "C" int s3d_num_octaves(s3d_ctx *ctx) { return (ctx && ctx->plan) ? ctx->plan->n_oct : 0; }
+
+extern "C" s3d_status s3d_get_level(s3d_ctx *ctx, int octave, int is_dog, int level, float *h_out, int dims[3])
+{
+    if (!ctx || !ctx->plan || !ctx->has_result) return S3D_ERR_INVALID;
+    Plan *p = ctx->plan;
+    if (octave < 0 || octave >= p->n_oct || level < 0 || level >= (is_dog ? 5 : 6)) return fail(ctx, S3D_ERR_INVALID, "no such level");
+    CK(cudaSetDevice(ctx->device));
+    Vol &v = is_dog ? p->d[octave * 5 + level] : p->g[octave * 6 + level];
+    if (dims) { dims[0] = v.X; dims[1] = v.Y; dims[2] = v.Z; }
+    if (h_out) {
+        CK(cudaMemcpy2DAsync(h_out, sizeof(float) * v.X, v.p, sizeof(float) * v.pitch, sizeof(float) * v.X, (size_t)v.Y * v.Z,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return S3D_OK;
+}
+
+extern "C" s3d_status s3d_get_keypoints(s3d_ctx *ctx, s3d_keypoint **out, int *n_out)
+{
+    if (!ctx || !out || !n_out) return S3D_ERR_INVALID;
+    s3d_status s = fetch_counts(ctx);
+    if (s != S3D_OK) return s;
+    int n = ctx->h_counts[0];
+    s3d_keypoint *h = (s3d_keypoint *)malloc(sizeof(s3d_keypoint) * (size_t)(n > 0 ? n : 1));
+    if (n > 0) {
+        CK(cudaMemcpyAsync(h, ctx->plan->kps, sizeof(s3d_keypoint) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    *out = h; *n_out = n;
+    return S3D_OK;
+}
+
+extern "C" s3d_status s3d_get_patches(s3d_ctx *ctx, float **patches, float **prerank, int *n_out)
+{
+    if (!ctx || !n_out) return S3D_ERR_INVALID;
+    s3d_status s = fetch_counts(ctx);
+    if (s != S3D_OK) return s;
+    if (!ctx->plan->keep_patches) return fail(ctx, S3D_ERR_INVALID, "extraction was run without keep_patches");
+    int n = ctx->h_counts[1];
+    *n_out = n;
+    if (patches) {
+        *patches = (float *)malloc(sizeof(float) * PV * (size_t)(n > 0 ? n : 1));
+        if (n > 0) CK(cudaMemcpyAsync(*patches, ctx->plan->dbg_patches, sizeof(float) * PV * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (prerank) {
+        *prerank = (float *)malloc(sizeof(float) * 64 * (size_t)(n > 0 ? n : 1));
+        if (n > 0) CK(cudaMemcpyAsync(*prerank, ctx->plan->dbg_prerank, sizeof(float) * 64 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return S3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// feature file writer (kept host code): msFeature3DVectorOutputText, reference MultiScale.h:386-474
+// ---------------------------------------------------------------------------------------------------
+extern "C" s3d_status s3d_write_features_text(const char *path, const s3d_feature *feats, int n, float fEigThres,
+                                              int n_comments, const char *const *comments)
+{
+    if (!path || (n > 0 && !feats)) return S3D_ERR_INVALID;
+    FILE *f = fopen(path, "wt");
+    if (!f) return S3D_ERR_INVALID;
+    auto keep = [&](const s3d_feature &ft) {
+        float fEigSum = ft.eigs[0] + ft.eigs[1] + ft.eigs[2];
+        float fEigPrd = ft.eigs[0] * ft.eigs[1] * ft.eigs[2];
+        float fEigSumProd = fEigSum * fEigSum * fEigSum;
+        return (fEigSumProd < fEigThres * fEigPrd || fEigThres < 0);
+    };
+    int cnt = 0;
+    for (int i = 0; i < n; i++) if (keep(feats[i])) cnt++;
+    fprintf(f, "# featExtract %s\n", "1.1");
+    for (int i = 0; i < n_comments; i++) fprintf(f, "# %s\n", comments[i]);
+    fprintf(f, "Features: %d\n", cnt);
+    fprintf(f, "Scale-space location[x y z scale] orientation[o11 o12 o13 o21 o22 o23 o31 o32 o32] 2nd moment eigenvalues[e1 e2 e3] info flag[i1] descriptor[d1 .. d64]\n");
+    for (int i = 0; i < n; i++) {
+        const s3d_feature &ft = feats[i];
+        if (!keep(ft)) continue;
+        fprintf(f, "%f\t%f\t%f\t%f\t", ft.x, ft.y, ft.z, ft.scale);
+        for (int j = 0; j < 9; j++) fprintf(f, "%f\t", ft.ori[j]);
+        for (int j = 0; j < 3; j++) fprintf(f, "%f\t", ft.eigs[j]);
+        fprintf(f, "%d\t", ft.flag);
+        for (int j = 0; j < 64; j++) fprintf(f, "%i\t", (char)(ft.pc[j]));
+        fprintf(f, "\n");
+    }
+    fclose(f);
+    return S3D_OK;
+}

@@ -1,0 +1,959 @@
+// s3d_keypoint.cuh -- per-keypoint stages for sm_100a: deferred validation + sub-voxel refinement,
+// 11^3 patch gather, normalisation, structure-tensor eigen-orientation, canonical orientation
+// histograms, SIFT-Rank / BRIEF-family descriptors, rank transform.
+//
+// These stages are CPU-only in the reference; here each keypoint (or feature row) is
+// one CTA.  The arithmetic follows the reference operation for operation so the output is
+// bit-identical: per-sample work (trilinear gathers, gradients, blurs, contributions) is done by all
+// threads, while the few order-sensitive fp32 accumulations (patch mean / energy, structure tensor,
+// histogram splats, descriptor bins) are walked in the reference's raster order by the thread that
+// owns the accumulator.  Compiled with -fmad=false; divisions and square roots are IEEE (nvcc default).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include "../../include/s3d.h"
+
+namespace s3d {
+
+constexpr int PD = 11;
+constexpr int PV = 1331;
+constexpr int kMaxOct = 12;
+constexpr int kMaxRowsPerKp = 12;   // 1 non-reoriented + at most 11 orientations (reference MultiScale.cpp:2875, 2966)
+constexpr int kMaxSphere = 640;
+
+struct OctaveDesc {
+    int X, Y, Z, pitch;
+    const float *g[6];
+    const float *d[5];
+    float sigma[6];
+};
+struct PyramidDesc {
+    int n_oct;
+    OctaveDesc oct[kMaxOct];
+};
+
+// Small tables shared by all keypoint kernels; filled once per context (s3d_engine.cu).
+struct KpTables {
+    int n_sphere;                         // voxels with dx^2+dy^2+dz^2 < 25, raster order
+    unsigned short sphere[kMaxSphere];
+    int n_hist_taps;                      // sigma 0.5 (fBlurGradOriHist, reference MultiScale.cpp:37)
+    float hist_taps[9];
+    int n_brief_taps;                     // sigma 0.95 (reference MultiScale.cpp:1032)
+    float brief_taps[9];
+    float desc_w[PD];                     // weight of the lower spatial bin per patch coordinate
+    unsigned short brief_a[64], brief_b[64];   // linear patch offsets of the 64 BRIEF pairs
+    float brief_dist[64];                 // (int)|a-b| as float, NRRIEF divisor
+};
+__constant__ KpTables c_tab;
+
+enum { ERR_CAND_OVERFLOW = 1, ERR_KP_OVERFLOW = 2, ERR_ROW_OVERFLOW = 4 };
+
+// ------------------------------------------------------------------------------------------------
+// scalar helpers (reference MultiScale.cpp:1614-1697, 2531-2534; FeatureIO.cpp:757-850)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double finddet(double a1, double a2, double a3, double b1, double b2, double b3,
+                                          double c1, double c2, double c3)
+{
+    return ((a1 * b2 * c3) - (a1 * b3 * c2) - (a2 * b1 * c3) + (a3 * b1 * c2) + (a2 * b3 * c1) - (a3 * b2 * c1));
+}
+
+__device__ double interp_quadratic(double x0, double x1, double x2, double fx0, double fx1, double fx2)
+{
+    if (!(fx1 < fx0 && fx1 < fx2) && !(fx1 > fx0 && fx1 > fx2)) return x1;
+    double a1 = x0 * x0, b1 = x0, c1 = 1;
+    double a2 = x1 * x1, b2 = x1, c2 = 1;
+    double a3 = x2 * x2, b3 = x2, c3 = 1;
+    double det = finddet(a1, a2, a3, b1, b2, b3, c1, c2, c3);
+    double detx = finddet(fx0, fx1, fx2, b1, b2, b3, c1, c2, c3);
+    double dety = finddet(a1, a2, a3, fx0, fx1, fx2, c1, c2, c3);
+    if (fx0 == 0 && fx1 == 0 && fx2 == 0) return x1;
+    if (det != 0) {
+        if (detx != 0) return dety / (-2.0 * detx);
+    }
+    return x1;
+}
+
+__device__ __forceinline__ void interp_coord(float fX, float fMaxX, int &iX, float &fW)
+{
+    if (fX < 0.5f) {
+        iX = 0;
+        fW = 1.0f;
+    } else if (fX >= fMaxX - 0.5f) {
+        iX = (int)(fMaxX - 2);
+        fW = 0.0f;
+    } else {
+        float fMinusHalf = fX - 0.5f;
+        iX = (int)floorf(fMinusHalf);
+        fW = 1.0f - (fMinusHalf - ((float)iX));
+    }
+}
+
+__device__ __forceinline__ float trilinear_get(const float *__restrict__ img, int X, int Y, int Z, int pitch,
+                                               float x, float y, float z)
+{
+    int iX, iY, iZ;
+    float wx, wy, wz;
+    interp_coord(x, (float)X, iX, wx);
+    interp_coord(y, (float)Y, iY, wy);
+    interp_coord(z, (float)Z, iZ, wz);
+    const float *p = img + ((long long)iZ * Y + iY) * pitch + iX;
+    long long plane = (long long)pitch * Y;
+    float f000 = __ldg(p), f100 = __ldg(p + 1), f010 = __ldg(p + pitch), f110 = __ldg(p + pitch + 1);
+    float f001 = __ldg(p + plane), f101 = __ldg(p + plane + 1), f011 = __ldg(p + plane + pitch), f111 = __ldg(p + plane + pitch + 1);
+    float fn00 = wx * f000 + (1.0f - wx) * f100;
+    float fn01 = wx * f001 + (1.0f - wx) * f101;
+    float fn10 = wx * f010 + (1.0f - wx) * f110;
+    float fn11 = wx * f011 + (1.0f - wx) * f111;
+    float fnn0 = wy * fn00 + (1.0f - wy) * fn10;
+    float fnn1 = wy * fn01 + (1.0f - wy) * fn11;
+    return wz * fnn0 + (1.0f - wz) * fnn1;
+}
+
+// invert_3x3<float,double> (reference MultiScale.h:192-222)
+__device__ void invert3(const float *m, float *o)
+{
+    float a11 = m[0], a12 = m[1], a13 = m[2];
+    float a21 = m[3], a22 = m[4], a23 = m[5];
+    float a31 = m[6], a32 = m[7], a33 = m[8];
+    float det = a11 * (a33 * a22 - a32 * a23) - a21 * (a33 * a12 - a32 * a13) + a31 * (a23 * a12 - a22 * a13);
+    double div = 1 / (double)det;
+    o[0] = (float)((a33 * a22 - a32 * a23) * div);
+    o[3] = (float)(-(a33 * a21 - a31 * a23) * div);
+    o[6] = (float)((a32 * a21 - a31 * a22) * div);
+    o[1] = (float)(-(a33 * a12 - a32 * a13) * div);
+    o[4] = (float)((a33 * a11 - a31 * a13) * div);
+    o[7] = (float)(-(a32 * a11 - a31 * a12) * div);
+    o[2] = (float)((a23 * a12 - a22 * a13) * div);
+    o[5] = (float)(-(a23 * a11 - a21 * a13) * div);
+    o[8] = (float)((a22 * a11 - a21 * a12) * div);
+}
+
+__device__ __forceinline__ void vec_norm(float *p)
+{
+    float fSumSqr = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+    if (fSumSqr > 0) {
+        float fDiv = (float)(1.0 / (double)sqrtf(fSumSqr));
+        p[0] *= fDiv; p[1] *= fDiv; p[2] *= fDiv;
+    } else {
+        p[0] = 1; p[1] = 0; p[2] = 0;
+    }
+}
+__device__ __forceinline__ float vec_mag(const float *p)
+{
+    float fSumSqr = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+    return fSumSqr > 0 ? sqrtf(fSumSqr) : 0.0f;
+}
+__device__ __forceinline__ float vec_dot(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// ------------------------------------------------------------------------------------------------
+// block-cooperative pieces (blockDim.x threads, all must call)
+// ------------------------------------------------------------------------------------------------
+
+// sampleImage3D (reference MultiScale.cpp:2614-2714): inv = inverse orientation, already in smem.
+__device__ void gather_patch(const float *__restrict__ img, int X, int Y, int Z, int pitch,
+                             float fx, float fy, float fz, float scale, const float *inv, float *patch)
+{
+    float fImageRad = 2.0f * scale;
+    float fScale = fImageRad / (float)(PD / 2);
+    for (int i = threadIdx.x; i < PV; i += blockDim.x) {
+        int x = i % PD - 5, y = (i / PD) % PD - 5, z = i / (PD * PD) - 5;
+        float f[3] = { (float)x, (float)y, (float)z }, p[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            float s = 0.0f;
+            s = s + inv[a * 3 + 0] * f[0];
+            s = s + inv[a * 3 + 1] * f[1];
+            s = s + inv[a * 3 + 2] * f[2];
+            p[a] = s;
+        }
+        p[0] *= fScale; p[1] *= fScale; p[2] *= fScale;
+        p[0] += fx; p[1] += fy; p[2] += fz;
+        float pix;
+        if (p[0] < 0 || p[0] >= X) pix = 0.0f;
+        else pix = trilinear_get(img, X, Y, Z, pitch, p[0], p[1], p[2]);
+        patch[i] = pix;
+    }
+}
+
+// Feature3D::NormalizeData (reference MultiScale.cpp:127-205).  scratch: PV floats, red: 2 floats.
+__device__ void normalize_patch(float *patch, float *scratch, float *red)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+        for (int i = 0; i < PV; i++) s = s + patch[i];
+        red[0] = s / (float)(PD * PD * PD);
+    }
+    __syncthreads();
+    float mean = red[0];
+    for (int i = threadIdx.x; i < PV; i += blockDim.x) {
+        float v = patch[i] - mean;
+        patch[i] = v;
+        scratch[i] = v * v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+        for (int i = 0; i < PV; i++) s = s + scratch[i];
+        red[1] = 1.0f / sqrtf(s);
+    }
+    __syncthreads();
+    float fDiv = red[1];
+    for (int i = threadIdx.x; i < PV; i += blockDim.x) patch[i] = patch[i] * fDiv;
+    __syncthreads();
+}
+
+// fioGenerateEdgeImages3D on the patch (reference FeatureIO.cpp:2284-2326)
+__device__ void patch_gradients(const float *p, float *dx, float *dy, float *dz)
+{
+    for (int i = threadIdx.x; i < PV; i += blockDim.x) {
+        int x = i % PD, y = (i / PD) % PD, z = i / (PD * PD);
+        float gx = 0.0f, gy = 0.0f, gz = 0.0f;
+        if (x >= 1 && x < PD - 1 && y >= 1 && y < PD - 1 && z >= 1 && z < PD - 1) {
+            gx = p[i + 1] - p[i - 1];
+            gy = p[i + PD] - p[i - PD];
+            gz = p[i + PD * PD] - p[i - PD * PD];
+        }
+        dx[i] = gx; dy[i] = gy; dz[i] = gz;
+    }
+    __syncthreads();
+}
+
+// blur_3d_simpleborders on an 11^3 image (reference GaussBlur3D.cpp:329-479): src -> dst, tmp scratch.
+// src may be clobbered?  No: src is left intact; dst and tmp must differ from src and each other.
+__device__ void blur_patch(const float *src, float *tmp, float *dst, const float *taps, int ntaps)
+{
+    int r = ntaps / 2;
+    __syncthreads();
+    for (int i = threadIdx.x; i < PV; i += blockDim.x) {   // x: src -> dst
+        int x = i % PD;
+        float s = 0.0f;
+        for (int j = 0; j < ntaps; j++) { int p = x + j - r; float v = (p >= 0 && p < PD) ? src[i + j - r] : 0.0f; s = s + taps[j] * v; }
+        dst[i] = s;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PV; i += blockDim.x) {   // y: dst -> tmp
+        int y = (i / PD) % PD;
+        float s = 0.0f;
+        for (int j = 0; j < ntaps; j++) { int p = y + j - r; float v = (p >= 0 && p < PD) ? dst[i + (j - r) * PD] : 0.0f; s = s + taps[j] * v; }
+        tmp[i] = s;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PV; i += blockDim.x) {   // z: tmp -> dst
+        int z = i / (PD * PD);
+        float s = 0.0f;
+        for (int j = 0; j < ntaps; j++) { int p = z + j - r; float v = (p >= 0 && p < PD) ? tmp[i + (j - r) * PD * PD] : 0.0f; s = s + taps[j] * v; }
+        dst[i] = s;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// SingularValueDecomp<float,3,3> + SortEigenDecomp (reference SVD.h:15-228): float storage, double scalars.
+// ------------------------------------------------------------------------------------------------
+#define S3D_SIGN(a, b) ((b) >= 0.0 ? fabs(a) : -fabs(a))
+#define S3D_PYTHAG(a, b) (sqrt((a) * (a) + (b) * (b)))
+
+__device__ void svd3(float mat[3][3], float w[3], float v[3][3])
+{
+    const int m = 3, n = 3;
+    int flag, i, its, j, jj, k, l = 0, nm = 0;
+    double anorm, c, f, g, h, s, scale, x, y, z;
+    double rv1[3];
+    g = scale = anorm = 0.0;
+    for (i = 1; i <= n; i++) {
+        l = i + 1;
+        rv1[i - 1] = scale * g;
+        g = s = scale = 0.0;
+        if (i <= m) {
+            for (k = i; k <= m; k++) scale += fabs((double)mat[k - 1][i - 1]);
+            if (scale) {
+                for (k = i; k <= m; k++) {
+                    mat[k - 1][i - 1] = (float)(mat[k - 1][i - 1] / scale);
+                    s += (double)(mat[k - 1][i - 1] * mat[k - 1][i - 1]);
+                }
+                f = mat[i - 1][i - 1];
+                g = -S3D_SIGN(sqrt(s), f);
+                h = f * g - s;
+                mat[i - 1][i - 1] = (float)(f - g);
+                for (j = l; j <= n; j++) {
+                    for (s = 0.0, k = i; k <= m; k++) s += (double)(mat[k - 1][i - 1] * mat[k - 1][j - 1]);
+                    f = s / h;
+                    for (k = i; k <= m; k++) mat[k - 1][j - 1] = (float)(mat[k - 1][j - 1] + f * mat[k - 1][i - 1]);
+                }
+                for (k = i; k <= m; k++) mat[k - 1][i - 1] = (float)(mat[k - 1][i - 1] * scale);
+            }
+        }
+        w[i - 1] = (float)(scale * g);
+        g = s = scale = 0.0;
+        if (i <= m && i != n) {
+            for (k = l; k <= n; k++) scale += fabs((double)mat[i - 1][k - 1]);
+            if (scale) {
+                for (k = l; k <= n; k++) {
+                    mat[i - 1][k - 1] = (float)(mat[i - 1][k - 1] / scale);
+                    s += (double)(mat[i - 1][k - 1] * mat[i - 1][k - 1]);
+                }
+                f = mat[i - 1][l - 1];
+                g = -S3D_SIGN(sqrt(s), f);
+                h = f * g - s;
+                mat[i - 1][l - 1] = (float)(f - g);
+                for (k = l; k <= n; k++) rv1[k - 1] = mat[i - 1][k - 1] / h;
+                for (j = l; j <= m; j++) {
+                    for (s = 0.0, k = l; k <= n; k++) s += (double)(mat[j - 1][k - 1] * mat[i - 1][k - 1]);
+                    for (k = l; k <= n; k++) mat[j - 1][k - 1] = (float)(mat[j - 1][k - 1] + s * rv1[k - 1]);
+                }
+                for (k = l; k <= n; k++) mat[i - 1][k - 1] = (float)(mat[i - 1][k - 1] * scale);
+            }
+        }
+        {
+            double t = fabs((double)w[i - 1]) + fabs(rv1[i - 1]);
+            anorm = (anorm > t ? anorm : t);
+        }
+    }
+    for (i = n; i >= 1; i--) {
+        if (i < n) {
+            if (g) {
+                for (j = l; j <= n; j++) v[j - 1][i - 1] = (float)((mat[i - 1][j - 1] / mat[i - 1][l - 1]) / g);
+                for (j = l; j <= n; j++) {
+                    for (s = 0.0, k = l; k <= n; k++) s += (double)(mat[i - 1][k - 1] * v[k - 1][j - 1]);
+                    for (k = l; k <= n; k++) v[k - 1][j - 1] = (float)(v[k - 1][j - 1] + s * v[k - 1][i - 1]);
+                }
+            }
+            for (j = l; j <= n; j++) v[i - 1][j - 1] = v[j - 1][i - 1] = 0.0f;
+        }
+        v[i - 1][i - 1] = 1.0f;
+        g = rv1[i - 1];
+        l = i;
+    }
+    for (i = n; i >= 1; i--) {
+        l = i + 1;
+        g = w[i - 1];
+        for (j = l; j <= n; j++) mat[i - 1][j - 1] = 0.0f;
+        if (g) {
+            g = 1.0 / g;
+            for (j = l; j <= n; j++) {
+                for (s = 0.0, k = l; k <= m; k++) s += (double)(mat[k - 1][i - 1] * mat[k - 1][j - 1]);
+                f = (s / mat[i - 1][i - 1]) * g;
+                for (k = i; k <= m; k++) mat[k - 1][j - 1] = (float)(mat[k - 1][j - 1] + f * mat[k - 1][i - 1]);
+            }
+            for (j = i; j <= m; j++) mat[j - 1][i - 1] = (float)(mat[j - 1][i - 1] * g);
+        } else {
+            for (j = i; j <= m; j++) mat[j - 1][i - 1] = 0.0f;
+        }
+        mat[i - 1][i - 1] = mat[i - 1][i - 1] + 1;
+    }
+    for (k = n; k >= 1; k--) {
+        for (its = 1; its <= 30; its++) {
+            flag = 1;
+            for (l = k; l >= 1; l--) {
+                nm = l - 1;
+                if ((double)(fabs(rv1[l - 1]) + anorm) == anorm) { flag = 0; break; }
+                if ((double)(fabs((double)w[nm - 1]) + anorm) == anorm) break;
+            }
+            if (flag) {
+                c = 0.0;
+                s = 1.0;
+                for (i = l; i <= k; i++) {
+                    f = s * rv1[i - 1];
+                    rv1[i - 1] = c * rv1[i - 1];
+                    if ((double)(fabs(f) + anorm) == anorm) break;
+                    g = w[i - 1];
+                    h = S3D_PYTHAG(f, g);
+                    w[i - 1] = (float)h;
+                    h = 1.0 / h;
+                    c = g * h;
+                    s = -f * h;
+                    for (j = 1; j <= m; j++) {
+                        y = mat[j - 1][nm - 1];
+                        z = mat[j - 1][i - 1];
+                        mat[j - 1][nm - 1] = (float)(y * c + z * s);
+                        mat[j - 1][i - 1] = (float)(z * c - y * s);
+                    }
+                }
+            }
+            z = w[k - 1];
+            if (l == k) {
+                if (z < 0.0) {
+                    w[k - 1] = (float)(-z);
+                    for (j = 1; j <= n; j++) v[j - 1][k - 1] = -v[j - 1][k - 1];
+                }
+                break;
+            }
+            x = w[l - 1];
+            nm = k - 1;
+            y = w[nm - 1];
+            g = rv1[nm - 1];
+            h = rv1[k - 1];
+            f = ((y - z) * (y + z) + (g - h) * (g + h)) / (2.0 * h * y);
+            g = S3D_PYTHAG(f, 1.0);
+            f = ((x - z) * (x + z) + h * ((y / (f + S3D_SIGN(g, f))) - h)) / x;
+            c = s = 1.0;
+            for (j = l; j <= nm; j++) {
+                i = j + 1;
+                g = rv1[i - 1];
+                y = w[i - 1];
+                h = s * g;
+                g = c * g;
+                z = S3D_PYTHAG(f, h);
+                rv1[j - 1] = z;
+                c = f / z;
+                s = h / z;
+                f = x * c + g * s;
+                g = g * c - x * s;
+                h = y * s;
+                y *= c;
+                for (jj = 1; jj <= n; jj++) {
+                    x = v[jj - 1][j - 1];
+                    z = v[jj - 1][i - 1];
+                    v[jj - 1][j - 1] = (float)(x * c + z * s);
+                    v[jj - 1][i - 1] = (float)(z * c - x * s);
+                }
+                z = S3D_PYTHAG(f, h);
+                w[j - 1] = (float)z;
+                if (z) {
+                    z = 1.0 / z;
+                    c = f * z;
+                    s = h * z;
+                }
+                f = c * g + s * y;
+                x = c * y - s * g;
+                for (jj = 1; jj <= m; jj++) {
+                    y = mat[jj - 1][j - 1];
+                    z = mat[jj - 1][i - 1];
+                    mat[jj - 1][j - 1] = (float)(y * c + z * s);
+                    mat[jj - 1][i - 1] = (float)(z * c - y * s);
+                }
+            }
+            rv1[l - 1] = 0.0;
+            rv1[k - 1] = f;
+            w[k - 1] = (float)x;
+        }
+    }
+}
+
+__device__ void sort_eigen(float w[3], float v[3][3])
+{
+    for (int i = 0; i < 3; i++)
+        for (int j = i + 1; j < 3; j++)
+            if (w[i] < w[j]) {
+                float t = w[j]; w[j] = w[i]; w[i] = t;
+                for (int k = 0; k < 3; k++) { t = v[k][j]; v[k][j] = v[k][i]; v[k][i] = t; }
+            }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 1: deferred validation + refinement + bounds test + ordered compaction of one candidate list
+// (reference MultiScale.cpp:424-455, 1135-1318, 1372-1386, 2633-2643).  One CTA; lists are short.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) refine_kernel(const __grid_constant__ PyramidDesc pyr, int octave, int c, int is_max,
+                                                     const s3d_cand *__restrict__ list, const int *__restrict__ count, int cap,
+                                                     s3d_keypoint *__restrict__ kps, int *kp_count, int kp_cap, int *err)
+{
+    __shared__ int s_warp[8];
+    __shared__ int s_base, s_run;
+    const OctaveDesc &o = pyr.oct[octave];
+    const int X = o.X, Y = o.Y, Z = o.Z, pitch = o.pitch;
+    const long long plane = (long long)pitch * Y;
+    int n = *count;
+    if (threadIdx.x == 0) {
+        if (n > cap) atomicOr(err, ERR_CAND_OVERFLOW);
+        s_base = *kp_count;
+        s_run = 0;
+    }
+    n = min(n, cap);
+    __syncthreads();
+    const float *dH = o.d[c - 1], *dC = o.d[c], *dL = o.d[c + 1];
+    for (int start = 0; start < n; start += blockDim.x) {
+        int k = start + threadIdx.x;
+        bool valid = false;
+        s3d_keypoint kp;
+        if (k < n) {
+            s3d_cand cd = list[k];
+            long long i = (long long)cd.z * plane + (long long)cd.y * pitch + cd.x;
+            float cv = cd.value;
+            bool ok = true;
+            for (int dz = -1; dz <= 1 && ok; dz++)
+                for (int dy = -1; dy <= 1 && ok; dy++) {
+                    const float *row = dL + i + dz * plane + dy * pitch;
+                    float a = row[-1], b = row[0], d = row[1];
+                    ok = is_max ? ((a < cv) && (b < cv) && (d < cv)) : ((a > cv) && (b > cv) && (d > cv));
+                }
+            if (ok) {
+                float fx = (float)interp_quadratic(cd.x - 1, cd.x, cd.x + 1, dC[i - 1], dC[i], dC[i + 1]);
+                float fy = (float)interp_quadratic(cd.y - 1, cd.y, cd.y + 1, dC[i - pitch], dC[i], dC[i + pitch]);
+                float fz = (float)interp_quadratic(cd.z - 1, cd.z, cd.z + 1, dC[i - plane], dC[i], dC[i + plane]);
+                float scale = (float)(2 * interp_quadratic(o.sigma[c - 1], o.sigma[c], o.sigma[c + 1], dH[i], dC[i], dL[i]));
+                fx += 0.5f; fy += 0.5f; fz += 0.5f;
+                float fImageRad = 2.0f * scale;
+                int iRadMax = (int)(fImageRad + 2);
+                bool out_of_bounds = (fx - iRadMax < 0 || fy - iRadMax < 0 || fz - iRadMax < 0 ||
+                                      fx + iRadMax >= X || fy + iRadMax >= Y || fz + iRadMax >= Z);
+                if (!out_of_bounds) {
+                    valid = true;
+                    kp.octave = octave; kp.level = c; kp.is_max = is_max;
+                    kp.ix = cd.x; kp.iy = cd.y; kp.iz = cd.z;
+                    kp.x = fx; kp.y = fy; kp.z = fz; kp.scale = scale;
+                }
+            }
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, valid);
+        int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        int pre = __popc(bal & ((1u << lane) - 1));
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { if (w < wid) woff += s_warp[w]; tot += s_warp[w]; }
+        int pos = s_base + s_run + woff + pre;
+        if (valid) {
+            if (pos < kp_cap) kps[pos] = kp;
+            else atomicOr(err, ERR_KP_OVERFLOW);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_run += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *kp_count = min(s_base + s_run, kp_cap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 2: orientation assignment, one CTA per keypoint (persistent grid-stride loop).
+// Reference: generateFeature3D (MultiScale.cpp:1705-1862), determineOrientation3D (:2541-2607),
+// determineCanonicalOrientation3D (:2722-3037).
+// Outputs per keypoint: nrows (0 when rejected by the eigenvalue test), eigs, ori0 (sorted V),
+// rots (n_ori x 9), and the normalised identity patch (row 0 of the keypoint).
+// ------------------------------------------------------------------------------------------------
+struct OrientSmem {
+    float patch[PV];
+    float dx[PV], dy[PV], dz[PV];
+    float h0[PV], h1[PV], h2[PV];
+    float contrib[kMaxSphere * 8];
+    int cbase[kMaxSphere];
+    s3d_cand peaks[128], peaks2[128], psort[128];
+    float oriData[PD * 3];
+    float rots[kMaxRowsPerKp * 9];
+    float inv[9];
+    float fmat[9];
+    float red[2];
+    float eigs[3];
+    float ori0[9];
+    int np, np2, nret, keep;
+};
+
+// Sequential splat of the per-voxel contributions into a zeroed 11^3 histogram, in sphere (raster)
+// order: 8 lanes own the 8 corners of a voxel's 2x2x2 footprint (distinct bins), __syncwarp orders
+// successive voxels (fioIncPixelTrilinearInterp, reference FeatureIO.cpp:853-889).
+__device__ void splat_histogram(float *hist, const float *contrib, const int *cbase, int n_sphere)
+{
+    for (int i = threadIdx.x; i < PV; i += blockDim.x) hist[i] = 0.0f;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int lane = threadIdx.x;
+        int off = (lane & 1) + ((lane >> 1) & 1) * PD + ((lane >> 2) & 1) * PD * PD;
+        for (int n = 0; n < n_sphere; n++) {
+            int b = cbase[n];
+            if (b >= 0 && lane < 8) hist[b + off] = hist[b + off] + contrib[n * 8 + lane];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
+// contributions of one voxel at histogram position (px,py,pz) with value v
+__device__ __forceinline__ void make_contrib(float px, float py, float pz, float v, float *c8, int &base)
+{
+    int iX, iY, iZ;
+    float wx, wy, wz;
+    interp_coord(px, (float)PD, iX, wx);
+    interp_coord(py, (float)PD, iY, wy);
+    interp_coord(pz, (float)PD, iZ, wz);
+    base = (iZ * PD + iY) * PD + iX;
+    c8[0] = v * wx * wy * wz;
+    c8[1] = v * (1.0f - wx) * wy * wz;
+    c8[2] = v * wx * (1.0f - wy) * wz;
+    c8[3] = v * (1.0f - wx) * (1.0f - wy) * wz;
+    c8[4] = v * wx * wy * (1.0f - wz);
+    c8[5] = v * (1.0f - wx) * wy * (1.0f - wz);
+    c8[6] = v * wx * (1.0f - wy) * (1.0f - wz);
+    c8[7] = v * (1.0f - wx) * (1.0f - wy) * (1.0f - wz);
+}
+
+// regFindFEATUREIOPeaks + lvSortHighLow on an 11^3 histogram (reference MultiScale.cpp:1987-2121,
+// LocationValue.cpp:28-56).  Result in `sorted` (descending value, ties in raster order), count in *np.
+__device__ void find_sort_peaks(const float *h, s3d_cand *raw, s3d_cand *sorted, int *np)
+{
+    if (threadIdx.x < 32) {
+        int lane = threadIdx.x, n = 0;
+        for (int t0 = 0; t0 < 729; t0 += 32) {
+            int t = t0 + lane;
+            bool pk = false;
+            int x = 0, y = 0, z = 0;
+            float c = 0.0f;
+            if (t < 729) {
+                x = 1 + t % 9; y = 1 + (t / 9) % 9; z = 1 + t / 81;
+                int i = (z * PD + y) * PD + x;
+                c = h[i];
+                pk = true;
+                for (int dz = -1; dz <= 1; dz++)
+                    for (int dy = -1; dy <= 1; dy++)
+                        for (int dx = -1; dx <= 1; dx++) {
+                            if (dx == 0 && dy == 0 && dz == 0) continue;
+                            pk = pk && (h[i + (dz * PD + dy) * PD + dx] < c);
+                        }
+            }
+            unsigned bal = __ballot_sync(0xffffffffu, pk);
+            if (pk) {
+                int pos = n + __popc(bal & ((1u << lane) - 1));
+                if (pos < 128) raw[pos] = s3d_cand{ x, y, z, c };
+            }
+            n += __popc(bal);
+        }
+        if (lane == 0) *np = min(n, 128);
+    }
+    __syncthreads();
+    int n = *np;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float v = raw[i].value;
+        int rank = 0;
+        for (int j = 0; j < n; j++) {
+            float u = raw[j].value;
+            rank += (u > v) || (u == v && j < i);
+        }
+        sorted[rank] = raw[i];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void interp_point_patch(const float *h, int ix, int iy, int iz, float *o)
+{
+    int i = (iz * PD + iy) * PD + ix;
+    o[0] = (float)interp_quadratic(ix - 1, ix, ix + 1, h[i - 1], h[i], h[i + 1]);
+    o[1] = (float)interp_quadratic(iy - 1, iy, iy + 1, h[i - PD], h[i], h[i + PD]);
+    o[2] = (float)interp_quadratic(iz - 1, iz, iz + 1, h[i - PD * PD], h[i], h[i + PD * PD]);
+}
+
+__global__ void __launch_bounds__(256) orient_kernel(const __grid_constant__ PyramidDesc pyr,
+                                                     const s3d_keypoint *__restrict__ kps, const int *__restrict__ kp_count,
+                                                     float eig_thres,
+                                                     int *__restrict__ nrows, float *__restrict__ kp_eigs, float *__restrict__ kp_ori0,
+                                                     float *__restrict__ kp_rots, float *__restrict__ kp_patch0)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    OrientSmem &S = *reinterpret_cast<OrientSmem *>(smem_raw);
+    const int nkp = *kp_count;
+    const int nsph = c_tab.n_sphere;
+    const float fRadius = 5.0f;
+
+    for (int kpi = blockIdx.x; kpi < nkp; kpi += gridDim.x) {
+        __syncthreads();
+        const s3d_keypoint kp = kps[kpi];
+        const OctaveDesc &o = pyr.oct[kp.octave];
+        const float *img = o.g[kp.level];
+
+        // --- identity patch, normalised (generateFeature3D :1721-1739)
+        if (threadIdx.x < 9) S.inv[threadIdx.x] = (threadIdx.x % 4 == 0) ? 1.0f : 0.0f;
+        __syncthreads();
+        if (threadIdx.x == 0) { float id[9]; for (int q = 0; q < 9; q++) id[q] = S.inv[q]; invert3(id, S.inv); }
+        __syncthreads();
+        gather_patch(img, o.X, o.Y, o.Z, o.pitch, kp.x, kp.y, kp.z, kp.scale, S.inv, S.patch);
+        normalize_patch(S.patch, S.h0, S.red);
+        for (int i = threadIdx.x; i < PV; i += blockDim.x) kp_patch0[(long long)kpi * PV + i] = S.patch[i];
+
+        // --- eigen-orientation (determineOrientation3D)
+        patch_gradients(S.patch, S.dx, S.dy, S.dz);
+        if (threadIdx.x < 9) {
+            const float *ea = (threadIdx.x / 3 == 0) ? S.dx : (threadIdx.x / 3 == 1) ? S.dy : S.dz;
+            const float *eb = (threadIdx.x % 3 == 0) ? S.dx : (threadIdx.x % 3 == 1) ? S.dy : S.dz;
+            float m = 0.0f;
+            for (int n = 0; n < nsph; n++) { int i = c_tab.sphere[n]; m = m + ea[i] * eb[i]; }
+            S.fmat[threadIdx.x] = m;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float mat[3][3], w[3], v[3][3];
+            for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) mat[a][b] = S.fmat[a * 3 + b];
+            svd3(mat, w, v);
+            sort_eigen(w, v);
+            for (int a = 0; a < 3; a++) { S.eigs[a] = w[a]; for (int b = 0; b < 3; b++) S.ori0[a * 3 + b] = v[a][b]; }
+            float fEigSum = w[0] + w[1] + w[2];
+            float fEigPrd = w[0] * w[1] * w[2];
+            float fEigSumProd = fEigSum * fEigSum * fEigSum;
+            S.keep = (fEigSumProd < eig_thres * fEigPrd || eig_thres < 0) ? 1 : 0;
+            S.nret = 0;
+        }
+        __syncthreads();
+        if (!S.keep) {
+            if (threadIdx.x == 0) nrows[kpi] = 0;
+            continue;
+        }
+
+        // --- primary histogram (determineCanonicalOrientation3D :2779-2817)
+        for (int n = threadIdx.x; n < nsph; n += blockDim.x) {
+            int i = c_tab.sphere[n];
+            float e[3] = { S.dx[i], S.dy[i], S.dz[i] };
+            float fEdgeMagSqr = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+            int base = -1;
+            if (fEdgeMagSqr != 0) {
+                float fEdgeMag = sqrtf(fEdgeMagSqr);
+                float u[3];
+                for (int k = 0; k < 3; k++) u[k] = e[k] * fRadius / fEdgeMag;
+                for (int k = 0; k < 3; k++) u[k] = u[k] + fRadius;
+                make_contrib((float)((double)u[0] + 0.5), (float)((double)u[1] + 0.5), (float)((double)u[2] + 0.5),
+                             fEdgeMag, &S.contrib[n * 8], base);
+            }
+            S.cbase[n] = base;
+        }
+        __syncthreads();
+        splat_histogram(S.h0, S.contrib, S.cbase, nsph);
+        blur_patch(S.h0, S.h1, S.h2, c_tab.hist_taps, c_tab.n_hist_taps);
+        find_sort_peaks(S.h2, S.psort, S.peaks, &S.np);
+        {
+            int lim = min(S.np, PD);
+            if (threadIdx.x < lim) {
+                float o3[3];
+                interp_point_patch(S.h2, S.peaks[threadIdx.x].x, S.peaks[threadIdx.x].y, S.peaks[threadIdx.x].z, o3);
+                o3[0] -= fRadius; o3[1] -= fRadius; o3[2] -= fRadius;
+                vec_norm(o3);
+                S.oriData[threadIdx.x * 3 + 0] = o3[0]; S.oriData[threadIdx.x * 3 + 1] = o3[1]; S.oriData[threadIdx.x * 3 + 2] = o3[2];
+            }
+        }
+        __syncthreads();
+
+        // --- secondary direction per strong primary peak (:2875-3033)
+        const int np = S.np;
+        const float top = np > 0 ? S.peaks[0].value : 0.0f;
+        for (int pi = 0; pi < np && pi < PD && S.nret < 30; pi++) {
+            if ((double)S.peaks[pi].value < 0.8 * (double)top) break;
+            const float p1[3] = { S.oriData[pi * 3], S.oriData[pi * 3 + 1], S.oriData[pi * 3 + 2] };
+            for (int n = threadIdx.x; n < nsph; n += blockDim.x) {
+                int i = c_tab.sphere[n];
+                float e[3] = { S.dx[i], S.dy[i], S.dz[i] };
+                float fEdgeMag = vec_mag(e);
+                int base = -1;
+                if (fEdgeMag != 0) {
+                    float u[3] = { e[0], e[1], e[2] };
+                    vec_norm(u);
+                    float fPar = vec_dot(p1, u);
+                    float perp[3];
+                    perp[0] = u[0] - fPar * p1[0];
+                    perp[1] = u[1] - fPar * p1[1];
+                    perp[2] = u[2] - fPar * p1[2];
+                    vec_norm(perp);
+                    for (int k = 0; k < 3; k++) { perp[k] = perp[k] * fRadius; perp[k] = perp[k] + fRadius; }
+                    make_contrib((float)((double)perp[0] + 0.5), (float)((double)perp[1] + 0.5), (float)((double)perp[2] + 0.5),
+                                 fEdgeMag, &S.contrib[n * 8], base);
+                }
+                S.cbase[n] = base;
+            }
+            __syncthreads();
+            splat_histogram(S.h0, S.contrib, S.cbase, nsph);
+            blur_patch(S.h0, S.h1, S.h2, c_tab.hist_taps, c_tab.n_hist_taps);
+            find_sort_peaks(S.h2, S.psort, S.peaks2, &S.np2);
+            if (threadIdx.x == 0) {
+                int nret = S.nret;
+                for (int j = 0; j < S.np2 && nret < PD && nret < 30; j++) {
+                    if (S.peaks2[j].value < 0.5f * S.peaks2[0].value) break;
+                    float p2[3], p3[3];
+                    interp_point_patch(S.h2, S.peaks2[j].x, S.peaks2[j].y, S.peaks2[j].z, p2);
+                    p2[0] -= fRadius; p2[1] -= fRadius; p2[2] -= fRadius;
+                    vec_norm(p2);
+                    float fPar = vec_dot(p1, p2);
+                    p2[0] = p2[0] - fPar * p1[0];
+                    p2[1] = p2[1] - fPar * p1[1];
+                    p2[2] = p2[2] - fPar * p1[2];
+                    vec_norm(p2);
+                    p3[0] = p1[1] * p2[2] - p1[2] * p2[1];
+                    p3[1] = -p1[0] * p2[2] + p1[2] * p2[0];
+                    p3[2] = p1[0] * p2[1] - p1[1] * p2[0];
+                    float *m = &S.rots[nret * 9];
+                    for (int k = 0; k < 3; k++) { m[k] = p1[k]; m[3 + k] = p2[k]; m[6 + k] = p3[k]; }
+                    nret++;
+                }
+                S.nret = nret;
+            }
+            __syncthreads();
+        }
+
+        // --- publish
+        const int nret = S.nret;
+        if (threadIdx.x == 0) nrows[kpi] = 1 + nret;
+        if (threadIdx.x < 3) kp_eigs[kpi * 3 + threadIdx.x] = S.eigs[threadIdx.x];
+        if (threadIdx.x < 9) kp_ori0[kpi * 9 + threadIdx.x] = S.ori0[threadIdx.x];
+        for (int i = threadIdx.x; i < nret * 9; i += blockDim.x) kp_rots[(long long)kpi * (kMaxRowsPerKp * 9) + i] = S.rots[i];
+    }
+}
+
+// Exclusive prefix sum of rows per keypoint -> first feature row of each keypoint; total -> n_features.
+__global__ void __launch_bounds__(1024) row_offsets_kernel(const int *__restrict__ nrows, const int *__restrict__ kp_count,
+                                                           int *__restrict__ row_off, int *n_features, int row_cap, int *err)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_run;
+    int n = *kp_count;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int start = 0; start < n; start += blockDim.x) {
+        int k = start + threadIdx.x;
+        int v = (k < n) ? nrows[k] : 0;
+        int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        int inc = v;
+        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int w = 0; w < 32; w++) { if (w < wid) woff += s_warp[w]; tot += s_warp[w]; }
+        if (k < n) row_off[k] = s_run + woff + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_run += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (s_run > row_cap) atomicOr(err, ERR_ROW_OVERFLOW);
+        *n_features = min(s_run, row_cap);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 3: one CTA per feature row (work item = keypoint * 12 + row): re-gather with the row's
+// orientation, descriptor loop of featExtract's main() (reference featExtract.cpp:477-505):
+// NormalizeData, descriptor, rank transform, size factor.
+// ------------------------------------------------------------------------------------------------
+struct DescribeSmem {
+    float patch[PV];
+    float dx[PV], dy[PV], dz[PV];   // SIFT: gradients -> (mag, bin); BRIEF: blur scratch
+    float inv[9];
+    float red[2];
+    float pc[64];
+    float pc2[64];
+};
+
+__global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ PyramidDesc pyr,
+                                                       const s3d_keypoint *__restrict__ kps, const int *__restrict__ kp_count,
+                                                       const int *__restrict__ nrows, const int *__restrict__ row_off,
+                                                       const float *__restrict__ kp_eigs, const float *__restrict__ kp_ori0,
+                                                       const float *__restrict__ kp_rots, const float *__restrict__ kp_patch0,
+                                                       int descriptor, float size_factor, int row_cap,
+                                                       s3d_feature *__restrict__ feats,
+                                                       float *__restrict__ dbg_patches, float *__restrict__ dbg_prerank)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DescribeSmem &S = *reinterpret_cast<DescribeSmem *>(smem_raw);
+    const int nkp = *kp_count;
+    const long long n_work = (long long)nkp * kMaxRowsPerKp;
+    for (long long wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const int kpi = (int)(wi / kMaxRowsPerKp), r = (int)(wi % kMaxRowsPerKp);
+        if (r >= nrows[kpi]) continue;
+        const int row = row_off[kpi] + r;
+        if (row >= row_cap) continue;
+        __syncthreads();
+        const s3d_keypoint kp = kps[kpi];
+        const OctaveDesc &o = pyr.oct[kp.octave];
+        const float *ori = (r == 0) ? (kp_ori0 + kpi * 9) : (kp_rots + (long long)kpi * (kMaxRowsPerKp * 9) + (r - 1) * 9);
+
+        if (r == 0) {
+            for (int i = threadIdx.x; i < PV; i += blockDim.x) S.patch[i] = kp_patch0[(long long)kpi * PV + i];
+        } else {
+            if (threadIdx.x == 0) { float m[9]; for (int q = 0; q < 9; q++) m[q] = ori[q]; invert3(m, S.inv); }
+            __syncthreads();
+            gather_patch(o.g[kp.level], o.X, o.Y, o.Z, o.pitch, kp.x, kp.y, kp.z, kp.scale, S.inv, S.patch);
+        }
+        __syncthreads();
+        if (dbg_patches) for (int i = threadIdx.x; i < PV; i += blockDim.x) dbg_patches[(long long)row * PV + i] = S.patch[i];
+
+        normalize_patch(S.patch, S.dx, S.red);
+
+        if (descriptor == S3D_DESC_SIFT) {
+            // msResampleFeaturesGradientOrientationHistogram (reference MultiScale.cpp:583-710)
+            patch_gradients(S.patch, S.dx, S.dy, S.dz);
+            for (int i = threadIdx.x; i < PV; i += blockDim.x) {
+                float e[3] = { S.dx[i], S.dy[i], S.dz[i] };
+                float fEdgeMag = vec_mag(e);
+                int bin = -1;
+                if (fEdgeMag > 0) {
+                    vec_norm(e);
+                    // dot with (+-1,+-1,+-1) in the reference's bin order, first maximum wins
+                    float best = 0.0f;
+                    for (int k = 0; k < 8; k++) {
+                        float sx = (k & 4) ? -1.0f : 1.0f, sy = (k & 2) ? -1.0f : 1.0f, sz = (k & 1) ? -1.0f : 1.0f;
+                        float fDot = sx * e[0] + sy * e[1] + sz * e[2];
+                        if (k == 0 || fDot > best) { best = fDot; bin = k; }
+                    }
+                }
+                S.dx[i] = fEdgeMag;
+                S.dy[i] = __int_as_float(bin);
+            }
+            __syncthreads();
+            if (threadIdx.x < 64) {
+                // thread owns PC[((sz*2+sy)*2+sx)*8 + k]; walks the voxels that can reach it in raster order
+                const int k = threadIdx.x & 7, sx = (threadIdx.x >> 3) & 1, sy = (threadIdx.x >> 4) & 1, sz = (threadIdx.x >> 5) & 1;
+                const int x0 = sx ? 5 : 0, y0 = sy ? 5 : 0, z0 = sz ? 5 : 0;
+                float acc = 0.0f;
+                for (int z = z0; z <= z0 + 5; z++) {
+                    float wz = sz ? (1.0f - c_tab.desc_w[z]) : c_tab.desc_w[z];
+                    for (int y = y0; y <= y0 + 5; y++) {
+                        float wy = sy ? (1.0f - c_tab.desc_w[y]) : c_tab.desc_w[y];
+                        for (int x = x0; x <= x0 + 5; x++) {
+                            int i = (z * PD + y) * PD + x;
+                            if (__float_as_int(S.dy[i]) == k) {
+                                float wx = sx ? (1.0f - c_tab.desc_w[x]) : c_tab.desc_w[x];
+                                acc = acc + S.dx[i] * wx * wy * wz;
+                            }
+                        }
+                    }
+                }
+                S.pc[threadIdx.x] = acc;
+            }
+            __syncthreads();
+            // msNormalizeDataPositive (reference MultiScale.cpp:1580-1611)
+            if (threadIdx.x == 0) {
+                float fMin = 100000;
+                for (int i = 0; i < 64; i++) if (S.pc[i] < fMin) fMin = S.pc[i];
+                float fSumSqr = 0.0f;
+                for (int i = 0; i < 64; i++) { float v = S.pc[i] - fMin; S.pc[i] = v; fSumSqr = fSumSqr + v * v; }
+                float fDiv = 1.0f / sqrtf(fSumSqr);
+                for (int i = 0; i < 64; i++) S.pc[i] = S.pc[i] * fDiv;
+            }
+            __syncthreads();
+        } else {
+            // msResampleFeaturesBRIEF (reference MultiScale.cpp:989-1049), blur with CPU semantics
+            blur_patch(S.patch, S.dy, S.dx, c_tab.brief_taps, c_tab.n_brief_taps);
+            if (threadIdx.x < 64) {
+                float d = S.dx[c_tab.brief_a[threadIdx.x]] - S.dx[c_tab.brief_b[threadIdx.x]];
+                float v;
+                if (descriptor == S3D_DESC_BRIEF) v = (d < 0) ? 1.0f : 0.0f;
+                else if (descriptor == S3D_DESC_RRIEF) v = d;
+                else v = d / c_tab.brief_dist[threadIdx.x];
+                S.pc[threadIdx.x] = v;
+            }
+            __syncthreads();
+        }
+        if (dbg_prerank && threadIdx.x < 64) dbg_prerank[(long long)row * 64 + threadIdx.x] = S.pc[threadIdx.x];
+
+        // NormalizeDataRankedPCs (reference MultiScale.cpp:207-233, ties by index :3148-3176)
+        if (threadIdx.x < 64) {
+            float v = S.pc[threadIdx.x];
+            int rank = 0;
+            for (int j = 0; j < 64; j++) {
+                float u = S.pc[j];
+                rank += (u < v) || (u == v && j < (int)threadIdx.x);
+            }
+            S.pc2[threadIdx.x] = (float)rank;
+        }
+        __syncthreads();
+
+        // geometry: octave rescale (reference MultiScale.cpp:531-543) then featExtract's size factor (:502-505)
+        s3d_feature *f = feats + row;
+        if (threadIdx.x == 0) {
+            float fFactor = 1.0f;
+            for (int q = 0; q < kp.octave; q++) fFactor = fFactor * 2.0f;
+            float sc = kp.scale * fFactor;
+            float x = kp.x * fFactor + 0.0f, y = kp.y * fFactor + 0.0f, z = kp.z * fFactor + 0.0f;
+            f->flag = (kp.is_max ? 0x10u : 0u) | (r > 0 ? 0x20u : 0u);
+            f->x = x * size_factor; f->y = y * size_factor; f->z = z * size_factor; f->scale = sc * size_factor;
+            for (int q = 0; q < 3; q++) f->eigs[q] = kp_eigs[kpi * 3 + q];
+            for (int q = 0; q < 9; q++) f->ori[q] = ori[q];
+        }
+        if (threadIdx.x < 64) f->pc[threadIdx.x] = S.pc2[threadIdx.x];
+    }
+}
+
+} // namespace s3d

@@ -1,0 +1,359 @@
+// s3d_voxel.cuh -- voxel-parallel stages of the pyramid for sm_100a: separable Gaussian blur
+// (x pass + strided "march" pass used for y and z, DoG fused into the z pass), 2x2x2 subsample,
+// -2+/-2- resampling, 53-neighbour extrema detection, candidate ordering.
+//
+// Arithmetic contract (checked bit-for-bit by tests/): every product and every sum is rounded to
+// fp32 separately and taps are accumulated left to right, exactly like the reference CPU loop
+// filter_1d (reference GaussBlur3D.cpp:43-61).  The translation unit is compiled with -fmad=false
+// so the compiler never contracts a*b+c.  Nothing here is a contraction over a long axis, so no
+// tensor cores: these are streaming stencils bounded by HBM/L2 bandwidth and FP32 issue rate.
+//
+// Layout: element (x,y,z) at p[(z*Y+y)*pitch + x]; padding columns X..pitch-1 are kept at zero.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/s3d.h"
+
+namespace s3d {
+
+constexpr int kMaxFastR = 8;      // widest templated radius (17 taps, sigma 3.09 of the octave schedule)
+constexpr int kMaxTaps = 129;
+
+struct TapsSmall { float w[2 * kMaxFastR + 1]; };
+struct TapsAny { int n; float w[kMaxTaps]; };
+
+// ---------------------------------------------------------------------------------------------
+// x pass.  The volume is treated as one linear array of pitch*Y*Z floats (rows are contiguous and
+// pitch % 8 == 0, so an 8-float chunk never straddles a row).  Each thread produces 8 consecutive
+// outputs from a register window loaded with aligned 128-bit loads; neighbouring threads overlap in
+// L1.  Window groups that fall left of x=0 or right of x=pitch-1 are zero (zero padding).
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(256) blur_x_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                     int pitch, int X, long long n_chunks,
+                                                     const __grid_constant__ TapsSmall taps)
+{
+    constexpr int RP = (R + 3) & ~3;
+    constexpr int NW = 8 + 2 * RP;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_chunks) return;
+    long long base = t * 8;
+    int x0 = (int)(base % pitch);
+    float win[NW];
+#pragma unroll
+    for (int g = 0; g < NW / 4; g++) {
+        int x = x0 - RP + 4 * g;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x >= 0 && x < pitch) v = __ldg(reinterpret_cast<const float4 *>(in + base - RP + 4 * g));
+        win[4 * g + 0] = v.x; win[4 * g + 1] = v.y; win[4 * g + 2] = v.z; win[4 * g + 3] = v.w;
+    }
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        float acc = taps.w[0] * win[k + RP - R];
+#pragma unroll
+        for (int j = 1; j <= 2 * R; j++) acc = acc + taps.w[j] * win[k + j + RP - R];
+        o[k] = (x0 + k < X) ? acc : 0.0f;
+    }
+    float4 *dst = reinterpret_cast<float4 *>(out + base);
+    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+}
+
+// Scalar x pass for any pitch / radius (slow path; identical results).
+__global__ void blur_x_generic_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                      int pitch, int X, long long n_elems, const __grid_constant__ TapsAny taps)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_elems) return;
+    int x = (int)(i % pitch);
+    int r = taps.n / 2;
+    float acc = 0.0f;
+    if (x < X) {
+        for (int j = 0; j < taps.n; j++) {
+            int p = x + j - r;
+            float v = (p >= 0 && p < X) ? in[i + j - r] : 0.0f;
+            acc = acc + taps.w[j] * v;
+        }
+    }
+    out[i] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// March pass (y or z).  Threads are laid along the contiguous direction (one column each) and walk
+// the blur axis through a segment [a0, a1).  Scatter form: the T = 2R+1 partial sums of the outputs
+// around the current input live in registers; each input value is loaded once, multiplied into all
+// T accumulators (T independent FMUL+FADD pairs -> ILP), and the oldest accumulator -- which has now
+// received its taps in the order j = 0..2R, the reference's left-to-right order -- is stored.
+// The loop is unrolled by T so accumulator indices are static (no register shuffling).
+// Columns are flattened so every lane is busy: column q -> (other = q / w_inner, inner = q % w_inner),
+// first element at other*other_stride + inner.
+//   y pass: w_inner = pitch,   n_cols = pitch*Z,  other_stride = pitch*Y, stride = pitch,   len = Y
+//   z pass: w_inner = pitch*Y, n_cols = pitch*Y,                          stride = pitch*Y, len = Z
+// DOG: also writes dog = prev - out (prev = the blur's input volume), i.e. fioMultSum(prev, out, -1).
+// ---------------------------------------------------------------------------------------------
+template <int R, bool DOG>
+__global__ void __launch_bounds__(128) blur_march_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                         const float *__restrict__ prev, float *__restrict__ dog,
+                                                         long long n_cols, long long w_inner, long long other_stride,
+                                                         long long stride, int len, int seg_len,
+                                                         const __grid_constant__ TapsSmall taps)
+{
+    constexpr int T = 2 * R + 1;
+    long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_cols) return;
+    long long other = q / w_inner;
+    long long col = other * other_stride + (q - other * w_inner);
+    int a0 = blockIdx.y * seg_len;
+    int a1 = min(len, a0 + seg_len);
+    int n_in = (a1 - a0) + 2 * R;
+    const float *src = in + col;
+    float acc[T];
+#pragma unroll
+    for (int s = 0; s < T; s++) acc[s] = 0.0f;
+    for (int ub = 0; ub < n_in; ub += T) {
+        float v[T];
+#pragma unroll
+        for (int s = 0; s < T; s++) {
+            int i = a0 - R + ub + s;
+            v[s] = (i >= 0 && i < len && ub + s < n_in) ? __ldg(src + (long long)i * stride) : 0.0f;
+        }
+#pragma unroll
+        for (int s = 0; s < T; s++) {
+            acc[s] = taps.w[0] * v[s];
+#pragma unroll
+            for (int j = 1; j <= 2 * R; j++) acc[(s - j + 2 * T) % T] = acc[(s - j + 2 * T) % T] + taps.w[j] * v[s];
+            int c = a0 + ub + s - 2 * R;
+            if (c >= a0 && c < a1) {
+                float g = acc[(s + 1) % T];
+                long long idx = col + (long long)c * stride;
+                out[idx] = g;
+                if (DOG) dog[idx] = __ldg(prev + idx) + (-1.0f) * g;
+            }
+        }
+    }
+}
+
+// Generic march (any radius): gather form straight from global memory.
+template <bool DOG>
+__global__ void blur_march_generic_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                          const float *__restrict__ prev, float *__restrict__ dog,
+                                          long long n_cols, long long w_inner, long long other_stride,
+                                          long long stride, int len, const __grid_constant__ TapsAny taps)
+{
+    long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_cols) return;
+    long long other = q / w_inner;
+    long long col = other * other_stride + (q - other * w_inner);
+    int r = taps.n / 2;
+    for (int c = blockIdx.y; c < len; c += gridDim.y) {
+        float acc = 0.0f;
+        for (int j = 0; j < taps.n; j++) {
+            int p = c + j - r;
+            float v = (p >= 0 && p < len) ? in[col + (long long)p * stride] : 0.0f;
+            acc = acc + taps.w[j] * v;
+        }
+        long long idx = col + (long long)c * stride;
+        out[idx] = acc;
+        if (DOG) dog[idx] = prev[idx] + (-1.0f) * acc;
+    }
+}
+
+// out = a + (-1)*b   (fioMultSum, reference FeatureIO.cpp:1950-1987)
+__global__ void dog_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + (-1.0f) * b[i];
+}
+
+// 2x2x2 mean (fioSubSampleInterpolate, reference FeatureIO.cpp:1474-1554); one thread per output voxel
+// (including output padding columns, written as zero).
+__global__ void subsample_kernel(const float *__restrict__ in, int X, int Y, int Z, int pitch,
+                                 float *__restrict__ out, int ox, int oy, int oz, int opitch)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    int z = blockIdx.z;
+    if (x >= opitch || y >= oy) return;
+    float r = 0.0f;
+    if (x < ox) {
+        const float *p0 = in + ((long long)(2 * z) * Y + 2 * y) * pitch + 2 * x;
+        const float *p1 = p0 + (long long)Y * pitch;
+        float s = 0.0f;
+        s = s + (((p0[0] + p0[pitch]) + p0[1]) + p0[pitch + 1]);
+        if (2 * z + 1 < Z) {
+            s = s + (((p1[0] + p1[pitch]) + p1[1]) + p1[pitch + 1]);
+            s = s * 0.125f;
+        } else {
+            s = s * 0.25f;
+        }
+        r = s;
+    }
+    out[((long long)z * oy + y) * opitch + x] = r;
+}
+
+// fioSubSample2DCenterPixel (-2-), reference FeatureIO.cpp:1670-1714.
+__global__ void halve_kernel(const float *__restrict__ in, int X, int Y, int Z, int pitch,
+                             float *__restrict__ out, int ox, int oy, int oz, int opitch)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    int z = blockIdx.z;
+    if (x >= opitch || y >= oy) return;
+    float r = 0.0f;
+    if (x < ox) {
+        const float *p0 = in + ((long long)(2 * z) * Y + 2 * y) * pitch + 2 * x;
+        const float *p1 = p0 + (long long)Y * pitch;
+        float v = 0.0f;
+        v = v + p0[0];
+        v = v + p1[0];
+        v = v + p0[pitch];
+        v = v + p1[pitch];
+        v = v + p0[1];
+        v = v + p1[1];
+        v = v + p0[pitch + 1];
+        v = v + p1[pitch + 1];
+        r = v / 8.0f;
+    }
+    out[((long long)z * oy + y) * opitch + x] = r;
+}
+
+// fioDoubleSize (-2+), reference FeatureIO.cpp:2452-2548; one thread per OUTPUT voxel.  The
+// reference scatters 2x2x2 blocks per input voxel; every output voxel is written exactly once
+// (dims are doubled exactly), by the input voxel (x/2,y/2,z/2) with sub-position (x&1,y&1,z&1).
+__global__ void double_kernel(const float *__restrict__ in, int X, int Y, int Z, int pitch,
+                              float *__restrict__ out, int opitch)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    int z = blockIdx.z;
+    int DX = 2 * X, DY = 2 * Y;
+    if (x >= opitch || y >= DY) return;
+    float r = 0.0f;
+    if (x < DX) {
+        int sx = x >> 1, sy = y >> 1, sz = z >> 1;
+        int bx = x & 1, by = y & 1, bz = z & 1;
+        float lo[2][2][2];
+#pragma unroll
+        for (int zz = 0; zz < 2; zz++)
+#pragma unroll
+            for (int yy = 0; yy < 2; yy++)
+#pragma unroll
+                for (int xx = 0; xx < 2; xx++) {
+                    int dz = (sz + zz >= Z) ? 0 : zz, dy = (sy + yy >= Y) ? 0 : yy, dx = (sx + xx >= X) ? 0 : xx;
+                    lo[zz][yy][xx] = in[((long long)(sz + dz) * Y + (sy + dy)) * pitch + (sx + dx)];
+                }
+        int code = bz * 4 + by * 2 + bx;
+        switch (code) {
+        case 0: r = lo[0][0][0]; break;
+        case 4: r = 0.5f * (lo[0][0][0] + lo[1][0][0]); break;
+        case 2: r = 0.5f * (lo[0][0][0] + lo[0][1][0]); break;
+        case 1: r = 0.5f * (lo[0][0][0] + lo[0][0][1]); break;
+        case 6: r = 0.25f * (((lo[0][0][0] + lo[1][0][0]) + lo[0][1][0]) + lo[1][1][0]); break;
+        case 3: r = 0.25f * (((lo[0][0][0] + lo[0][1][0]) + lo[0][0][1]) + lo[0][1][1]); break;
+        case 5: r = 0.25f * (((lo[0][0][0] + lo[1][0][0]) + lo[0][0][1]) + lo[1][0][1]); break;
+        default:
+            r = 0.125f * (((((((lo[0][0][0] + lo[0][0][1]) + lo[0][1][0]) + lo[0][1][1]) + lo[1][0][0]) + lo[1][0][1]) + lo[1][1][0]) + lo[1][1][1]);
+            break;
+        }
+    }
+    out[((long long)z * DY + y) * opitch + x] = r;
+}
+
+// dense (pitch == X) <-> pitched copies with zeroed padding
+__global__ void pad_rows_kernel(const float *__restrict__ in, int X, long long rows, float *__restrict__ out, int pitch)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * pitch) return;
+    long long row = i / pitch;
+    int x = (int)(i - row * pitch);
+    out[i] = (x < X) ? in[row * X + x] : 0.0f;
+}
+
+__global__ void unpad_rows_kernel(const float *__restrict__ in, int pitch, long long rows, float *__restrict__ out, int X)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * X) return;
+    long long row = i / X;
+    int x = (int)(i - row * X);
+    out[i] = in[row * pitch + x];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Detection (reference MultiScale.cpp:2260-2524): a voxel of the centre DoG is a candidate when it
+// is strictly above (below) its 26 neighbours and all 27 voxels of the finer DoG.  One thread per
+// interior voxel; the x neighbours reject most voxels after two loads, the rest exit as soon as a
+// comparison fails, so the pass costs little more than reading the centre volume once.
+// Survivors are appended through an atomic counter; order_candidates_kernel restores raster order.
+// ---------------------------------------------------------------------------------------------
+struct CandList {
+    s3d_cand *items;
+    int *count;
+};
+
+__global__ void __launch_bounds__(256) detect_kernel(const float *__restrict__ finer, const float *__restrict__ centre,
+                                                     int X, int Y, int Z, int pitch,
+                                                     CandList mins, CandList maxs, int cap)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    int y = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    int z = blockIdx.z + 1;
+    if (x > X - 2 || y > Y - 2 || z > Z - 2) return;
+    long long plane = (long long)pitch * Y;
+    long long i = (long long)z * plane + (long long)y * pitch + x;
+    float c = centre[i];
+    float l = centre[i - 1], r = centre[i + 1];
+    bool mx = (l < c) && (r < c);
+    bool mn = (l > c) && (r > c);
+    if (!(mx || mn)) return;
+#pragma unroll 1
+    for (int dz = -1; dz <= 1 && (mx || mn); dz++)
+#pragma unroll 1
+        for (int dy = -1; dy <= 1 && (mx || mn); dy++) {
+            const float *row = centre + i + dz * plane + dy * pitch;
+            float a = row[-1], b = row[0], d = row[1];
+            if (dz == 0 && dy == 0) b = a; // skip self
+            mx = mx && (a < c) && (b < c) && (d < c);
+            mn = mn && (a > c) && (b > c) && (d > c);
+        }
+    if (!(mx || mn)) return;
+#pragma unroll 1
+    for (int dz = -1; dz <= 1 && (mx || mn); dz++)
+#pragma unroll 1
+        for (int dy = -1; dy <= 1 && (mx || mn); dy++) {
+            const float *row = finer + i + dz * plane + dy * pitch;
+            float a = row[-1], b = row[0], d = row[1];
+            mx = mx && (a < c) && (b < c) && (d < c);
+            mn = mn && (a > c) && (b > c) && (d > c);
+        }
+    if (mx) {
+        int k = atomicAdd(maxs.count, 1);
+        if (k < cap) maxs.items[k] = s3d_cand{ x, y, z, c };
+    }
+    if (mn) {
+        int k = atomicAdd(mins.count, 1);
+        if (k < cap) mins.items[k] = s3d_cand{ x, y, z, c };
+    }
+}
+
+// Rank-by-counting sort of a candidate list into raster order (keys are unique voxel indices).
+// When the list overflowed (count > cap) the retained subset depends on atomic order; the
+// engine reports S3D_ERR_CAPACITY in that case.
+__global__ void order_candidates_kernel(const s3d_cand *__restrict__ in, const int *__restrict__ count,
+                                        s3d_cand *__restrict__ out, int X, int Y, int cap)
+{
+    int n = min(*count, cap);
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    s3d_cand me = in[k];
+    long long key = ((long long)me.z * Y + me.y) * X + me.x;
+    int rank = 0;
+    for (int j = 0; j < n; j++) {
+        s3d_cand o = in[j];
+        long long kj = ((long long)o.z * Y + o.y) * X + o.x;
+        rank += (kj < key);
+    }
+    out[rank] = me;
+}
+
+} // namespace s3d

@@ -1,0 +1,183 @@
+/*
+ * s3d.h -- C-ABI of the B200-native 3D SIFT engine (lib3dsift_b200.so).
+ *
+ * This is the drop-in boundary for the featExtract hot path of CarluerJB/3D_SIFT_CUDA.  It replaces
+ * the reference's cuda_common layer (four C++ launchers taking FEATUREIO& + raw cudart calls scattered
+ * through src_common) with plain pointers and sizes; each entry point cites what it replaces.
+ *   R/ = 3dsift_cleanup-softVote_App_Weight_SoftMax/ in the reference tree.
+ *
+ * Conventions
+ *   - Volumes are fp32, x fastest.  A volume is described by (X, Y, Z, pitch): element (x,y,z) lives at
+ *     p[(z*Y + y)*pitch + x], pitch >= X (pitch == X is the reference's dense FEATUREIO layout,
+ *     R/src_common/FeatureIO.cpp:739).  Columns X..pitch-1 are padding and are kept at zero by every
+ *     stage.  Fast paths need pitch % 8 == 0 and 32-byte aligned bases; anything else takes a
+ *     scalar path with identical results.
+ *   - All device work is stream-ordered on the context's stream (or the stream given to
+ *     s3d_ctx_create_on_stream, e.g. torch's current stream); stage-level calls never synchronise.
+ *   - Every call returns an s3d_status; nothing ever calls exit() (the reference's gpuErrchk does,
+ *     R/cuda_common/SIFT_cuda_Tools.cuh:13-21).  s3d_last_error() gives the text.
+ *   - There is no CPU fallback: without a usable CUDA device s3d_ctx_create fails.
+ *   - Arithmetic is the reference CPU path's, operation for operation (no FMA contraction, same
+ *     summation order), so results are bit-identical to featExtract without -d.
+ */
+#ifndef S3D_H
+#define S3D_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S3D_VERSION 0x000100
+
+typedef enum s3d_status {
+    S3D_OK = 0,
+    S3D_ERR_INVALID = 1,   /* bad argument (null pointer, dimension mismatch: the reference returns 0) */
+    S3D_ERR_CUDA = 2,      /* CUDA runtime error (the reference prints GPUassert and exits) */
+    S3D_ERR_NOMEM = 3,     /* allocation failed (the reference: "insufficient memory") */
+    S3D_ERR_CAPACITY = 4,  /* candidate / keypoint / feature capacity exceeded (the reference overruns
+                              its X0*Y0 arrays silently, R/src_common/MultiScale.cpp:255-267) */
+    S3D_ERR_UNSUPPORTED = 5
+} s3d_status;
+
+typedef struct s3d_ctx s3d_ctx;
+
+/* Feature record, layout-compatible with Feature3DInfo (R/src_common/MultiScale.h:111-129). */
+typedef struct s3d_feature {
+    unsigned int flag;   /* 0x10 = maximum (INFO_FLAG_MIN0MAX1), 0x20 = reoriented (INFO_FLAG_REORIENT) */
+    float x, y, z, scale;
+    float ori[9];        /* row-major 3x3 */
+    float eigs[3];
+    float pc[64];        /* descriptor: ranks 0..63 stored as float, as the reference does */
+} s3d_feature;
+
+/* Candidate record = LOCATION_VALUE_XYZ (R/src_common/LocationValue.h:41-47). */
+typedef struct s3d_cand {
+    int x, y, z;
+    float value;
+} s3d_cand;
+
+/* A refined keypoint before orientation assignment (octave coordinates, +0.5 applied;
+ * R/src_common/MultiScale.cpp:1372-1386). */
+typedef struct s3d_keypoint {
+    int octave, level, is_max;
+    int ix, iy, iz;
+    float x, y, z, scale;
+} s3d_keypoint;
+
+enum { S3D_DESC_SIFT = 0, S3D_DESC_BRIEF = 1, S3D_DESC_RRIEF = 2, S3D_DESC_NRRIEF = 3 };
+
+/* Options of one extraction = featExtract's command line (R/featExtract/featExtract.cpp:299-350,
+ * README -b/-br/-bn). */
+typedef struct s3d_params {
+    int double_mode;     /* 0, +1 (-2+ : double the input, features scaled by 1/2), -1 (-2- : halve) */
+    int descriptor;      /* S3D_DESC_* ; featExtract default is S3D_DESC_SIFT (brief=0, featExtract.cpp:474) */
+    float eig_thres;     /* structure-tensor test, 140 in featExtract (featExtract.cpp:297); < 0 disables */
+    int max_keypoints;   /* 0 = default (16384) */
+    int max_features;    /* 0 = default (8 * max_keypoints) */
+    int keep_patches;    /* debug: keep the 11^3 patch of every feature row (s3d_get_patches) */
+} s3d_params;
+
+/* ---- context ------------------------------------------------------------------------------------
+ * Replaces cudaSetDevice/cudaMalloc/cudaFree scattered through src_common
+ * (R/src_common/FeatureIO.cpp:384-421, 527-530) and check_best_device (featExtract.cpp:237-263).
+ * A context owns one device, one stream, and every buffer of the pyramid; it is not thread-safe,
+ * use one context per host thread (contexts are independent). */
+s3d_status s3d_ctx_create(int device, s3d_ctx **ctx);
+s3d_status s3d_ctx_create_on_stream(int device, void *cuda_stream, s3d_ctx **ctx);
+void s3d_ctx_destroy(s3d_ctx *ctx);
+const char *s3d_last_error(const s3d_ctx *ctx);
+int s3d_device_count(void);
+s3d_status s3d_sync(s3d_ctx *ctx);
+void *s3d_stream(s3d_ctx *ctx);
+
+/* ---- Gaussian taps (host arithmetic, as in the reference) --------------------------------------
+ * calculate_gaussian_filter_size + generate_gaussian_filter1d + normalisation
+ * (R/src_common/GaussianMask.cpp:12-57, 241-265; R/src_common/GaussBlur3D.cpp:1174-1206).
+ * Returns the tap count (odd), or -needed if cap is too small. */
+int s3d_gaussian_taps(float sigma, float *taps, int cap);
+
+/* ---- stage level: drop-ins for the four dispatch sites ------------------------------------------
+ * All pointers are DEVICE pointers. */
+
+/* blur_3d_simpleborders_CUDA_Row_Col_Shared_mem (R/cuda_common/SIFT_cuda_Tools.cuh:69-76,
+ * called from R/src_common/GaussBlur3D.cpp:1244).  Separable correlation, zero padding, x then y
+ * then z.  d_in is NOT modified (the reference clobbers it).  d_tmp: scratch of the same size.
+ * If d_dog != NULL, also writes d_dog = d_in - d_out (fioCudaMultSum fused into the last pass). */
+s3d_status s3d_blur3d(s3d_ctx *ctx, const float *d_in, float *d_tmp, float *d_out,
+                      int X, int Y, int Z, int pitch, const float *h_taps, int ntaps, float *d_dog);
+
+/* fioCudaMultSum with m = -1 (R/cuda_common/SIFT_cuda_Tools.cuh:213-217, called from
+ * R/src_common/FeatureIO.cpp:1942): d_out = d_a - d_b over Z*Y*pitch elements. */
+s3d_status s3d_dog(s3d_ctx *ctx, const float *d_a, const float *d_b, float *d_out,
+                   int X, int Y, int Z, int pitch);
+
+/* SubSampleInterpolateCuda (SIFT_cuda_Tools.cuh:202-205, called from FeatureIO.cpp:1559):
+ * 2x2x2 mean, output dims floor(X/2) etc. with its own pitch. */
+s3d_status s3d_subsample2(s3d_ctx *ctx, const float *d_in, int X, int Y, int Z, int pitch,
+                          float *d_out, int out_pitch);
+
+/* detectExtrema4D_test_cuda (SIFT_cuda_Tools.cuh:32-38, called from R/src_common/MultiScale.cpp:1531).
+ * Writes candidates in raster order (z, y, x), minima and maxima separately; counts are device ints.
+ * Lists are truncated at cap (the counts still report the true totals). */
+s3d_status s3d_detect(s3d_ctx *ctx, const float *d_finer, const float *d_centre,
+                      int X, int Y, int Z, int pitch,
+                      s3d_cand *d_min, int *d_n_min, s3d_cand *d_max, int *d_n_max, int cap);
+
+/* fioDoubleSize / fioSubSample2DCenterPixel, the -2+ / -2- pre-steps
+ * (R/src_common/FeatureIO.cpp:2452-2548, 1670-1714; host loops in the reference). */
+s3d_status s3d_double_size(s3d_ctx *ctx, const float *d_in, int X, int Y, int Z, int pitch,
+                           float *d_out, int out_pitch);
+s3d_status s3d_halve_size(s3d_ctx *ctx, const float *d_in, int X, int Y, int Z, int pitch,
+                          float *d_out, int out_pitch);
+
+/* ---- pipeline level: what featExtract -dN calls --------------------------------------------------
+ * Replaces msGeneratePyramidDOG3D_efficient (R/featExtract/featExtract.cpp:409,
+ * R/src_common/MultiScale.cpp:236-570) plus the descriptor loop (featExtract.cpp:474-505).
+ *
+ * s3d_extract        : volume is a dense HOST array (X*Y*Z floats); H2D, compute and D2H of the
+ *                      result are all inside the call.  *out is malloc'ed; release with s3d_free.
+ * s3d_extract_device : volume is a dense DEVICE array; enqueues the whole path on the stream and
+ *                      returns without synchronising; results stay on the device until
+ *                      s3d_fetch_features.  This is the form the throughput benchmark times.
+ */
+s3d_status s3d_extract(s3d_ctx *ctx, const float *h_volume, int X, int Y, int Z,
+                       const s3d_params *params, s3d_feature **out, int *n_out);
+s3d_status s3d_extract_device(s3d_ctx *ctx, const float *d_volume, int X, int Y, int Z,
+                              const s3d_params *params);
+/* Stage the next volume from host memory (pinned or pageable) into the context's input slot
+ * asynchronously, then run s3d_extract_device on it. */
+s3d_status s3d_extract_host_async(s3d_ctx *ctx, const float *h_volume, int X, int Y, int Z,
+                                  const s3d_params *params);
+/* Synchronise, then copy the last extraction's feature rows to the host (malloc'ed). */
+s3d_status s3d_fetch_features(s3d_ctx *ctx, s3d_feature **out, int *n_out);
+/* Synchronise and return only the counts of the last extraction. */
+s3d_status s3d_fetch_counts(s3d_ctx *ctx, int *n_keypoints, int *n_features);
+/* Device-resident results of the last extraction (valid until the next one). */
+s3d_status s3d_result_device(s3d_ctx *ctx, const s3d_feature **d_features, const int **d_n_features);
+void s3d_free(void *p);
+
+/* ---- introspection for parity tests --------------------------------------------------------------
+ * Pyramid of the last extraction: Gaussian level g (0..5) or DoG level (0..4) of an octave, copied
+ * densely (X*Y*Z floats) to host memory.  dims receives X, Y, Z of that octave. */
+int s3d_num_octaves(s3d_ctx *ctx);
+s3d_status s3d_get_level(s3d_ctx *ctx, int octave, int is_dog, int level, float *h_out, int dims[3]);
+/* Refined keypoints (after validation and the bounds test) in output order. */
+s3d_status s3d_get_keypoints(s3d_ctx *ctx, s3d_keypoint **out, int *n_out);
+/* With params.keep_patches: n_features * 1331 floats, the 11^3 patch of each row as the pyramid
+ * stage leaves it (before the descriptor loop's NormalizeData), and the 64 pre-rank values. */
+s3d_status s3d_get_patches(s3d_ctx *ctx, float **patches, float **prerank, int *n_out);
+/* Number of kernel launches (graph nodes included) issued by the last extraction. */
+int s3d_last_launch_count(s3d_ctx *ctx);
+
+/* ---- feature file (kept host code) ----------------------------------------------------------------
+ * msFeature3DVectorOutputText (R/src_common/MultiScale.h:386-474) with the three comment lines
+ * featExtract writes (R/featExtract/featExtract.cpp:542-575). */
+s3d_status s3d_write_features_text(const char *path, const s3d_feature *feats, int n, float eig_thres,
+                                   int n_comments, const char *const *comments);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S3D_H */

@@ -1,0 +1,158 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (include/s3d.h), against the oracle
+(oracle/sift3d_oracle.c) on the same seeded inputs.  Bit-exact everywhere: the kernels reproduce the
+reference CPU arithmetic operation for operation, so tolerances are zero ULP for voxels, geometry and
+pre-rank descriptors, and integer equality for candidate indices and ranks.  (north_star allows
+<=1e-5 relative for floats; these tests hold the stricter bar.)
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def to_dev(vol, pitch=None):
+    import torch
+    Z, Y, X = vol.shape
+    pitch = pitch or ((X + 7) // 8 * 8)
+    buf = np.zeros((Z, Y, pitch), np.float32)
+    buf[:, :, :X] = vol
+    return torch.from_numpy(buf).cuda()
+
+
+def from_dev(t, X):
+    return t.cpu().numpy()[:, :, :X].copy()
+
+
+@pytest.mark.parametrize("sigma", [0.5, 0.95, 1.2263, 1.2490, 1.5199, 1.5450, 1.9466, 2.4525, 3.0900, 4.0])
+def test_taps_bit_exact(pkg, oracle, sigma):
+    assert (bits(pkg.gaussian_taps(sigma)) == bits(oracle.taps(sigma))).all()
+
+
+@pytest.mark.parametrize("shape_xyz", [(48, 40, 36), (37, 29, 23), (64, 64, 64), (9, 7, 5)])
+@pytest.mark.parametrize("sigma", [0.5, 1.2263, 1.5199, 1.9466, 2.4525, 3.0900, 4.0])
+def test_blur_bit_exact(pkg, oracle, engine, shape_xyz, sigma):
+    import torch
+    vol = pkg.phantom.blob_phantom(shape_xyz, seed=3, nblobs=20)
+    X = shape_xyz[0]
+    want = oracle.blur(vol, sigma)
+    d_in = to_dev(vol)
+    d_tmp, d_out, d_dog = torch.zeros_like(d_in), torch.zeros_like(d_in), torch.zeros_like(d_in)
+    engine.blur3d(d_in, d_tmp, d_out, X, pkg.gaussian_taps(sigma), d_dog)
+    engine.sync()
+    assert (bits(from_dev(d_out, X)) == bits(want)).all()
+    assert (bits(from_dev(d_dog, X)) == bits(oracle.dog(vol, want))).all()
+    assert (bits(from_dev(d_in, X)) == bits(vol)).all(), "input must not be clobbered"
+    assert float(d_out[:, :, X:].abs().sum()) == 0.0, "padding columns must stay zero"
+
+
+def test_blur_unaligned_pitch_takes_scalar_path(pkg, oracle, engine):
+    import torch
+    vol = pkg.phantom.blob_phantom((21, 17, 13), seed=5, nblobs=8)
+    d_in = torch.from_numpy(vol).cuda()   # pitch == X == 21: the reference's dense layout
+    d_tmp, d_out = torch.zeros_like(d_in), torch.zeros_like(d_in)
+    engine.blur3d(d_in, d_tmp, d_out, 21, pkg.gaussian_taps(1.5199))
+    engine.sync()
+    assert (bits(d_out.cpu().numpy()) == bits(oracle.blur(vol, 1.5199))).all()
+
+
+def test_dog_subsample_resize_bit_exact(pkg, oracle, engine):
+    import torch
+    vol = pkg.phantom.blob_phantom((45, 38, 33), seed=7, nblobs=25)
+    vol2 = oracle.blur(vol, 1.5)
+    X = 45
+    a, b = to_dev(vol), to_dev(vol2)
+    out = torch.zeros_like(a)
+    engine.dog(a, b, out, X)
+    engine.sync()
+    assert (bits(from_dev(out, X)) == bits(oracle.dog(vol, vol2))).all()
+    for name, num, den in (("subsample2", 1, 2), ("halve_size", 1, 2), ("double_size", 2, 1)):
+        want = getattr(oracle, {"subsample2": "subsample", "halve_size": "halve_size", "double_size": "double_size"}[name])(vol)
+        oz, oy, ox = want.shape
+        d_out = torch.full((oz, oy, (ox + 7) // 8 * 8), 7.0, dtype=torch.float32, device="cuda")
+        getattr(engine, name)(a, X, d_out)
+        engine.sync()
+        assert (bits(from_dev(d_out, ox)) == bits(want)).all(), name
+        assert float(d_out[:, :, ox:].abs().sum()) == 0.0, name
+
+
+def test_detect_bit_exact_and_ordered(pkg, oracle, engine):
+    vol = pkg.phantom.blob_phantom((64, 56, 48), seed=11, nblobs=80)
+    g1 = oracle.blur(vol, 1.5199)
+    g2 = oracle.blur(g1, 1.2263)
+    g3 = oracle.blur(g2, 1.5450)
+    d0, d1 = oracle.dog(g1, g2), oracle.dog(g2, g3)
+    want_min, want_max = oracle.detect(d0, d1)
+    got_min, got_max = engine.detect(to_dev(d0), to_dev(d1), 64)
+    assert len(want_min) + len(want_max) > 10
+    assert got_min.tobytes() == want_min.tobytes()
+    assert got_max.tobytes() == want_max.tobytes()
+
+
+CASES = [
+    ("blob64", lambda p: p.blob_phantom((64, 64, 64), 0, 60), 0),
+    ("blob_odd", lambda p: p.blob_phantom((61, 53, 47), 4, 50), 0),
+    ("blob40_double", lambda p: p.blob_phantom((40, 44, 36), 5, 30), 1),
+    ("blob96_halve", lambda p: p.blob_phantom((96, 90, 100), 6, 120), -1),
+    ("brain_small", lambda p: p.brain_phantom((91, 109, 91), 1, 100), 0),
+]
+
+
+@pytest.mark.parametrize("name,make,double_mode", CASES, ids=[c[0] for c in CASES])
+def test_extract_pyramid_keypoints_features_bit_exact(pkg, oracle, engine, name, make, double_mode):
+    vol = make(pkg.phantom)
+    want = oracle.extract(vol, double_mode, 0, want_keypoints=True)
+    feats = engine.extract(vol, pkg.Params(double_mode=double_mode, keep_patches=True))
+    # pyramid levels of octave 0 and 1 against the oracle's octave builder
+    g0 = engine.level(0, 0)
+    og, od, _ = oracle.octave_levels(g0)
+    for j in range(6):
+        assert (bits(engine.level(0, j)) == bits(og[j])).all(), "G%d" % j
+    for j in range(5):
+        assert (bits(engine.level(0, j, dog=True)) == bits(od[j])).all(), "D%d" % j
+    if engine.num_octaves() > 1:
+        assert (bits(engine.level(1, 0)) == bits(oracle.subsample(og[3]))).all()
+    kps = engine.keypoints()
+    assert kps.tobytes() == want["keypoints"].tobytes()
+    patches, prerank = engine.patches()
+    assert len(feats) == len(want["features"]) and len(feats) > 0
+    assert (bits(patches) == bits(want["patches"])).all()
+    assert (bits(prerank) == bits(want["prerank"])).all()
+    assert feats.tobytes() == want["features"].tobytes()
+
+
+@pytest.mark.parametrize("descriptor", [1, 2, 3])
+def test_brief_family_bit_exact(pkg, oracle, engine, descriptor):
+    vol = pkg.phantom.blob_phantom((64, 64, 64), 0, 60)
+    want = oracle.extract(vol, 0, descriptor)
+    feats = engine.extract(vol, pkg.Params(descriptor=descriptor, keep_patches=True))
+    _, prerank = engine.patches()
+    assert (bits(prerank) == bits(want["prerank"])).all()
+    assert feats.tobytes() == want["features"].tobytes()
+
+
+def test_extract_is_deterministic_and_reusable(pkg, engine):
+    vol = pkg.phantom.blob_phantom((64, 64, 64), 0, 60)
+    a = engine.extract(vol)
+    b = engine.extract(pkg.phantom.blob_phantom((64, 64, 64), 1, 60))
+    c = engine.extract(vol)
+    assert a.tobytes() == c.tobytes() and a.tobytes() != b.tobytes()
+
+
+def test_errors_are_reported_not_fatal(pkg, engine):
+    vol = pkg.phantom.blob_phantom((64, 64, 64), 0, 60)
+    with pytest.raises(pkg.S3DError):
+        engine.extract(vol, pkg.Params(descriptor=9))
+    with pytest.raises(pkg.S3DError):
+        engine.extract(vol, pkg.Params(max_keypoints=4, max_features=8))   # capacity exceeded, reported
+    assert len(engine.extract(vol)) > 0   # the context is still usable
+
+
+def test_tiny_and_empty_volumes(pkg, oracle, engine):
+    flat = np.full((16, 16, 16), 3.0, np.float32)
+    assert len(engine.extract(flat)) == 0 == len(oracle.extract(flat)["features"])
+    tiny = pkg.phantom.blob_phantom((2, 5, 5), 1, 1)
+    assert len(engine.extract(tiny)) == 0
