@@ -30,10 +30,11 @@ def blob_phantom(shape_xyz=(128, 128, 128), seed=2, nblobs=200):
     X, Y, Z = shape_xyz
     rng = np.random.default_rng(seed)
     vol = np.full((Z, Y, X), 50.0, dtype=np.float64)
+    mx, my, mz = min(12, X // 4), min(12, Y // 4), min(12, Z // 4)   # 12 at the named sizes
     for _ in range(nblobs):
-        cx = rng.uniform(12, X - 12)
-        cy = rng.uniform(12, Y - 12)
-        cz = rng.uniform(12, Z - 12)
+        cx = rng.uniform(mx, X - mx)
+        cy = rng.uniform(my, Y - my)
+        cz = rng.uniform(mz, Z - mz)
         sigma = rng.uniform(1.5, 6.0)
         a = 60.0 * rng.uniform(-1.0, 1.0)
         _add_blob(vol, cx, cy, cz, sigma, a)

@@ -1038,7 +1038,12 @@ int s3o_extract(const float *vol, int X, int Y, int Z, int double_mode, int desc
                     interp_point(d[c], X, Y, lst[k].x, lst[k].y, lst[k].z, &fx, &fy, &fz);
                     float scale = (float)(2 * interp_quadratic(sig[c - 1], sig[c], sig[c + 1], d[c - 1][vi], d[c][vi], d[c + 1][vi]));
                     fx += 0.5f; fy += 0.5f; fz += 0.5f;
-                    if (keypoints) {
+                    /* a keypoint whose support box leaves the volume is dropped (sampleImage3D returns -1,
+                     * MultiScale.cpp:2633-2643); only the survivors are reported as keypoints */
+                    int iRadMax = (int)(2.0f * scale + 2);
+                    int inside = !(fx - iRadMax < 0 || fy - iRadMax < 0 || fz - iRadMax < 0 ||
+                                   fx + iRadMax >= X || fy + iRadMax >= Y || fz + iRadMax >= Z);
+                    if (keypoints && inside) {
                         if (nkp == kpcap) { kpcap = kpcap ? 2 * kpcap : 256; kps = (s3o_keypoint *)realloc(kps, sizeof(s3o_keypoint) * kpcap); }
                         s3o_keypoint kp = { oct, c, pass, lst[k].x, lst[k].y, lst[k].z, fx, fy, fz, scale };
                         kps[nkp++] = kp;
