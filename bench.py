@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the featExtract hot path (pyramid + DoG + detection + refinement +
+orientation + SIFT-Rank descriptors) on synthetic MNI-sized phantoms.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one 182x218x182 fp32 volume through the whole path on each GPU (BASELINE.json config 2;
+with N > 1 this is config 4's batch sharding: every rank extracts its own volume, no data-path
+collective, weak scaling).  Prints ONE JSON line on rank 0:
+
+  value      volumes/s, whole job, volume already resident in HBM when the timed region starts
+             (CUDA events on the engine's stream, per step, L2 flushed between steps, max over ranks)
+  e2e        same metric through the public C-ABI call with HOST buffers: pinned H2D of the volume and
+             D2H of the feature rows inside the timed region, every step
+  roofline   the heaviest blur level (17 taps + fused DoG at octave-0 size): algorithmic bytes
+             (read G_{j-1}, write G_j, write DoG = 12 B/voxel) / measured duration vs MEASURED_PEAKS.json
+  cpu_baseline  the reference's own CPU path (oracle/_ref) on the host cores, bounded sample
+
+--impl reference times the reference's CPU implementation (oracle/_ref, else the oracle port) with
+all usable host cores on the same workload and prints the same JSON shape.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHAPE = (182, 218, 182)      # X, Y, Z  (MNI)
+NBLOBS = 400
+WORKLOAD = "single MNI-sized 182x218x182 synthetic brain phantom, SIFT-Rank descriptor"
+N0 = SHAPE[0] * SHAPE[1] * SHAPE[2]
+
+
+def octave_voxels(shape):
+    x, y, z = shape
+    out = []
+    while not (x <= 2 or y <= 2 or z <= 2):
+        out.append(x * y * z)
+        x, y, z = x // 2, y // 2, z // 2
+    return out
+
+
+def algorithmic_bytes(shape):
+    """92.5 B/voxel on octave 0, 84.5 B/voxel on later octaves."""
+    v = octave_voxels(shape)
+    return 92.5 * v[0] + 84.5 * sum(v[1:])
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_reference(args):
+    """Reference CPU arm: rank 0 only; all usable host cores, one MNI volume per worker per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_baseline as cb
+    procs = cb.usable_cores()
+    pool = cb.CpuPool(SHAPE, 1, NBLOBS, os.path.join(ROOT, "3d_sift_cuda_b200", "phantom.py"), procs)
+    for _ in range(args.warmup):
+        pool.step(1)
+    vols, secs, rows = 0, 0.0, 0
+    for _ in range(args.steps):
+        n, dt, rows = pool.step(1)
+        vols += n
+        secs += dt
+    pool.close()
+    value = vols / secs
+    line = {
+        "impl": "reference", "metric": "volumes/sec (pyramid+detect+describe)", "value": value, "unit": "volumes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "gvoxels_per_s": value * N0 / 1e9,
+        "config": {"workload": WORKLOAD, "shape_xyz": list(SHAPE), "rows_per_volume": rows,
+                   "note": "reference CPU path (featExtract without -d): %d worker processes, one volume each per step" % procs},
+        "cpu_baseline": {"value": value, "unit": "volumes/s", "cores": procs, "kind": cb.kind(),
+                         "sample": "%d steps x %d volumes (one per worker process)" % (args.steps, procs)},
+        "e2e": {"value": value, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    pkg = importlib.import_module("3d_sift_cuda_b200")
+    dmod = importlib.import_module("3d_sift_cuda_b200.dist")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # CPU baseline first (rank 0, N=1 only), before the GPU is busy
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import cpu_baseline as cb
+        procs = min(cb.usable_cores(), 16)
+        pool = cb.CpuPool(SHAPE, 1, NBLOBS, os.path.join(ROOT, "3d_sift_cuda_b200", "phantom.py"), procs)
+        pool.step(1)
+        n, dt, _ = pool.step(1)
+        n2, dt2, _ = pool.step(1)
+        pool.close()
+        cpu = {"value": (n + n2) / (dt + dt2), "unit": "volumes/s", "cores": procs, "kind": cb.kind(),
+               "sample": "2 timed rounds x %d volumes (one MNI volume per worker process), 1 warm-up round" % procs}
+
+    eng = pkg.Engine(local)
+    st = torch.cuda.ExternalStream(eng.stream, device=dev)
+    params = pkg.Params()
+    # a small pool of distinct volumes per rank so no step can reuse a previous step's result
+    npool = 4
+    vols = [pkg.phantom.brain_phantom(SHAPE, 1 + rank * npool + i, NBLOBS) for i in range(npool)]
+    X, Y, Z = SHAPE
+    d_vols = [torch.from_numpy(v).to(dev) for v in vols]
+    h_vols = [torch.from_numpy(v).pin_memory() for v in vols]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    torch.cuda.synchronize()
+
+    # ---- device-resident throughput (value) ----
+    for i in range(args.warmup):
+        eng.extract_device(d_vols[i % npool], SHAPE, params)
+    eng.sync()
+    nk, nf = eng.fetch_counts()
+    launches_per_step = eng.launch_count()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    evs = []
+    with torch.cuda.stream(st):
+        for i in range(args.steps):
+            flush.zero_()                                  # evict L2 (untimed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            eng.extract_device(d_vols[i % npool], SHAPE, params)
+            e1.record(st)
+            evs.append((e0, e1))
+    eng.sync()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    total_ms = dmod.max_over_ranks(total_ms, device=dev)
+    ms_per_step = total_ms / args.steps
+    value = world * 1e3 / ms_per_step
+
+    # ---- end to end through the public call with host buffers (e2e) ----
+    for i in range(args.warmup):
+        eng.extract_host_async(h_vols[i % npool], params)
+        eng.fetch_features()
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for i in range(args.steps):
+        eng.extract_host_async(h_vols[i % npool], params)
+        f = eng.fetch_features()
+        d2h += f.nbytes + 12
+    torch.cuda.synchronize()
+    e2e_s = dmod.max_over_ranks(time.perf_counter() - t0, device=dev)
+    e2e = {"value": world * args.steps / e2e_s, "unit": "volumes/s", "h2d_bytes_per_step": N0 * 4,
+           "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * e2e_s / args.steps}
+
+    # ---- roofline of the dominant stage: the 17-tap blur level at octave-0 size with fused DoG ----
+    roof = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        pitch = (X + 7) // 8 * 8
+        a = torch.zeros((Z, Y, pitch), dtype=torch.float32, device=dev)
+        a[:, :, :X] = d_vols[0]
+        tmp, out, dog = torch.empty_like(a), torch.empty_like(a), torch.empty_like(a)
+        taps = pkg.gaussian_taps(3.0900)    # level 4 -> 5 of every octave: 17 taps
+        for _ in range(3):
+            eng.blur3d(a, tmp, out, X, taps, dog)
+        eng.sync()
+        reps, ms = 10, 0.0
+        with torch.cuda.stream(st):
+            for _ in range(reps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                eng.blur3d(a, tmp, out, X, taps, dog)
+                e1.record(st)
+                evs.append((e0, e1))
+        eng.sync()
+        ms = sum(x.elapsed_time(y) for x, y in evs[-reps:]) / reps
+        alg = 12.0 * N0                   # read G_{j-1}, write G_j, write DoG
+        achieved = alg / (ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "blur level (x + y + z passes, 17 taps, fused DoG) at 182x218x182",
+                "ms_per_launch": ms, "algorithmic_bytes": alg, "peak_source": peak_src,
+                "pipeline": {"algorithmic_bytes": algorithmic_bytes(SHAPE), "ms": ms_per_step,
+                             "achieved": algorithmic_bytes(SHAPE) / (ms_per_step * 1e-3) / 1e9,
+                             "frac": algorithmic_bytes(SHAPE) / (ms_per_step * 1e-3) / 1e9 / peak,
+                             "note": "whole step incl. keypoint stages vs SURVEY 8(d) algorithmic bytes"}}
+
+    if rank == 0:
+        line = {
+            "metric": "volumes/sec (pyramid+detect+describe)", "value": value, "unit": "volumes/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "gvoxels_per_s": value * N0 / 1e9,
+            "config": {"workload": WORKLOAD, "shape_xyz": list(SHAPE), "phantom": "brain_phantom(seed=1.., nblobs=400)",
+                       "parallelism": "one volume per GPU per step, no data-path collective" if world > 1 else "single GPU",
+                       "l2": "256 MiB buffer written between timed steps (L2 flush, untimed)",
+                       "keypoints_per_volume": nk, "rows_per_volume": nf},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "launches_per_step": launches_per_step, "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,62 @@
+"""CPU: the N>1 sharding path with the gloo backend, world_size 2 (host logic only, no kernels)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    d = importlib.import_module("3d_sift_cuda_b200.dist")
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    vols = [np.full((2, 2, 2), float(i), np.float32) for i in range(7)]
+    calls = []
+
+    def fake_extract(v):
+        calls.append(int(v[0, 0, 0]))
+        return np.arange(int(v[0, 0, 0]) + 1, dtype=np.float32)   # result identifies the volume
+
+    out = d.extract_sharded(fake_extract, vols, rank, world)
+    tmax = d.max_over_ranks(1.0 + rank)
+    q.put((rank, calls, None if out is None else [o.tolist() for o in out], tmax))
+    dist.destroy_process_group()
+
+
+def test_shard_indices(pkg):
+    d = importlib.import_module("3d_sift_cuda_b200.dist")
+    assert d.shard_indices(7, 0, 2) == [0, 2, 4, 6] and d.shard_indices(7, 1, 2) == [1, 3, 5]
+    for world in (1, 2, 3, 8):
+        allidx = sorted(i for r in range(world) for i in d.shard_indices(256, r, world))
+        assert allidx == list(range(256))
+    assert d.shard_indices(1, 3, 8) == []
+    with pytest.raises(ValueError):
+        d.shard_indices(4, 2, 2)
+
+
+def test_extract_sharded_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, calls0, out0, t0), (r1, calls1, out1, t1) = res
+    assert calls0 == [0, 2, 4, 6] and calls1 == [1, 3, 5]          # no volume processed twice
+    assert out1 is None
+    assert out0 == [list(map(float, range(i + 1))) for i in range(7)]   # input order restored on rank 0
+    assert t0 == t1 == 2.0                                          # max over ranks
+
+
+def test_extract_sharded_single_rank(pkg):
+    d = importlib.import_module("3d_sift_cuda_b200.dist")
+    out = d.extract_sharded(lambda v: v * 2, [np.ones(2), np.zeros(2)])
+    assert out[0].tolist() == [2, 2] and out[1].tolist() == [0, 0]
