@@ -132,12 +132,15 @@ struct Plan {
     Vol img0;                    // pre-stepped, pitched input of the pyramid
     std::vector<Vol> g, d;       // [oct*6 + level], [oct*5 + level]
     float *tmp1 = nullptr, *tmp2 = nullptr;
-    s3d_cand *cand_raw = nullptr, *cand_sorted = nullptr;   // [list][cand_cap], list = (oct*3 + (c-1))*2 + is_max
+    s3d_cand *cand_raw = nullptr;     // [list][cand_cap], list = (oct*3 + (c-1))*2 + is_max (atomic order)
+    s3d_keypoint *kp_stage = nullptr; // [list][cand_cap] refined candidates at their raster rank
+    unsigned char *stage_flags = nullptr;
     int *counts = nullptr;       // [n_lists] candidate counts, then kp_count, n_features, err
     int n_lists = 0;
     s3d_keypoint *kps = nullptr;
     int *nrows = nullptr, *row_off = nullptr;
-    float *kp_eigs = nullptr, *kp_ori0 = nullptr, *kp_rots = nullptr, *kp_patch0 = nullptr;
+    float *kp_eigs = nullptr, *kp_ori0 = nullptr, *kp_rots = nullptr, *kp_patch0 = nullptr, *kp_p1 = nullptr;
+    int *kp_nprim = nullptr, *kp_nsec = nullptr;
     s3d_feature *feats = nullptr;
     float *dbg_patches = nullptr, *dbg_prerank = nullptr;
     PyramidDesc pyr;
@@ -217,7 +220,8 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
     KpTables t;
     build_tables(t);
     CK(cudaMemcpyToSymbol(c_tab, &t, sizeof(t)));
-    CK(cudaFuncSetAttribute(orient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrientSmem)));
+    CK(cudaFuncSetAttribute(orient_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HistSmem)));
+    CK(cudaFuncSetAttribute(orient_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HistSmem)));
     CK(cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DescribeSmem)));
     CK(cudaMallocHost((void **)&ctx->h_counts, 4 * sizeof(int)));
     const char *g = getenv("S3D_NO_GRAPH");
@@ -263,6 +267,17 @@ extern "C" s3d_status s3d_sync(s3d_ctx *ctx)
 }
 extern "C" void s3d_free(void *p) { free(p); }
 extern "C" int s3d_last_launch_count(s3d_ctx *ctx) { return ctx ? ctx->last_launches : 0; }
+
+#ifdef S3D_PHASE_TIMERS
+// profiling builds only: read (and clear) the per-phase cycle counters of the keypoint kernels
+extern "C" int s3d_debug_phase_cycles(unsigned long long *out32)
+{
+    unsigned long long z[32] = { 0 };
+    if (cudaMemcpyFromSymbol(out32, g_phase, sizeof(z)) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(g_phase, z, sizeof(z)) != cudaSuccess) return -1;
+    return 0;
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------------
 // stage launchers
@@ -418,19 +433,31 @@ extern "C" s3d_status s3d_double_size(s3d_ctx *ctx, const float *d_in, int X, in
     return resize_launch(ctx, 2, d_in, X, Y, Z, pitch, d_out, out_pitch);
 }
 
-// detection + ordering; raw lists are scratch owned by the caller (engine) or allocated here (stage API)
-static s3d_status detect_launch(s3d_ctx *ctx, const float *finer, const float *centre, int X, int Y, int Z, int pitch,
-                                s3d_cand *raw_min, s3d_cand *raw_max, s3d_cand *out_min, int *n_min,
-                                s3d_cand *out_max, int *n_max, int cap)
+// detection into raw (atomic-order) lists
+static s3d_status detect_raw_launch(s3d_ctx *ctx, const float *finer, const float *centre, int X, int Y, int Z, int pitch,
+                                    s3d_cand *raw_min, int *n_min, s3d_cand *raw_max, int *n_max, int cap)
 {
     if (X < 3 || Y < 3 || Z < 3) return S3D_OK;   // no interior voxel
     dim3 block(32, 8), grid((X - 2 + 31) / 32, (Y - 2 + 7) / 8, Z - 2);
     CandList lmin{ raw_min, n_min }, lmax{ raw_max, n_max };
     detect_kernel<<<grid, block, 0, ctx->stream>>>(finer, centre, X, Y, Z, pitch, lmin, lmax, cap);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return S3D_OK;
+}
+
+// detection + raster ordering (stage-level API)
+static s3d_status detect_launch(s3d_ctx *ctx, const float *finer, const float *centre, int X, int Y, int Z, int pitch,
+                                s3d_cand *raw_min, s3d_cand *raw_max, s3d_cand *out_min, int *n_min,
+                                s3d_cand *out_max, int *n_max, int cap)
+{
+    if (X < 3 || Y < 3 || Z < 3) return S3D_OK;
+    s3d_status st = detect_raw_launch(ctx, finer, centre, X, Y, Z, pitch, raw_min, n_min, raw_max, n_max, cap);
+    if (st != S3D_OK) return st;
     int blocks = (cap + 255) / 256;
     order_candidates_kernel<<<blocks, 256, 0, ctx->stream>>>(raw_min, n_min, out_min, X, Y, cap);
     order_candidates_kernel<<<blocks, 256, 0, ctx->stream>>>(raw_max, n_max, out_max, X, Y, cap);
-    ctx->launches += 3;
+    ctx->launches += 2;
     CK(cudaGetLastError());
     return S3D_OK;
 }
@@ -549,8 +576,9 @@ static s3d_status plan_build(s3d_ctx *ctx, int X, int Y, int Z, const s3d_params
     p->cand_cap = (int)cc;
     p->n_lists = n_oct * 3 * 2;
     if (p->n_lists > 0) {
-        PA(&p->cand_raw, (size_t)2 * p->cand_cap);                 // scratch shared by all lists
-        PA(&p->cand_sorted, (size_t)p->n_lists * p->cand_cap);
+        PA(&p->cand_raw, (size_t)p->n_lists * p->cand_cap);
+        PA(&p->kp_stage, (size_t)p->n_lists * p->cand_cap);
+        PA(&p->stage_flags, (size_t)p->n_lists * p->cand_cap);
     }
     PA(&p->counts, p->n_lists + 8);
     PA(&p->kps, kp_cap);
@@ -558,7 +586,10 @@ static s3d_status plan_build(s3d_ctx *ctx, int X, int Y, int Z, const s3d_params
     PA(&p->row_off, kp_cap);
     PA(&p->kp_eigs, (size_t)kp_cap * 3);
     PA(&p->kp_ori0, (size_t)kp_cap * 9);
-    PA(&p->kp_rots, (size_t)kp_cap * kMaxRowsPerKp * 9);
+    PA(&p->kp_rots, (size_t)kp_cap * PD * PD * 9);
+    PA(&p->kp_p1, (size_t)kp_cap * PD * 3);
+    PA(&p->kp_nprim, kp_cap);
+    PA(&p->kp_nsec, (size_t)kp_cap * PD);
     PA(&p->kp_patch0, (size_t)kp_cap * PV);
     PA(&p->feats, row_cap);
     if (p->keep_patches) {
@@ -620,27 +651,29 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
         }
         for (int c = 1; c <= 3; c++) {
             int l0 = (o * 3 + (c - 1)) * 2;
-            s3d_cand *smin = p->cand_sorted + (size_t)l0 * p->cand_cap, *smax = p->cand_sorted + (size_t)(l0 + 1) * p->cand_cap;
-            s3d_status s = detect_launch(ctx, od.d[c - 1], od.d[c], od.X, od.Y, od.Z, od.pitch,
-                                         p->cand_raw, p->cand_raw + p->cand_cap, smin, p->counts + l0, smax, p->counts + l0 + 1, p->cand_cap);
+            s3d_status s = detect_raw_launch(ctx, od.d[c - 1], od.d[c], od.X, od.Y, od.Z, od.pitch,
+                                             p->cand_raw + (size_t)l0 * p->cand_cap, p->counts + l0,
+                                             p->cand_raw + (size_t)(l0 + 1) * p->cand_cap, p->counts + l0 + 1, p->cand_cap);
             if (s != S3D_OK) return s;
-            if (od.X < 3 || od.Y < 3 || od.Z < 3) continue;
-            refine_kernel<<<1, 256, 0, st>>>(p->pyr, o, c, 0, smin, p->counts + l0, p->cand_cap, p->kps, kp_count, p->kp_cap, err);
-            refine_kernel<<<1, 256, 0, st>>>(p->pyr, o, c, 1, smax, p->counts + l0 + 1, p->cand_cap, p->kps, kp_count, p->kp_cap, err);
-            ctx->launches += 2;
         }
     }
+    // candidate stage: rank + validate + refine every candidate of every list, then ordered compaction
+    ListDesc L{ p->n_lists, p->cand_cap, p->cand_raw, p->counts };
+    cand_refine_kernel<<<dim3(p->n_lists, 4), 256, 0, st>>>(p->pyr, L, p->kp_stage, p->stage_flags, err);
+    compact_kernel<<<1, 1024, 0, st>>>(L, p->kp_stage, p->stage_flags, p->kps, kp_count, p->kp_cap, err);
+    // orientation: per keypoint, then per (keypoint, primary direction)
     float eig = prm->eig_thres;
-    int grid_o = ctx->sm_count * 3;
-    orient_kernel<<<grid_o, 256, sizeof(OrientSmem), st>>>(p->pyr, p->kps, kp_count, eig, p->nrows, p->kp_eigs, p->kp_ori0, p->kp_rots, p->kp_patch0);
-    row_offsets_kernel<<<1, 1024, 0, st>>>(p->nrows, kp_count, p->row_off, n_features, p->row_cap, err);
+    orient_a_kernel<<<ctx->sm_count * 3, 256, sizeof(HistSmem), st>>>(p->pyr, p->kps, kp_count, eig, p->kp_nprim, p->kp_eigs,
+                                                                     p->kp_ori0, p->kp_p1, p->kp_patch0);
+    orient_b_kernel<<<ctx->sm_count * 3, 256, sizeof(HistSmem), st>>>(kp_count, p->kp_nprim, p->kp_p1, p->kp_patch0, p->kp_nsec, p->kp_rots);
+    row_offsets_kernel<<<1, 1024, 0, st>>>(p->kp_nprim, p->kp_nsec, kp_count, p->nrows, p->row_off, n_features, p->row_cap, err);
     float size_factor = 1.0f;
     if (p->double_mode > 0) size_factor /= 2; else if (p->double_mode < 0) size_factor *= 2;
     int grid_d = ctx->sm_count * 8;
-    describe_kernel<<<grid_d, 128, sizeof(DescribeSmem), st>>>(p->pyr, p->kps, kp_count, p->nrows, p->row_off, p->kp_eigs, p->kp_ori0,
-                                                              p->kp_rots, p->kp_patch0, prm->descriptor, size_factor, p->row_cap,
-                                                              p->feats, p->dbg_patches, p->dbg_prerank);
-    ctx->launches += 3;
+    describe_kernel<<<grid_d, 128, sizeof(DescribeSmem), st>>>(p->pyr, p->kps, kp_count, p->nrows, p->row_off, p->kp_nsec, p->kp_eigs,
+                                                              p->kp_ori0, p->kp_rots, p->kp_patch0, prm->descriptor, size_factor,
+                                                              p->row_cap, p->feats, p->dbg_patches, p->dbg_prerank);
+    ctx->launches += 6;
     CK(cudaGetLastError());
     return S3D_OK;
 }

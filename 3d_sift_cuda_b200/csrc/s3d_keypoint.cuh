@@ -48,6 +48,24 @@ __constant__ KpTables c_tab;
 
 enum { ERR_CAND_OVERFLOW = 1, ERR_KP_OVERFLOW = 2, ERR_ROW_OVERFLOW = 4 };
 
+// Optional per-phase cycle counters (profiling builds only: -DS3D_PHASE_TIMERS); thread 0 of each CTA
+// accumulates clock64() deltas so the split of a keypoint kernel's latency can be read back.
+#ifdef S3D_PHASE_TIMERS
+__device__ unsigned long long g_phase[32];
+#define PHASE_INIT() long long ph_t_ = clock64()
+#define PHASE(i)                                                                   \
+    do {                                                                           \
+        if (threadIdx.x == 0) {                                                    \
+            long long n_ = clock64();                                              \
+            atomicAdd(&g_phase[i], (unsigned long long)(n_ - ph_t_));              \
+            ph_t_ = n_;                                                            \
+        }                                                                          \
+    } while (0)
+#else
+#define PHASE_INIT()
+#define PHASE(i)
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // scalar helpers (reference MultiScale.cpp:1614-1697, 2531-2534; FeatureIO.cpp:757-850)
 // ------------------------------------------------------------------------------------------------
@@ -148,42 +166,77 @@ __device__ __forceinline__ float vec_dot(const float *a, const float *b) { retur
 // ------------------------------------------------------------------------------------------------
 // block-cooperative pieces (blockDim.x threads, all must call)
 // ------------------------------------------------------------------------------------------------
+constexpr int PVP = 1332;   // patch arrays are padded to a multiple of 4 floats so each starts 16-byte aligned
 
 // sampleImage3D (reference MultiScale.cpp:2614-2714): inv = inverse orientation, already in smem.
+// Each thread owns up to 6 samples; the loop is fully unrolled and branch-light so the 8 corner loads of
+// all of a thread's samples are in flight together (the gather is pure latency otherwise).
 __device__ void gather_patch(const float *__restrict__ img, int X, int Y, int Z, int pitch,
                              float fx, float fy, float fz, float scale, const float *inv, float *patch)
 {
-    float fImageRad = 2.0f * scale;
-    float fScale = fImageRad / (float)(PD / 2);
-    for (int i = threadIdx.x; i < PV; i += blockDim.x) {
-        int x = i % PD - 5, y = (i / PD) % PD - 5, z = i / (PD * PD) - 5;
-        float f[3] = { (float)x, (float)y, (float)z }, p[3];
+    const float fImageRad = 2.0f * scale;
+    const float fScale = fImageRad / (float)(PD / 2);
+    const float m00 = inv[0], m01 = inv[1], m02 = inv[2], m10 = inv[3], m11 = inv[4], m12 = inv[5], m20 = inv[6], m21 = inv[7], m22 = inv[8];
+    const long long plane = (long long)pitch * Y;
+    for (int i0 = threadIdx.x; i0 < PV; i0 += 2 * blockDim.x) {
+        float v[2][8], w[2][3];
+        bool inside[2], live[2];
 #pragma unroll
-        for (int a = 0; a < 3; a++) {
-            float s = 0.0f;
-            s = s + inv[a * 3 + 0] * f[0];
-            s = s + inv[a * 3 + 1] * f[1];
-            s = s + inv[a * 3 + 2] * f[2];
-            p[a] = s;
+        for (int u = 0; u < 2; u++) {
+            int i = i0 + u * blockDim.x;
+            live[u] = i < PV;
+            int ii = live[u] ? i : 0;
+            float f0 = (float)(ii % PD - 5), f1 = (float)((ii / PD) % PD - 5), f2 = (float)(ii / (PD * PD) - 5);
+            float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f;
+            p0 = p0 + m00 * f0; p0 = p0 + m01 * f1; p0 = p0 + m02 * f2;
+            p1 = p1 + m10 * f0; p1 = p1 + m11 * f1; p1 = p1 + m12 * f2;
+            p2 = p2 + m20 * f0; p2 = p2 + m21 * f1; p2 = p2 + m22 * f2;
+            p0 = p0 * fScale; p1 = p1 * fScale; p2 = p2 * fScale;
+            p0 = p0 + fx; p1 = p1 + fy; p2 = p2 + fz;
+            inside[u] = !(p0 < 0 || p0 >= X);
+            int iX, iY, iZ;
+            interp_coord(p0, (float)X, iX, w[u][0]);
+            interp_coord(p1, (float)Y, iY, w[u][1]);
+            interp_coord(p2, (float)Z, iZ, w[u][2]);
+            if (!inside[u]) iX = 0;   // value unused; keep the address legal
+            const float *p = img + ((long long)iZ * Y + iY) * pitch + iX;
+            v[u][0] = __ldg(p); v[u][1] = __ldg(p + 1); v[u][2] = __ldg(p + pitch); v[u][3] = __ldg(p + pitch + 1);
+            v[u][4] = __ldg(p + plane); v[u][5] = __ldg(p + plane + 1); v[u][6] = __ldg(p + plane + pitch); v[u][7] = __ldg(p + plane + pitch + 1);
         }
-        p[0] *= fScale; p[1] *= fScale; p[2] *= fScale;
-        p[0] += fx; p[1] += fy; p[2] += fz;
-        float pix;
-        if (p[0] < 0 || p[0] >= X) pix = 0.0f;
-        else pix = trilinear_get(img, X, Y, Z, pitch, p[0], p[1], p[2]);
-        patch[i] = pix;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            float wx = w[u][0], wy = w[u][1], wz = w[u][2];
+            float fn00 = wx * v[u][0] + (1.0f - wx) * v[u][1];
+            float fn01 = wx * v[u][4] + (1.0f - wx) * v[u][5];
+            float fn10 = wx * v[u][2] + (1.0f - wx) * v[u][3];
+            float fn11 = wx * v[u][6] + (1.0f - wx) * v[u][7];
+            float fnn0 = wy * fn00 + (1.0f - wy) * fn10;
+            float fnn1 = wy * fn01 + (1.0f - wy) * fn11;
+            float r = wz * fnn0 + (1.0f - wz) * fnn1;
+            if (live[u]) patch[i0 + u * blockDim.x] = inside[u] ? r : 0.0f;
+        }
     }
 }
 
-// Feature3D::NormalizeData (reference MultiScale.cpp:127-205).  scratch: PV floats, red: 2 floats.
+// left-to-right fp32 sum of n floats in shared memory (16-byte aligned, n padded reads allowed up to PVP)
+__device__ __forceinline__ float seq_sum(const float *a, int n)
+{
+    float s = 0.0f;
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+        float4 u = *reinterpret_cast<const float4 *>(a + i), v = *reinterpret_cast<const float4 *>(a + i + 4);
+        s = s + u.x; s = s + u.y; s = s + u.z; s = s + u.w;
+        s = s + v.x; s = s + v.y; s = s + v.z; s = s + v.w;
+    }
+    for (; i < n; i++) s = s + a[i];
+    return s;
+}
+
+// Feature3D::NormalizeData (reference MultiScale.cpp:127-205).  scratch: PVP floats, red: 2 floats.
 __device__ void normalize_patch(float *patch, float *scratch, float *red)
 {
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.0f;
-        for (int i = 0; i < PV; i++) s = s + patch[i];
-        red[0] = s / (float)(PD * PD * PD);
-    }
+    if (threadIdx.x == 0) red[0] = seq_sum(patch, PV) / (float)(PD * PD * PD);
     __syncthreads();
     float mean = red[0];
     for (int i = threadIdx.x; i < PV; i += blockDim.x) {
@@ -192,11 +245,7 @@ __device__ void normalize_patch(float *patch, float *scratch, float *red)
         scratch[i] = v * v;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.0f;
-        for (int i = 0; i < PV; i++) s = s + scratch[i];
-        red[1] = 1.0f / sqrtf(s);
-    }
+    if (threadIdx.x == 0) red[1] = 1.0f / sqrtf(seq_sum(scratch, PV));
     __syncthreads();
     float fDiv = red[1];
     for (int i = threadIdx.x; i < PV; i += blockDim.x) patch[i] = patch[i] * fDiv;
@@ -219,8 +268,8 @@ __device__ void patch_gradients(const float *p, float *dx, float *dy, float *dz)
     __syncthreads();
 }
 
-// blur_3d_simpleborders on an 11^3 image (reference GaussBlur3D.cpp:329-479): src -> dst, tmp scratch.
-// src may be clobbered?  No: src is left intact; dst and tmp must differ from src and each other.
+// blur_3d_simpleborders on an 11^3 image (reference GaussBlur3D.cpp:329-479): src -> dst, tmp scratch;
+// src is left intact; src, tmp, dst must be distinct.  taps: shared or constant memory.
 __device__ void blur_patch(const float *src, float *tmp, float *dst, const float *taps, int ntaps)
 {
     int r = ntaps / 2;
@@ -441,121 +490,179 @@ __device__ void sort_eigen(float w[3], float v[3][3])
             }
 }
 
+
 // ------------------------------------------------------------------------------------------------
-// Kernel 1: deferred validation + refinement + bounds test + ordered compaction of one candidate list
-// (reference MultiScale.cpp:424-455, 1135-1318, 1372-1386, 2633-2643).  One CTA; lists are short.
+// Candidate stage.  detect_kernel (s3d_voxel.cuh) appends candidates of every (octave, centre level,
+// min/max) list in atomic order.  cand_refine_kernel then handles every candidate of every list in
+// parallel: its raster rank inside its list (rank by counting; keys are unique voxel indices), the
+// deferred validation against the coarser DoG, the parabola refinement and the support-box test
+// (reference MultiScale.cpp:424-455, 1135-1318, 1372-1386, 2633-2643); survivors are staged at
+// stage[list][rank].  compact_kernel makes the ordered keypoint array (octave, level, min then max,
+// raster order = the reference's output order).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) refine_kernel(const __grid_constant__ PyramidDesc pyr, int octave, int c, int is_max,
-                                                     const s3d_cand *__restrict__ list, const int *__restrict__ count, int cap,
-                                                     s3d_keypoint *__restrict__ kps, int *kp_count, int kp_cap, int *err)
+struct ListDesc {            // list = (octave*3 + (c-1))*2 + is_max
+    int n_lists, cap;
+    const s3d_cand *raw;     // [n_lists][cap]
+    const int *counts;       // [n_lists]
+};
+
+__global__ void __launch_bounds__(256) cand_refine_kernel(const __grid_constant__ PyramidDesc pyr, ListDesc L,
+                                                          s3d_keypoint *__restrict__ stage, unsigned char *__restrict__ flags,
+                                                          int *err)
 {
-    __shared__ int s_warp[8];
-    __shared__ int s_base, s_run;
+    const int list = blockIdx.x;
+    const int octave = list / 6, c = (list / 2) % 3 + 1, is_max = list & 1;
     const OctaveDesc &o = pyr.oct[octave];
     const int X = o.X, Y = o.Y, Z = o.Z, pitch = o.pitch;
     const long long plane = (long long)pitch * Y;
-    int n = *count;
-    if (threadIdx.x == 0) {
-        if (n > cap) atomicOr(err, ERR_CAND_OVERFLOW);
-        s_base = *kp_count;
-        s_run = 0;
-    }
-    n = min(n, cap);
-    __syncthreads();
+    int n = L.counts[list];
+    if (n > L.cap) { if (threadIdx.x == 0 && blockIdx.y == 0) atomicOr(err, ERR_CAND_OVERFLOW); n = L.cap; }
+    const s3d_cand *raw = L.raw + (long long)list * L.cap;
     const float *dH = o.d[c - 1], *dC = o.d[c], *dL = o.d[c + 1];
-    for (int start = 0; start < n; start += blockDim.x) {
-        int k = start + threadIdx.x;
+    for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < n; k += gridDim.y * blockDim.x) {
+        s3d_cand cd = raw[k];
+        long long key = ((long long)cd.z * Y + cd.y) * X + cd.x;
+        int rank = 0;
+        for (int j = 0; j < n; j++) {
+            s3d_cand q = raw[j];
+            rank += (((long long)q.z * Y + q.y) * X + q.x) < key;
+        }
+        long long i = (long long)cd.z * plane + (long long)cd.y * pitch + cd.x;
+        float cv = cd.value;
+        bool ok = true;
+        for (int dz = -1; dz <= 1 && ok; dz++)
+            for (int dy = -1; dy <= 1 && ok; dy++) {
+                const float *row = dL + i + dz * plane + dy * pitch;
+                float a = row[-1], b = row[0], d = row[1];
+                ok = is_max ? ((a < cv) && (b < cv) && (d < cv)) : ((a > cv) && (b > cv) && (d > cv));
+            }
         bool valid = false;
         s3d_keypoint kp;
-        if (k < n) {
-            s3d_cand cd = list[k];
-            long long i = (long long)cd.z * plane + (long long)cd.y * pitch + cd.x;
-            float cv = cd.value;
-            bool ok = true;
-            for (int dz = -1; dz <= 1 && ok; dz++)
-                for (int dy = -1; dy <= 1 && ok; dy++) {
-                    const float *row = dL + i + dz * plane + dy * pitch;
-                    float a = row[-1], b = row[0], d = row[1];
-                    ok = is_max ? ((a < cv) && (b < cv) && (d < cv)) : ((a > cv) && (b > cv) && (d > cv));
-                }
-            if (ok) {
-                float fx = (float)interp_quadratic(cd.x - 1, cd.x, cd.x + 1, dC[i - 1], dC[i], dC[i + 1]);
-                float fy = (float)interp_quadratic(cd.y - 1, cd.y, cd.y + 1, dC[i - pitch], dC[i], dC[i + pitch]);
-                float fz = (float)interp_quadratic(cd.z - 1, cd.z, cd.z + 1, dC[i - plane], dC[i], dC[i + plane]);
-                float scale = (float)(2 * interp_quadratic(o.sigma[c - 1], o.sigma[c], o.sigma[c + 1], dH[i], dC[i], dL[i]));
-                fx += 0.5f; fy += 0.5f; fz += 0.5f;
-                float fImageRad = 2.0f * scale;
-                int iRadMax = (int)(fImageRad + 2);
-                bool out_of_bounds = (fx - iRadMax < 0 || fy - iRadMax < 0 || fz - iRadMax < 0 ||
-                                      fx + iRadMax >= X || fy + iRadMax >= Y || fz + iRadMax >= Z);
-                if (!out_of_bounds) {
-                    valid = true;
-                    kp.octave = octave; kp.level = c; kp.is_max = is_max;
-                    kp.ix = cd.x; kp.iy = cd.y; kp.iz = cd.z;
-                    kp.x = fx; kp.y = fy; kp.z = fz; kp.scale = scale;
-                }
+        if (ok) {
+            float fx = (float)interp_quadratic(cd.x - 1, cd.x, cd.x + 1, dC[i - 1], dC[i], dC[i + 1]);
+            float fy = (float)interp_quadratic(cd.y - 1, cd.y, cd.y + 1, dC[i - pitch], dC[i], dC[i + pitch]);
+            float fz = (float)interp_quadratic(cd.z - 1, cd.z, cd.z + 1, dC[i - plane], dC[i], dC[i + plane]);
+            float scale = (float)(2 * interp_quadratic(o.sigma[c - 1], o.sigma[c], o.sigma[c + 1], dH[i], dC[i], dL[i]));
+            fx += 0.5f; fy += 0.5f; fz += 0.5f;
+            float fImageRad = 2.0f * scale;
+            int iRadMax = (int)(fImageRad + 2);
+            bool oob = (fx - iRadMax < 0 || fy - iRadMax < 0 || fz - iRadMax < 0 ||
+                        fx + iRadMax >= X || fy + iRadMax >= Y || fz + iRadMax >= Z);
+            if (!oob) {
+                valid = true;
+                kp.octave = octave; kp.level = c; kp.is_max = is_max;
+                kp.ix = cd.x; kp.iy = cd.y; kp.iz = cd.z;
+                kp.x = fx; kp.y = fy; kp.z = fz; kp.scale = scale;
             }
+        }
+        long long slot = (long long)list * L.cap + rank;
+        flags[slot] = valid ? 1 : 0;
+        if (valid) stage[slot] = kp;
+    }
+}
+
+// One CTA: ordered compaction of the staged keypoints over the concatenation of all lists.
+__global__ void __launch_bounds__(1024) compact_kernel(ListDesc L, const s3d_keypoint *__restrict__ stage,
+                                                       const unsigned char *__restrict__ flags,
+                                                       s3d_keypoint *__restrict__ kps, int *kp_count, int kp_cap, int *err)
+{
+    __shared__ int s_pref[kMaxOct * 6 + 1];
+    __shared__ int s_warp[32];
+    __shared__ int s_run;
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int l = 0; l < L.n_lists; l++) { s_pref[l] = acc; acc += min(L.counts[l], L.cap); }
+        s_pref[L.n_lists] = acc;
+        s_run = 0;
+    }
+    __syncthreads();
+    const int total = s_pref[L.n_lists];
+    for (int start = 0; start < total; start += blockDim.x) {
+        int g = start + threadIdx.x;
+        bool valid = false;
+        long long slot = 0;
+        if (g < total) {
+            int lo = 0, hi = L.n_lists - 1;     // last list with s_pref[l] <= g
+            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_pref[mid] <= g) lo = mid; else hi = mid - 1; }
+            slot = (long long)lo * L.cap + (g - s_pref[lo]);
+            valid = flags[slot] != 0;
         }
         unsigned bal = __ballot_sync(0xffffffffu, valid);
         int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        int pre = __popc(bal & ((1u << lane) - 1));
         if (lane == 0) s_warp[wid] = __popc(bal);
         __syncthreads();
         int woff = 0, tot = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { if (w < wid) woff += s_warp[w]; tot += s_warp[w]; }
-        int pos = s_base + s_run + woff + pre;
+        for (int w = 0; w < 32; w++) { if (w < wid) woff += s_warp[w]; tot += s_warp[w]; }
+        int pos = s_run + woff + __popc(bal & ((1u << lane) - 1));
         if (valid) {
-            if (pos < kp_cap) kps[pos] = kp;
+            if (pos < kp_cap) kps[pos] = stage[slot];
             else atomicOr(err, ERR_KP_OVERFLOW);
         }
         __syncthreads();
         if (threadIdx.x == 0) s_run += tot;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *kp_count = min(s_base + s_run, kp_cap);
+    if (threadIdx.x == 0) *kp_count = min(s_run, kp_cap);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Kernel 2: orientation assignment, one CTA per keypoint (persistent grid-stride loop).
-// Reference: generateFeature3D (MultiScale.cpp:1705-1862), determineOrientation3D (:2541-2607),
-// determineCanonicalOrientation3D (:2722-3037).
-// Outputs per keypoint: nrows (0 when rejected by the eigenvalue test), eigs, ori0 (sorted V),
-// rots (n_ori x 9), and the normalised identity patch (row 0 of the keypoint).
+// Orientation assignment (reference generateFeature3D MultiScale.cpp:1705-1862, determineOrientation3D
+// :2541-2607, determineCanonicalOrientation3D :2722-3037), split in two kernels so that the secondary
+// histograms of different primary peaks run as separate CTAs:
+//   orient_a_kernel  one CTA per keypoint: identity patch, normalise, gradients, structure tensor + SVD,
+//                    eigenvalue test, primary direction histogram, its peaks -> up to 11 primary directions
+//   orient_b_kernel  one CTA per (keypoint, primary direction): secondary histogram, peaks -> rotations
+// The reference caps the total at 11 rotations per keypoint, taken in (primary, secondary) order; that
+// truncation is applied when rows are counted (row_offsets_kernel).
 // ------------------------------------------------------------------------------------------------
-struct OrientSmem {
-    float patch[PV];
-    float dx[PV], dy[PV], dz[PV];
-    float h0[PV], h1[PV], h2[PV];
+struct HistSmem {
+    float patch[PVP];
+    float dx[PVP], dy[PVP], dz[PVP];
+    float h0[PVP], h1[PVP], h2[PVP];
     float contrib[kMaxSphere * 8];
     int cbase[kMaxSphere];
-    s3d_cand peaks[128], peaks2[128], psort[128];
+    float ex[kMaxSphere], ey[kMaxSphere], ez[kMaxSphere];
+    s3d_cand peaks[128], psort[128];
+    unsigned char pflag[736];
+    float taps[12];
     float oriData[PD * 3];
-    float rots[kMaxRowsPerKp * 9];
     float inv[9];
     float fmat[9];
     float red[2];
     float eigs[3];
     float ori0[9];
-    int np, np2, nret, keep;
+    int np, keep, nprim;
 };
 
 // Sequential splat of the per-voxel contributions into a zeroed 11^3 histogram, in sphere (raster)
 // order: 8 lanes own the 8 corners of a voxel's 2x2x2 footprint (distinct bins), __syncwarp orders
-// successive voxels (fioIncPixelTrilinearInterp, reference FeatureIO.cpp:853-889).
-__device__ void splat_histogram(float *hist, const float *contrib, const int *cbase, int n_sphere)
+// successive voxels (fioIncPixelTrilinearInterp, reference FeatureIO.cpp:853-889).  Runs on warp
+// `warp`; the caller synchronises the block afterwards.
+__device__ void splat_histogram_warp(float *hist, const float *contrib, const int *cbase, int n_sphere, int warp)
 {
-    for (int i = threadIdx.x; i < PV; i += blockDim.x) hist[i] = 0.0f;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        int lane = threadIdx.x;
+    if ((int)(threadIdx.x >> 5) == warp) {
+        int lane = threadIdx.x & 31;
         int off = (lane & 1) + ((lane >> 1) & 1) * PD + ((lane >> 2) & 1) * PD * PD;
-        for (int n = 0; n < n_sphere; n++) {
+        int n = 0;
+        for (; n + 4 <= n_sphere; n += 4) {
+            int b0 = cbase[n], b1 = cbase[n + 1], b2 = cbase[n + 2], b3 = cbase[n + 3];
+            float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+            if (lane < 8) { c0 = contrib[n * 8 + lane]; c1 = contrib[n * 8 + 8 + lane]; c2 = contrib[n * 8 + 16 + lane]; c3 = contrib[n * 8 + 24 + lane]; }
+            if (b0 >= 0 && lane < 8) hist[b0 + off] = hist[b0 + off] + c0;
+            __syncwarp();
+            if (b1 >= 0 && lane < 8) hist[b1 + off] = hist[b1 + off] + c1;
+            __syncwarp();
+            if (b2 >= 0 && lane < 8) hist[b2 + off] = hist[b2 + off] + c2;
+            __syncwarp();
+            if (b3 >= 0 && lane < 8) hist[b3 + off] = hist[b3 + off] + c3;
+            __syncwarp();
+        }
+        for (; n < n_sphere; n++) {
             int b = cbase[n];
             if (b >= 0 && lane < 8) hist[b + off] = hist[b + off] + contrib[n * 8 + lane];
             __syncwarp();
         }
     }
-    __syncthreads();
 }
 
 // contributions of one voxel at histogram position (px,py,pz) with value v
@@ -578,32 +685,37 @@ __device__ __forceinline__ void make_contrib(float px, float py, float pz, float
 }
 
 // regFindFEATUREIOPeaks + lvSortHighLow on an 11^3 histogram (reference MultiScale.cpp:1987-2121,
-// LocationValue.cpp:28-56).  Result in `sorted` (descending value, ties in raster order), count in *np.
-__device__ void find_sort_peaks(const float *h, s3d_cand *raw, s3d_cand *sorted, int *np)
+// LocationValue.cpp:28-56).  All threads test the 729 interior bins; warp 0 compacts them in raster
+// order; result in `sorted` (descending value, ties in raster order), count in *np.
+__device__ void find_sort_peaks(const float *h, unsigned char *pflag, s3d_cand *raw, s3d_cand *sorted, int *np)
 {
+    for (int t = threadIdx.x; t < 729; t += blockDim.x) {
+        int x = 1 + t % 9, y = 1 + (t / 9) % 9, z = 1 + t / 81;
+        int i = (z * PD + y) * PD + x;
+        float c = h[i];
+        bool pk = true;
+#pragma unroll
+        for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                for (int dx = -1; dx <= 1; dx++) {
+                    if (dx == 0 && dy == 0 && dz == 0) continue;
+                    pk = pk && (h[i + (dz * PD + dy) * PD + dx] < c);
+                }
+        pflag[t] = pk ? 1 : 0;
+    }
+    __syncthreads();
     if (threadIdx.x < 32) {
         int lane = threadIdx.x, n = 0;
         for (int t0 = 0; t0 < 729; t0 += 32) {
             int t = t0 + lane;
-            bool pk = false;
-            int x = 0, y = 0, z = 0;
-            float c = 0.0f;
-            if (t < 729) {
-                x = 1 + t % 9; y = 1 + (t / 9) % 9; z = 1 + t / 81;
-                int i = (z * PD + y) * PD + x;
-                c = h[i];
-                pk = true;
-                for (int dz = -1; dz <= 1; dz++)
-                    for (int dy = -1; dy <= 1; dy++)
-                        for (int dx = -1; dx <= 1; dx++) {
-                            if (dx == 0 && dy == 0 && dz == 0) continue;
-                            pk = pk && (h[i + (dz * PD + dy) * PD + dx] < c);
-                        }
-            }
+            bool pk = (t < 729) && pflag[t];
             unsigned bal = __ballot_sync(0xffffffffu, pk);
             if (pk) {
                 int pos = n + __popc(bal & ((1u << lane) - 1));
-                if (pos < 128) raw[pos] = s3d_cand{ x, y, z, c };
+                int x = 1 + t % 9, y = 1 + (t / 9) % 9, z = 1 + t / 81;
+                if (pos < 128) raw[pos] = s3d_cand{ x, y, z, h[(z * PD + y) * PD + x] };
             }
             n += __popc(bal);
         }
@@ -631,43 +743,66 @@ __device__ __forceinline__ void interp_point_patch(const float *h, int ix, int i
     o[2] = (float)interp_quadratic(iz - 1, iz, iz + 1, h[i - PD * PD], h[i], h[i + PD * PD]);
 }
 
-__global__ void __launch_bounds__(256) orient_kernel(const __grid_constant__ PyramidDesc pyr,
-                                                     const s3d_keypoint *__restrict__ kps, const int *__restrict__ kp_count,
-                                                     float eig_thres,
-                                                     int *__restrict__ nrows, float *__restrict__ kp_eigs, float *__restrict__ kp_ori0,
-                                                     float *__restrict__ kp_rots, float *__restrict__ kp_patch0)
+// gradients of the sphere voxels, in sphere order, for contiguous sequential walks
+__device__ __forceinline__ void sphere_gradients(HistSmem &S, int nsph)
+{
+    for (int n = threadIdx.x; n < nsph; n += blockDim.x) {
+        int i = c_tab.sphere[n];
+        S.ex[n] = S.dx[i]; S.ey[n] = S.dy[i]; S.ez[n] = S.dz[i];
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) orient_a_kernel(const __grid_constant__ PyramidDesc pyr,
+                                                       const s3d_keypoint *__restrict__ kps, const int *__restrict__ kp_count,
+                                                       float eig_thres,
+                                                       int *__restrict__ kp_nprim, float *__restrict__ kp_eigs, float *__restrict__ kp_ori0,
+                                                       float *__restrict__ kp_p1, float *__restrict__ kp_patch0)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    OrientSmem &S = *reinterpret_cast<OrientSmem *>(smem_raw);
+    HistSmem &S = *reinterpret_cast<HistSmem *>(smem_raw);
     const int nkp = *kp_count;
     const int nsph = c_tab.n_sphere;
     const float fRadius = 5.0f;
-
+    if (threadIdx.x < 12) S.taps[threadIdx.x] = threadIdx.x < 9 ? c_tab.hist_taps[threadIdx.x] : 0.0f;
+    PHASE_INIT();
     for (int kpi = blockIdx.x; kpi < nkp; kpi += gridDim.x) {
         __syncthreads();
         const s3d_keypoint kp = kps[kpi];
         const OctaveDesc &o = pyr.oct[kp.octave];
         const float *img = o.g[kp.level];
+        PHASE(0);
 
         // --- identity patch, normalised (generateFeature3D :1721-1739)
-        if (threadIdx.x < 9) S.inv[threadIdx.x] = (threadIdx.x % 4 == 0) ? 1.0f : 0.0f;
-        __syncthreads();
-        if (threadIdx.x == 0) { float id[9]; for (int q = 0; q < 9; q++) id[q] = S.inv[q]; invert3(id, S.inv); }
+        if (threadIdx.x == 0) { float id[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 }; invert3(id, S.inv); }
         __syncthreads();
         gather_patch(img, o.X, o.Y, o.Z, o.pitch, kp.x, kp.y, kp.z, kp.scale, S.inv, S.patch);
+        __syncthreads();
+        PHASE(1);
         normalize_patch(S.patch, S.h0, S.red);
+        PHASE(2);
         for (int i = threadIdx.x; i < PV; i += blockDim.x) kp_patch0[(long long)kpi * PV + i] = S.patch[i];
 
-        // --- eigen-orientation (determineOrientation3D)
+        // --- structure tensor over the sphere voxels, raster order (determineOrientation3D)
         patch_gradients(S.patch, S.dx, S.dy, S.dz);
+        sphere_gradients(S, nsph);
         if (threadIdx.x < 9) {
-            const float *ea = (threadIdx.x / 3 == 0) ? S.dx : (threadIdx.x / 3 == 1) ? S.dy : S.dz;
-            const float *eb = (threadIdx.x % 3 == 0) ? S.dx : (threadIdx.x % 3 == 1) ? S.dy : S.dz;
+            const float *ea = (threadIdx.x / 3 == 0) ? S.ex : (threadIdx.x / 3 == 1) ? S.ey : S.ez;
+            const float *eb = (threadIdx.x % 3 == 0) ? S.ex : (threadIdx.x % 3 == 1) ? S.ey : S.ez;
             float m = 0.0f;
-            for (int n = 0; n < nsph; n++) { int i = c_tab.sphere[n]; m = m + ea[i] * eb[i]; }
+            int n = 0;
+            for (; n + 4 <= nsph; n += 4) {
+                float4 a = *reinterpret_cast<const float4 *>(ea + n), b = *reinterpret_cast<const float4 *>(eb + n);
+                m = m + a.x * b.x; m = m + a.y * b.y; m = m + a.z * b.z; m = m + a.w * b.w;
+            }
+            for (; n < nsph; n++) m = m + ea[n] * eb[n];
             S.fmat[threadIdx.x] = m;
         }
         __syncthreads();
+        PHASE(3);
+
+        // --- warp 0 lane 0: SVD + eigenvalue test; the other warps meanwhile build the primary histogram
+        //     (determineCanonicalOrientation3D :2779-2817), whose result is simply dropped if the test fails
         if (threadIdx.x == 0) {
             float mat[3][3], w[3], v[3][3];
             for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) mat[a][b] = S.fmat[a * 3 + b];
@@ -678,112 +813,150 @@ __global__ void __launch_bounds__(256) orient_kernel(const __grid_constant__ Pyr
             float fEigPrd = w[0] * w[1] * w[2];
             float fEigSumProd = fEigSum * fEigSum * fEigSum;
             S.keep = (fEigSumProd < eig_thres * fEigPrd || eig_thres < 0) ? 1 : 0;
-            S.nret = 0;
-        }
-        __syncthreads();
-        if (!S.keep) {
-            if (threadIdx.x == 0) nrows[kpi] = 0;
-            continue;
-        }
-
-        // --- primary histogram (determineCanonicalOrientation3D :2779-2817)
-        for (int n = threadIdx.x; n < nsph; n += blockDim.x) {
-            int i = c_tab.sphere[n];
-            float e[3] = { S.dx[i], S.dy[i], S.dz[i] };
-            float fEdgeMagSqr = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
-            int base = -1;
-            if (fEdgeMagSqr != 0) {
-                float fEdgeMag = sqrtf(fEdgeMagSqr);
-                float u[3];
-                for (int k = 0; k < 3; k++) u[k] = e[k] * fRadius / fEdgeMag;
-                for (int k = 0; k < 3; k++) u[k] = u[k] + fRadius;
-                make_contrib((float)((double)u[0] + 0.5), (float)((double)u[1] + 0.5), (float)((double)u[2] + 0.5),
-                             fEdgeMag, &S.contrib[n * 8], base);
-            }
-            S.cbase[n] = base;
-        }
-        __syncthreads();
-        splat_histogram(S.h0, S.contrib, S.cbase, nsph);
-        blur_patch(S.h0, S.h1, S.h2, c_tab.hist_taps, c_tab.n_hist_taps);
-        find_sort_peaks(S.h2, S.psort, S.peaks, &S.np);
-        {
-            int lim = min(S.np, PD);
-            if (threadIdx.x < lim) {
-                float o3[3];
-                interp_point_patch(S.h2, S.peaks[threadIdx.x].x, S.peaks[threadIdx.x].y, S.peaks[threadIdx.x].z, o3);
-                o3[0] -= fRadius; o3[1] -= fRadius; o3[2] -= fRadius;
-                vec_norm(o3);
-                S.oriData[threadIdx.x * 3 + 0] = o3[0]; S.oriData[threadIdx.x * 3 + 1] = o3[1]; S.oriData[threadIdx.x * 3 + 2] = o3[2];
-            }
-        }
-        __syncthreads();
-
-        // --- secondary direction per strong primary peak (:2875-3033)
-        const int np = S.np;
-        const float top = np > 0 ? S.peaks[0].value : 0.0f;
-        for (int pi = 0; pi < np && pi < PD && S.nret < 30; pi++) {
-            if ((double)S.peaks[pi].value < 0.8 * (double)top) break;
-            const float p1[3] = { S.oriData[pi * 3], S.oriData[pi * 3 + 1], S.oriData[pi * 3 + 2] };
-            for (int n = threadIdx.x; n < nsph; n += blockDim.x) {
-                int i = c_tab.sphere[n];
-                float e[3] = { S.dx[i], S.dy[i], S.dz[i] };
-                float fEdgeMag = vec_mag(e);
+        } else if (threadIdx.x >= 32) {
+            for (int n = threadIdx.x - 32; n < nsph; n += blockDim.x - 32) {
+                float e[3] = { S.ex[n], S.ey[n], S.ez[n] };
+                float fEdgeMagSqr = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
                 int base = -1;
-                if (fEdgeMag != 0) {
-                    float u[3] = { e[0], e[1], e[2] };
-                    vec_norm(u);
-                    float fPar = vec_dot(p1, u);
-                    float perp[3];
-                    perp[0] = u[0] - fPar * p1[0];
-                    perp[1] = u[1] - fPar * p1[1];
-                    perp[2] = u[2] - fPar * p1[2];
-                    vec_norm(perp);
-                    for (int k = 0; k < 3; k++) { perp[k] = perp[k] * fRadius; perp[k] = perp[k] + fRadius; }
-                    make_contrib((float)((double)perp[0] + 0.5), (float)((double)perp[1] + 0.5), (float)((double)perp[2] + 0.5),
+                if (fEdgeMagSqr != 0) {
+                    float fEdgeMag = sqrtf(fEdgeMagSqr);
+                    float u[3];
+                    for (int k = 0; k < 3; k++) u[k] = e[k] * fRadius / fEdgeMag;
+                    for (int k = 0; k < 3; k++) u[k] = u[k] + fRadius;
+                    make_contrib((float)((double)u[0] + 0.5), (float)((double)u[1] + 0.5), (float)((double)u[2] + 0.5),
                                  fEdgeMag, &S.contrib[n * 8], base);
                 }
                 S.cbase[n] = base;
             }
-            __syncthreads();
-            splat_histogram(S.h0, S.contrib, S.cbase, nsph);
-            blur_patch(S.h0, S.h1, S.h2, c_tab.hist_taps, c_tab.n_hist_taps);
-            find_sort_peaks(S.h2, S.psort, S.peaks2, &S.np2);
-            if (threadIdx.x == 0) {
-                int nret = S.nret;
-                for (int j = 0; j < S.np2 && nret < PD && nret < 30; j++) {
-                    if (S.peaks2[j].value < 0.5f * S.peaks2[0].value) break;
-                    float p2[3], p3[3];
-                    interp_point_patch(S.h2, S.peaks2[j].x, S.peaks2[j].y, S.peaks2[j].z, p2);
-                    p2[0] -= fRadius; p2[1] -= fRadius; p2[2] -= fRadius;
-                    vec_norm(p2);
-                    float fPar = vec_dot(p1, p2);
-                    p2[0] = p2[0] - fPar * p1[0];
-                    p2[1] = p2[1] - fPar * p1[1];
-                    p2[2] = p2[2] - fPar * p1[2];
-                    vec_norm(p2);
-                    p3[0] = p1[1] * p2[2] - p1[2] * p2[1];
-                    p3[1] = -p1[0] * p2[2] + p1[2] * p2[0];
-                    p3[2] = p1[0] * p2[1] - p1[1] * p2[0];
-                    float *m = &S.rots[nret * 9];
-                    for (int k = 0; k < 3; k++) { m[k] = p1[k]; m[3 + k] = p2[k]; m[6 + k] = p3[k]; }
-                    nret++;
-                }
-                S.nret = nret;
-            }
-            __syncthreads();
+            for (int i = threadIdx.x - 32; i < PVP; i += blockDim.x - 32) S.h0[i] = 0.0f;
+            asm volatile("bar.sync 1, 224;" ::: "memory");    // warps 1..7 only
+            splat_histogram_warp(S.h0, S.contrib, S.cbase, nsph, 1);
         }
-
-        // --- publish
-        const int nret = S.nret;
-        if (threadIdx.x == 0) nrows[kpi] = 1 + nret;
+        __syncthreads();
+        PHASE(4);
+        if (!S.keep) {
+            if (threadIdx.x == 0) kp_nprim[kpi] = -1;
+            continue;
+        }
+        blur_patch(S.h0, S.h1, S.h2, S.taps, c_tab.n_hist_taps);
+        PHASE(7);
+        find_sort_peaks(S.h2, S.pflag, S.psort, S.peaks, &S.np);
+        PHASE(8);
+        // primary directions: peaks >= 0.8 * strongest, at most 11 (:2853-2885)
+        if (threadIdx.x == 0) {
+            int np = S.np, cnt = 0;
+            for (int pi = 0; pi < np && pi < PD; pi++) {
+                if ((double)S.peaks[pi].value < 0.8 * (double)S.peaks[0].value) break;
+                cnt++;
+            }
+            S.nprim = cnt;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < S.nprim) {
+            float o3[3];
+            interp_point_patch(S.h2, S.peaks[threadIdx.x].x, S.peaks[threadIdx.x].y, S.peaks[threadIdx.x].z, o3);
+            o3[0] -= fRadius; o3[1] -= fRadius; o3[2] -= fRadius;
+            vec_norm(o3);
+            float *dst = kp_p1 + ((long long)kpi * PD + threadIdx.x) * 3;
+            dst[0] = o3[0]; dst[1] = o3[1]; dst[2] = o3[2];
+        }
+        if (threadIdx.x == 0) kp_nprim[kpi] = S.nprim;
         if (threadIdx.x < 3) kp_eigs[kpi * 3 + threadIdx.x] = S.eigs[threadIdx.x];
         if (threadIdx.x < 9) kp_ori0[kpi * 9 + threadIdx.x] = S.ori0[threadIdx.x];
-        for (int i = threadIdx.x; i < nret * 9; i += blockDim.x) kp_rots[(long long)kpi * (kMaxRowsPerKp * 9) + i] = S.rots[i];
+        PHASE(13);
     }
 }
 
-// Exclusive prefix sum of rows per keypoint -> first feature row of each keypoint; total -> n_features.
-__global__ void __launch_bounds__(1024) row_offsets_kernel(const int *__restrict__ nrows, const int *__restrict__ kp_count,
+// one CTA per (keypoint, primary direction): secondary direction histogram (:2887-3033)
+__global__ void __launch_bounds__(256) orient_b_kernel(const int *__restrict__ kp_count, const int *__restrict__ kp_nprim,
+                                                       const float *__restrict__ kp_p1, const float *__restrict__ kp_patch0,
+                                                       int *__restrict__ kp_nsec, float *__restrict__ kp_rots)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HistSmem &S = *reinterpret_cast<HistSmem *>(smem_raw);
+    const int nkp = *kp_count;
+    const int nsph = c_tab.n_sphere;
+    const float fRadius = 5.0f;
+    if (threadIdx.x < 12) S.taps[threadIdx.x] = threadIdx.x < 9 ? c_tab.hist_taps[threadIdx.x] : 0.0f;
+    const long long n_work = (long long)nkp * PD;
+    PHASE_INIT();
+    for (long long wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const int kpi = (int)(wi / PD), pi = (int)(wi % PD);
+        const int nprim = kp_nprim[kpi];
+        if (pi >= nprim) {
+            if (threadIdx.x == 0) kp_nsec[wi] = 0;
+            continue;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < PV; i += blockDim.x) S.patch[i] = kp_patch0[(long long)kpi * PV + i];
+        __syncthreads();
+        patch_gradients(S.patch, S.dx, S.dy, S.dz);
+        sphere_gradients(S, nsph);
+        const float *pp = kp_p1 + ((long long)kpi * PD + pi) * 3;
+        const float p1[3] = { pp[0], pp[1], pp[2] };
+        PHASE(9);
+        for (int n = threadIdx.x; n < nsph; n += blockDim.x) {
+            float e[3] = { S.ex[n], S.ey[n], S.ez[n] };
+            float fEdgeMag = vec_mag(e);
+            int base = -1;
+            if (fEdgeMag != 0) {
+                float u[3] = { e[0], e[1], e[2] };
+                vec_norm(u);
+                float fPar = vec_dot(p1, u);
+                float perp[3];
+                perp[0] = u[0] - fPar * p1[0];
+                perp[1] = u[1] - fPar * p1[1];
+                perp[2] = u[2] - fPar * p1[2];
+                vec_norm(perp);
+                for (int k = 0; k < 3; k++) { perp[k] = perp[k] * fRadius; perp[k] = perp[k] + fRadius; }
+                make_contrib((float)((double)perp[0] + 0.5), (float)((double)perp[1] + 0.5), (float)((double)perp[2] + 0.5),
+                             fEdgeMag, &S.contrib[n * 8], base);
+            }
+            S.cbase[n] = base;
+        }
+        for (int i = threadIdx.x; i < PVP; i += blockDim.x) S.h0[i] = 0.0f;
+        __syncthreads();
+        splat_histogram_warp(S.h0, S.contrib, S.cbase, nsph, 0);
+        __syncthreads();
+        PHASE(10);
+        blur_patch(S.h0, S.h1, S.h2, S.taps, c_tab.n_hist_taps);
+        PHASE(11);
+        find_sort_peaks(S.h2, S.pflag, S.psort, S.peaks, &S.np);
+        PHASE(12);
+        // secondary peaks >= 0.5 * strongest, at most 11 per primary (the global cap of 11 is applied later)
+        const int np2 = S.np;
+        if (threadIdx.x < PD) {
+            const int j = threadIdx.x;
+            bool take = j < np2;
+            for (int q = 0; q <= j && take; q++)
+                if (S.peaks[q].value < 0.5f * S.peaks[0].value) take = false;   // first failure breaks the loop
+            if (take) {
+                float p2[3], p3[3];
+                interp_point_patch(S.h2, S.peaks[j].x, S.peaks[j].y, S.peaks[j].z, p2);
+                p2[0] -= fRadius; p2[1] -= fRadius; p2[2] -= fRadius;
+                vec_norm(p2);
+                float fPar = vec_dot(p1, p2);
+                p2[0] = p2[0] - fPar * p1[0];
+                p2[1] = p2[1] - fPar * p1[1];
+                p2[2] = p2[2] - fPar * p1[2];
+                vec_norm(p2);
+                p3[0] = p1[1] * p2[2] - p1[2] * p2[1];
+                p3[1] = -p1[0] * p2[2] + p1[2] * p2[0];
+                p3[2] = p1[0] * p2[1] - p1[1] * p2[0];
+                float *m = kp_rots + (wi * PD + j) * 9;
+                for (int k = 0; k < 3; k++) { m[k] = p1[k]; m[3 + k] = p2[k]; m[6 + k] = p3[k]; }
+            }
+            unsigned bal = __ballot_sync(0x7ffu, take);
+            if (j == 0) kp_nsec[wi] = __popc(bal);
+        }
+        PHASE(13);
+    }
+}
+
+// Rows per keypoint (1 + min(11, sum of secondary counts), or 0 when the eigenvalue test failed),
+// their exclusive prefix sum -> first feature row of each keypoint; total -> n_features.
+__global__ void __launch_bounds__(1024) row_offsets_kernel(const int *__restrict__ kp_nprim, const int *__restrict__ kp_nsec,
+                                                           const int *__restrict__ kp_count, int *__restrict__ nrows,
                                                            int *__restrict__ row_off, int *n_features, int row_cap, int *err)
 {
     __shared__ int s_warp[32];
@@ -793,7 +966,16 @@ __global__ void __launch_bounds__(1024) row_offsets_kernel(const int *__restrict
     __syncthreads();
     for (int start = 0; start < n; start += blockDim.x) {
         int k = start + threadIdx.x;
-        int v = (k < n) ? nrows[k] : 0;
+        int v = 0;
+        if (k < n) {
+            int np = kp_nprim[k];
+            if (np >= 0) {
+                int tot = 0;
+                for (int i = 0; i < np; i++) tot += kp_nsec[(long long)k * PD + i];
+                v = 1 + min(tot, PD);
+            }
+            nrows[k] = v;
+        }
         int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         int inc = v;
         for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
@@ -813,14 +995,17 @@ __global__ void __launch_bounds__(1024) row_offsets_kernel(const int *__restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// Kernel 3: one CTA per feature row (work item = keypoint * 12 + row): re-gather with the row's
-// orientation, descriptor loop of featExtract's main() (reference featExtract.cpp:477-505):
+// Descriptor stage: one CTA per feature row (work item = keypoint * 12 + row): re-gather with the row's
+// orientation, then the descriptor loop of featExtract's main() (reference featExtract.cpp:477-505):
 // NormalizeData, descriptor, rank transform, size factor.
 // ------------------------------------------------------------------------------------------------
 struct DescribeSmem {
-    float patch[PV];
-    float dx[PV], dy[PV], dz[PV];   // SIFT: gradients -> (mag, bin); BRIEF: blur scratch
+    float patch[PVP];
+    float dx[PVP], dy[PVP], dz[PVP];   // SIFT: gradients -> (mag, bin); BRIEF: blur scratch
+    float taps[12];
+    float wlo[12];
     float inv[9];
+    float ori[9];
     float red[2];
     float pc[64];
     float pc2[64];
@@ -829,6 +1014,7 @@ struct DescribeSmem {
 __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ PyramidDesc pyr,
                                                        const s3d_keypoint *__restrict__ kps, const int *__restrict__ kp_count,
                                                        const int *__restrict__ nrows, const int *__restrict__ row_off,
+                                                       const int *__restrict__ kp_nsec,
                                                        const float *__restrict__ kp_eigs, const float *__restrict__ kp_ori0,
                                                        const float *__restrict__ kp_rots, const float *__restrict__ kp_patch0,
                                                        int descriptor, float size_factor, int row_cap,
@@ -839,6 +1025,11 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ P
     DescribeSmem &S = *reinterpret_cast<DescribeSmem *>(smem_raw);
     const int nkp = *kp_count;
     const long long n_work = (long long)nkp * kMaxRowsPerKp;
+    if (threadIdx.x < 12) {
+        S.taps[threadIdx.x] = threadIdx.x < 9 ? c_tab.brief_taps[threadIdx.x] : 0.0f;
+        S.wlo[threadIdx.x] = threadIdx.x < PD ? c_tab.desc_w[threadIdx.x] : 0.0f;
+    }
+    PHASE_INIT();
     for (long long wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
         const int kpi = (int)(wi / kMaxRowsPerKp), r = (int)(wi % kMaxRowsPerKp);
         if (r >= nrows[kpi]) continue;
@@ -847,19 +1038,34 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ P
         __syncthreads();
         const s3d_keypoint kp = kps[kpi];
         const OctaveDesc &o = pyr.oct[kp.octave];
-        const float *ori = (r == 0) ? (kp_ori0 + kpi * 9) : (kp_rots + (long long)kpi * (kMaxRowsPerKp * 9) + (r - 1) * 9);
+        // row r > 0 is the (r-1)-th rotation in (primary, secondary) order
+        if (threadIdx.x == 0) {
+            const float *src;
+            if (r == 0) {
+                src = kp_ori0 + kpi * 9;
+            } else {
+                int left = r - 1, pi = 0;
+                while (left >= kp_nsec[(long long)kpi * PD + pi]) { left -= kp_nsec[(long long)kpi * PD + pi]; pi++; }
+                src = kp_rots + (((long long)kpi * PD + pi) * PD + left) * 9;
+            }
+            float m[9];
+            for (int q = 0; q < 9; q++) { m[q] = src[q]; S.ori[q] = m[q]; }
+            if (r > 0) invert3(m, S.inv);
+        }
+        PHASE(16);
 
         if (r == 0) {
             for (int i = threadIdx.x; i < PV; i += blockDim.x) S.patch[i] = kp_patch0[(long long)kpi * PV + i];
         } else {
-            if (threadIdx.x == 0) { float m[9]; for (int q = 0; q < 9; q++) m[q] = ori[q]; invert3(m, S.inv); }
             __syncthreads();
             gather_patch(o.g[kp.level], o.X, o.Y, o.Z, o.pitch, kp.x, kp.y, kp.z, kp.scale, S.inv, S.patch);
         }
         __syncthreads();
         if (dbg_patches) for (int i = threadIdx.x; i < PV; i += blockDim.x) dbg_patches[(long long)row * PV + i] = S.patch[i];
+        PHASE(17);
 
         normalize_patch(S.patch, S.dx, S.red);
+        PHASE(18);
 
         if (descriptor == S3D_DESC_SIFT) {
             // msResampleFeaturesGradientOrientationHistogram (reference MultiScale.cpp:583-710)
@@ -872,6 +1078,7 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ P
                     vec_norm(e);
                     // dot with (+-1,+-1,+-1) in the reference's bin order, first maximum wins
                     float best = 0.0f;
+#pragma unroll
                     for (int k = 0; k < 8; k++) {
                         float sx = (k & 4) ? -1.0f : 1.0f, sy = (k & 2) ? -1.0f : 1.0f, sz = (k & 1) ? -1.0f : 1.0f;
                         float fDot = sx * e[0] + sy * e[1] + sz * e[2];
@@ -882,27 +1089,33 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ P
                 S.dy[i] = __int_as_float(bin);
             }
             __syncthreads();
+            PHASE(19);
             if (threadIdx.x < 64) {
                 // thread owns PC[((sz*2+sy)*2+sx)*8 + k]; walks the voxels that can reach it in raster order
                 const int k = threadIdx.x & 7, sx = (threadIdx.x >> 3) & 1, sy = (threadIdx.x >> 4) & 1, sz = (threadIdx.x >> 5) & 1;
                 const int x0 = sx ? 5 : 0, y0 = sy ? 5 : 0, z0 = sz ? 5 : 0;
+                float wxs[6];
+#pragma unroll
+                for (int q = 0; q < 6; q++) wxs[q] = sx ? (1.0f - S.wlo[x0 + q]) : S.wlo[x0 + q];
                 float acc = 0.0f;
                 for (int z = z0; z <= z0 + 5; z++) {
-                    float wz = sz ? (1.0f - c_tab.desc_w[z]) : c_tab.desc_w[z];
+                    float wz = sz ? (1.0f - S.wlo[z]) : S.wlo[z];
                     for (int y = y0; y <= y0 + 5; y++) {
-                        float wy = sy ? (1.0f - c_tab.desc_w[y]) : c_tab.desc_w[y];
-                        for (int x = x0; x <= x0 + 5; x++) {
-                            int i = (z * PD + y) * PD + x;
-                            if (__float_as_int(S.dy[i]) == k) {
-                                float wx = sx ? (1.0f - c_tab.desc_w[x]) : c_tab.desc_w[x];
-                                acc = acc + S.dx[i] * wx * wy * wz;
-                            }
-                        }
+                        float wy = sy ? (1.0f - S.wlo[y]) : S.wlo[y];
+                        const int i0 = (z * PD + y) * PD + x0;
+                        int b[6];
+                        float mg[6];
+#pragma unroll
+                        for (int q = 0; q < 6; q++) { b[q] = __float_as_int(S.dy[i0 + q]); mg[q] = S.dx[i0 + q]; }
+#pragma unroll
+                        for (int q = 0; q < 6; q++)
+                            if (b[q] == k) acc = acc + mg[q] * wxs[q] * wy * wz;
                     }
                 }
                 S.pc[threadIdx.x] = acc;
             }
             __syncthreads();
+            PHASE(20);
             // msNormalizeDataPositive (reference MultiScale.cpp:1580-1611)
             if (threadIdx.x == 0) {
                 float fMin = 100000;
@@ -915,7 +1128,7 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ P
             __syncthreads();
         } else {
             // msResampleFeaturesBRIEF (reference MultiScale.cpp:989-1049), blur with CPU semantics
-            blur_patch(S.patch, S.dy, S.dx, c_tab.brief_taps, c_tab.n_brief_taps);
+            blur_patch(S.patch, S.dy, S.dx, S.taps, c_tab.n_brief_taps);
             if (threadIdx.x < 64) {
                 float d = S.dx[c_tab.brief_a[threadIdx.x]] - S.dx[c_tab.brief_b[threadIdx.x]];
                 float v;
@@ -950,9 +1163,10 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ P
             f->flag = (kp.is_max ? 0x10u : 0u) | (r > 0 ? 0x20u : 0u);
             f->x = x * size_factor; f->y = y * size_factor; f->z = z * size_factor; f->scale = sc * size_factor;
             for (int q = 0; q < 3; q++) f->eigs[q] = kp_eigs[kpi * 3 + q];
-            for (int q = 0; q < 9; q++) f->ori[q] = ori[q];
+            for (int q = 0; q < 9; q++) f->ori[q] = S.ori[q];
         }
         if (threadIdx.x < 64) f->pc[threadIdx.x] = S.pc2[threadIdx.x];
+        PHASE(21);
     }
 }
 

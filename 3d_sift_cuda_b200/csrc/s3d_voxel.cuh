@@ -306,6 +306,20 @@ __global__ void __launch_bounds__(256) detect_kernel(const float *__restrict__ f
     bool mx = (l < c) && (r < c);
     bool mn = (l > c) && (r > c);
     if (!(mx || mn)) return;
+    {   // face neighbours first: they reject almost everything that survived the x test
+        float a = centre[i - pitch], b = centre[i + pitch];
+        mx = mx && (a < c) && (b < c);
+        mn = mn && (a > c) && (b > c);
+        if (!(mx || mn)) return;
+        a = centre[i - plane]; b = centre[i + plane];
+        mx = mx && (a < c) && (b < c);
+        mn = mn && (a > c) && (b > c);
+        if (!(mx || mn)) return;
+        a = finer[i];
+        mx = mx && (a < c);
+        mn = mn && (a > c);
+        if (!(mx || mn)) return;
+    }
 #pragma unroll 1
     for (int dz = -1; dz <= 1 && (mx || mn); dz++)
 #pragma unroll 1
@@ -315,17 +329,12 @@ __global__ void __launch_bounds__(256) detect_kernel(const float *__restrict__ f
             if (dz == 0 && dy == 0) b = a; // skip self
             mx = mx && (a < c) && (b < c) && (d < c);
             mn = mn && (a > c) && (b > c) && (d > c);
-        }
-    if (!(mx || mn)) return;
-#pragma unroll 1
-    for (int dz = -1; dz <= 1 && (mx || mn); dz++)
-#pragma unroll 1
-        for (int dy = -1; dy <= 1 && (mx || mn); dy++) {
-            const float *row = finer + i + dz * plane + dy * pitch;
-            float a = row[-1], b = row[0], d = row[1];
+            row = finer + i + dz * plane + dy * pitch;
+            a = row[-1]; b = row[0]; d = row[1];
             mx = mx && (a < c) && (b < c) && (d < c);
             mn = mn && (a > c) && (b > c) && (d > c);
         }
+    if (!(mx || mn)) return;
     if (mx) {
         int k = atomicAdd(maxs.count, 1);
         if (k < cap) maxs.items[k] = s3d_cand{ x, y, z, c };
