@@ -131,7 +131,8 @@ struct Plan {
     Vol stage;                   // dense copy of the input (pitch == X)
     Vol img0;                    // pre-stepped, pitched input of the pyramid
     std::vector<Vol> g, d;       // [oct*6 + level], [oct*5 + level]
-    float *tmp1 = nullptr, *tmp2 = nullptr;
+    float *tmp1 = nullptr;            // scratch of the initial blur (octave-0 size)
+    float *oct_tmp[kMaxOct] = {};     // per-octave blur scratch (octaves run on concurrent branches)
     s3d_cand *cand_raw = nullptr;     // [list][cand_cap], list = (oct*3 + (c-1))*2 + is_max (atomic order)
     s3d_keypoint *kp_stage = nullptr; // [list][cand_cap] refined candidates at their raster rank
     unsigned char *stage_flags = nullptr;
@@ -164,6 +165,11 @@ struct s3d_ctx {
     int march_target = 0;
     bool has_result = false;
     int *h_counts = nullptr;     // pinned: kp_count, n_features, err
+    cudaStream_t cur = nullptr;  // stream the stage launchers enqueue on (main stream or an octave branch)
+    bool timing = false;         // S3D_STAGE_TIMING=1: no graph, events at stage boundaries of the main stream
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    cudaStream_t side[kMaxOct] = {};
+    cudaEvent_t ev_fork[kMaxOct] = {}, ev_done[kMaxOct] = {};
 };
 
 #define CK(call)                                                                                     \
@@ -224,8 +230,16 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
     CK(cudaFuncSetAttribute(orient_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HistSmem)));
     CK(cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DescribeSmem)));
     CK(cudaMallocHost((void **)&ctx->h_counts, 4 * sizeof(int)));
+    ctx->cur = ctx->stream;
+    for (int o = 1; o < kMaxOct; o++) {
+        CK(cudaStreamCreateWithFlags(&ctx->side[o], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_done[o], cudaEventDisableTiming));
+    }
+    for (int o = 0; o < kMaxOct; o++) CK(cudaEventCreateWithFlags(&ctx->ev_fork[o], cudaEventDisableTiming));
     const char *g = getenv("S3D_NO_GRAPH");
     if (g && g[0] == '1') ctx->use_graph = false;
+    const char *tm = getenv("S3D_STAGE_TIMING");
+    if (tm && tm[0] == '1') ctx->timing = true;   // works in graph mode too: the marks become event-record nodes
     const char *mt = getenv("S3D_MARCH_TARGET");
     ctx->march_target = mt ? atoi(mt) : 0;
     return S3D_OK;
@@ -252,6 +266,11 @@ extern "C" void s3d_ctx_destroy(s3d_ctx *ctx)
     if (!ctx) return;
     plan_free(ctx);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+    for (int o = 0; o < kMaxOct; o++) {
+        if (ctx->side[o]) cudaStreamDestroy(ctx->side[o]);
+        if (ctx->ev_fork[o]) cudaEventDestroy(ctx->ev_fork[o]);
+        if (ctx->ev_done[o]) cudaEventDestroy(ctx->ev_done[o]);
+    }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -309,7 +328,7 @@ static void launch_blur_fast(s3d_ctx *ctx, const float *in, float *tmp, float *o
     long long plane = (long long)pitch * Y;
     long long n_chunks = plane * Z / 8;
     // x: in -> out
-    blur_x_kernel<R><<<(unsigned)((n_chunks + 255) / 256), 256, 0, ctx->stream>>>(in, out, pitch, X, n_chunks, t);
+    blur_x_kernel<R><<<(unsigned)((n_chunks + 255) / 256), 256, 0, ctx->cur>>>(in, out, pitch, X, n_chunks, t);
     // y: out -> tmp
     int target = ctx->march_target > 0 ? ctx->march_target : ctx->sm_count * 1024;
     {
@@ -317,7 +336,7 @@ static void launch_blur_fast(s3d_ctx *ctx, const float *in, float *tmp, float *o
         int seg_len, n_seg;
         march_segments(target, cols, Y, seg_len, n_seg);
         dim3 grid((unsigned)((cols + 127) / 128), (unsigned)n_seg);
-        blur_march_kernel<R, false><<<grid, 128, 0, ctx->stream>>>(out, tmp, nullptr, nullptr, cols, pitch, plane, pitch, Y, seg_len, t);
+        blur_march_kernel<R, false><<<grid, 128, 0, ctx->cur>>>(out, tmp, nullptr, nullptr, cols, pitch, plane, pitch, Y, seg_len, t);
     }
     // z: tmp -> out (+ DoG)
     {
@@ -325,8 +344,8 @@ static void launch_blur_fast(s3d_ctx *ctx, const float *in, float *tmp, float *o
         int seg_len, n_seg;
         march_segments(target, cols, Z, seg_len, n_seg);
         dim3 grid((unsigned)((cols + 127) / 128), (unsigned)n_seg);
-        if (dog) blur_march_kernel<R, true><<<grid, 128, 0, ctx->stream>>>(tmp, out, in, dog, cols, plane, 0, plane, Z, seg_len, t);
-        else blur_march_kernel<R, false><<<grid, 128, 0, ctx->stream>>>(tmp, out, nullptr, nullptr, cols, plane, 0, plane, Z, seg_len, t);
+        if (dog) blur_march_kernel<R, true><<<grid, 128, 0, ctx->cur>>>(tmp, out, in, dog, cols, plane, 0, plane, Z, seg_len, t);
+        else blur_march_kernel<R, false><<<grid, 128, 0, ctx->cur>>>(tmp, out, nullptr, nullptr, cols, plane, 0, plane, Z, seg_len, t);
     }
     ctx->launches += 3;
 }
@@ -340,16 +359,16 @@ static void launch_blur_generic(s3d_ctx *ctx, const float *in, float *tmp, float
     for (int j = 0; j < ntaps; j++) t.w[j] = taps[j];
     long long plane = (long long)pitch * Y;
     long long n = plane * Z;
-    blur_x_generic_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(in, out, pitch, X, n, t);
+    blur_x_generic_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->cur>>>(in, out, pitch, X, n, t);
     {
         long long cols = (long long)pitch * Z;
         dim3 grid((unsigned)((cols + 127) / 128), (unsigned)(Y < 32 ? Y : 32));
-        blur_march_generic_kernel<false><<<grid, 128, 0, ctx->stream>>>(out, tmp, nullptr, nullptr, cols, pitch, plane, pitch, Y, t);
+        blur_march_generic_kernel<false><<<grid, 128, 0, ctx->cur>>>(out, tmp, nullptr, nullptr, cols, pitch, plane, pitch, Y, t);
     }
     {
         dim3 grid((unsigned)((plane + 127) / 128), (unsigned)(Z < 32 ? Z : 32));
-        if (dog) blur_march_generic_kernel<true><<<grid, 128, 0, ctx->stream>>>(tmp, out, in, dog, plane, plane, 0, plane, Z, t);
-        else blur_march_generic_kernel<false><<<grid, 128, 0, ctx->stream>>>(tmp, out, nullptr, nullptr, plane, plane, 0, plane, Z, t);
+        if (dog) blur_march_generic_kernel<true><<<grid, 128, 0, ctx->cur>>>(tmp, out, in, dog, plane, plane, 0, plane, Z, t);
+        else blur_march_generic_kernel<false><<<grid, 128, 0, ctx->cur>>>(tmp, out, nullptr, nullptr, plane, plane, 0, plane, Z, t);
     }
     ctx->launches += 3;
 }
@@ -385,6 +404,7 @@ extern "C" s3d_status s3d_blur3d(s3d_ctx *ctx, const float *d_in, float *d_tmp, 
 {
     if (!ctx) return S3D_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
+    ctx->cur = ctx->stream;
     return blur3d(ctx, d_in, d_tmp, d_out, X, Y, Z, pitch, h_taps, ntaps, d_dog);
 }
 
@@ -393,8 +413,9 @@ extern "C" s3d_status s3d_dog(s3d_ctx *ctx, const float *d_a, const float *d_b, 
     if (!ctx) return S3D_ERR_INVALID;
     if (!d_a || !d_b || !d_out || X <= 0 || Y <= 0 || Z <= 0 || pitch < X) return fail(ctx, S3D_ERR_INVALID, "s3d_dog: bad argument");
     CK(cudaSetDevice(ctx->device));
+    ctx->cur = ctx->stream;
     long long n = (long long)pitch * Y * Z;
-    dog_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_a, d_b, d_out, n);
+    dog_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->cur>>>(d_a, d_b, d_out, n);
     ctx->launches++;
     CK(cudaGetLastError());
     return S3D_OK;
@@ -406,9 +427,9 @@ static s3d_status resize_launch(s3d_ctx *ctx, int kind, const float *in, int X, 
     int ox = kind == 2 ? 2 * X : X / 2, oy = kind == 2 ? 2 * Y : Y / 2, oz = kind == 2 ? 2 * Z : Z / 2;
     if (ox < 1 || oy < 1 || oz < 1 || opitch < ox) return fail(ctx, S3D_ERR_INVALID, "resize: bad output shape");
     dim3 block(32, 8), grid((opitch + 31) / 32, (oy + 7) / 8, oz);
-    if (kind == 0) subsample_kernel<<<grid, block, 0, ctx->stream>>>(in, X, Y, Z, pitch, out, ox, oy, oz, opitch);
-    else if (kind == 1) halve_kernel<<<grid, block, 0, ctx->stream>>>(in, X, Y, Z, pitch, out, ox, oy, oz, opitch);
-    else double_kernel<<<grid, block, 0, ctx->stream>>>(in, X, Y, Z, pitch, out, opitch);
+    if (kind == 0) subsample_kernel<<<grid, block, 0, ctx->cur>>>(in, X, Y, Z, pitch, out, ox, oy, oz, opitch);
+    else if (kind == 1) halve_kernel<<<grid, block, 0, ctx->cur>>>(in, X, Y, Z, pitch, out, ox, oy, oz, opitch);
+    else double_kernel<<<grid, block, 0, ctx->cur>>>(in, X, Y, Z, pitch, out, opitch);
     ctx->launches++;
     CK(cudaGetLastError());
     return S3D_OK;
@@ -418,18 +439,21 @@ extern "C" s3d_status s3d_subsample2(s3d_ctx *ctx, const float *d_in, int X, int
 {
     if (!ctx) return S3D_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
+    ctx->cur = ctx->stream;
     return resize_launch(ctx, 0, d_in, X, Y, Z, pitch, d_out, out_pitch);
 }
 extern "C" s3d_status s3d_halve_size(s3d_ctx *ctx, const float *d_in, int X, int Y, int Z, int pitch, float *d_out, int out_pitch)
 {
     if (!ctx) return S3D_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
+    ctx->cur = ctx->stream;
     return resize_launch(ctx, 1, d_in, X, Y, Z, pitch, d_out, out_pitch);
 }
 extern "C" s3d_status s3d_double_size(s3d_ctx *ctx, const float *d_in, int X, int Y, int Z, int pitch, float *d_out, int out_pitch)
 {
     if (!ctx) return S3D_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
+    ctx->cur = ctx->stream;
     return resize_launch(ctx, 2, d_in, X, Y, Z, pitch, d_out, out_pitch);
 }
 
@@ -438,9 +462,9 @@ static s3d_status detect_raw_launch(s3d_ctx *ctx, const float *finer, const floa
                                     s3d_cand *raw_min, int *n_min, s3d_cand *raw_max, int *n_max, int cap)
 {
     if (X < 3 || Y < 3 || Z < 3) return S3D_OK;   // no interior voxel
-    dim3 block(32, 8), grid((X - 2 + 31) / 32, (Y - 2 + 7) / 8, Z - 2);
+    dim3 block(32, 8), grid((X - 2 + 31) / 32, (Y - 2 + 7) / 8, (Z - 2 + kDetectZ - 1) / kDetectZ);
     CandList lmin{ raw_min, n_min }, lmax{ raw_max, n_max };
-    detect_kernel<<<grid, block, 0, ctx->stream>>>(finer, centre, X, Y, Z, pitch, lmin, lmax, cap);
+    detect_kernel<<<grid, block, 0, ctx->cur>>>(finer, centre, X, Y, Z, pitch, lmin, lmax, cap);
     ctx->launches += 1;
     CK(cudaGetLastError());
     return S3D_OK;
@@ -455,8 +479,8 @@ static s3d_status detect_launch(s3d_ctx *ctx, const float *finer, const float *c
     s3d_status st = detect_raw_launch(ctx, finer, centre, X, Y, Z, pitch, raw_min, n_min, raw_max, n_max, cap);
     if (st != S3D_OK) return st;
     int blocks = (cap + 255) / 256;
-    order_candidates_kernel<<<blocks, 256, 0, ctx->stream>>>(raw_min, n_min, out_min, X, Y, cap);
-    order_candidates_kernel<<<blocks, 256, 0, ctx->stream>>>(raw_max, n_max, out_max, X, Y, cap);
+    order_candidates_kernel<<<blocks, 256, 0, ctx->cur>>>(raw_min, n_min, out_min, X, Y, cap);
+    order_candidates_kernel<<<blocks, 256, 0, ctx->cur>>>(raw_max, n_max, out_max, X, Y, cap);
     ctx->launches += 2;
     CK(cudaGetLastError());
     return S3D_OK;
@@ -469,6 +493,7 @@ extern "C" s3d_status s3d_detect(s3d_ctx *ctx, const float *d_finer, const float
     if (!d_finer || !d_centre || !d_min || !d_max || !d_n_min || !d_n_max || cap <= 0 || pitch < X)
         return fail(ctx, S3D_ERR_INVALID, "s3d_detect: bad argument");
     CK(cudaSetDevice(ctx->device));
+    ctx->cur = ctx->stream;
     s3d_cand *raw = nullptr;
     CK(cudaMallocAsync((void **)&raw, sizeof(s3d_cand) * 2 * (size_t)cap, ctx->stream));
     CK(cudaMemsetAsync(d_n_min, 0, sizeof(int), ctx->stream));
@@ -542,6 +567,7 @@ static s3d_status plan_build(s3d_ctx *ctx, int X, int Y, int Z, const s3d_params
             p->d.push_back(v);
             od.d[j] = v.p;
         }
+        PA(&p->oct_tmp[n_oct], (size_t)od.pitch * oy * oz);
         n_oct++;
         ox /= 2; oy /= 2; oz /= 2;
     }
@@ -602,17 +628,48 @@ static s3d_status plan_build(s3d_ctx *ctx, int X, int Y, int Z, const s3d_params
     CK(cudaMemsetAsync(p->tmp1, 0, p->img0.elems() * sizeof(float), ctx->stream));
     for (auto &v : p->g) CK(cudaMemsetAsync(v.p, 0, v.elems() * sizeof(float), ctx->stream));
     for (auto &v : p->d) CK(cudaMemsetAsync(v.p, 0, v.elems() * sizeof(float), ctx->stream));
+    for (int o = 0; o < n_oct; o++)
+        CK(cudaMemsetAsync(p->oct_tmp[o], 0, (size_t)p->pyr.oct[o].pitch * p->pyr.oct[o].Y * p->pyr.oct[o].Z * sizeof(float), ctx->stream));
     return S3D_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------
 // the whole path, enqueued on the stream (input already in plan->stage)
 // ---------------------------------------------------------------------------------------------------
+static void mark(s3d_ctx *ctx, const char *name)
+{
+    if (!ctx->timing) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, ctx->stream);
+    ctx->marks.emplace_back(name, e);
+}
+
+static void report_marks(s3d_ctx *ctx)
+{
+    if (!ctx->timing || ctx->marks.empty()) return;
+    fprintf(stderr, "s3d stage timing (main stream, us since previous mark):\n");
+    for (size_t i = 1; i < ctx->marks.size(); i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->marks[i - 1].second, ctx->marks[i].second);
+        fprintf(stderr, "  %-28s %9.1f\n", ctx->marks[i].first.c_str(), ms * 1e3f);
+    }
+    float tot = 0;
+    cudaEventElapsedTime(&tot, ctx->marks.front().second, ctx->marks.back().second);
+    fprintf(stderr, "  %-28s %9.1f\n", "total", tot * 1e3f);
+    if (!ctx->use_graph) {
+        for (auto &m : ctx->marks) cudaEventDestroy(m.second);
+        ctx->marks.clear();
+    }
+}
+
 static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
 {
     Plan *p = ctx->plan;
     cudaStream_t st = ctx->stream;
     int *kp_count = p->counts + p->n_lists, *n_features = kp_count + 1, *err = kp_count + 2;
+    ctx->cur = st;
+    mark(ctx, "start");
     CK(cudaMemsetAsync(p->counts, 0, sizeof(int) * (p->n_lists + 8), st));
 
     // pre-step: -2+ / -2- / plain copy into the pitched pyramid input
@@ -623,49 +680,68 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
         s3d_status s = resize_launch(ctx, 1, p->stage.p, p->X, p->Y, p->Z, p->X, p->img0.p, p->img0.pitch);
         if (s != S3D_OK) return s;
     } else {
-        long long rows = (long long)p->Y * p->Z, n = rows * p->img0.pitch;
-        pad_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->stage.p, p->X, rows, p->img0.p, p->img0.pitch);
+        long long rows = (long long)p->Y * p->Z;
+        dim3 grid((p->img0.pitch + 255) / 256, (unsigned)(rows < 8192 ? rows : 8192));
+        pad_rows_kernel<<<grid, 256, 0, st>>>(p->stage.p, p->X, rows, p->img0.p, p->img0.pitch);
         ctx->launches++;
     }
     if (p->n_oct == 0) {
         ctx->has_result = true;
         return S3D_OK;
     }
+    mark(ctx, "pre-step/pad");
     // initial blur (MultiScale.cpp:298)
     {
         Vol &g0 = p->g[0];
         s3d_status s = blur3d(ctx, p->img0.p, p->tmp1, g0.p, g0.X, g0.Y, g0.Z, g0.pitch, p->init_taps, p->n_init_taps, nullptr);
         if (s != S3D_OK) return s;
     }
+    mark(ctx, "initial blur");
+    // Octave o+1 only needs level 3 of octave o, so every octave runs on its own branch (stream / graph
+    // branch): the tail of an octave (levels 4, 5 and its three detection passes) overlaps the whole
+    // chain of smaller octaves, which is launch-latency bound.
     for (int o = 0; o < p->n_oct; o++) {
         const OctaveDesc &od = p->pyr.oct[o];
+        ctx->cur = (o == 0) ? st : ctx->side[o];
+        if (o > 0) CK(cudaStreamWaitEvent(ctx->cur, ctx->ev_fork[o - 1], 0));
         for (int j = 1; j < 6; j++) {
             Vol &a = p->g[o * 6 + j - 1], &b = p->g[o * 6 + j], &dd = p->d[o * 5 + j - 1];
-            s3d_status s = blur3d(ctx, a.p, p->tmp1, b.p, od.X, od.Y, od.Z, od.pitch, p->lvl_taps[j - 1], p->n_lvl_taps[j - 1], dd.p);
-            if (s != S3D_OK) return s;
+            s3d_status s = blur3d(ctx, a.p, p->oct_tmp[o], b.p, od.X, od.Y, od.Z, od.pitch, p->lvl_taps[j - 1], p->n_lvl_taps[j - 1], dd.p);
+            if (s != S3D_OK) { ctx->cur = st; return s; }
             if (j == 3 && o + 1 < p->n_oct) {
                 const OctaveDesc &nx = p->pyr.oct[o + 1];
                 s = resize_launch(ctx, 0, b.p, od.X, od.Y, od.Z, od.pitch, p->g[(o + 1) * 6].p, nx.pitch);
-                if (s != S3D_OK) return s;
+                if (s != S3D_OK) { ctx->cur = st; return s; }
+                CK(cudaEventRecord(ctx->ev_fork[o], ctx->cur));
             }
+            if (o == 0) { char nm[32]; snprintf(nm, sizeof(nm), "oct0 level %d", j); mark(ctx, nm); }
         }
         for (int c = 1; c <= 3; c++) {
             int l0 = (o * 3 + (c - 1)) * 2;
             s3d_status s = detect_raw_launch(ctx, od.d[c - 1], od.d[c], od.X, od.Y, od.Z, od.pitch,
                                              p->cand_raw + (size_t)l0 * p->cand_cap, p->counts + l0,
                                              p->cand_raw + (size_t)(l0 + 1) * p->cand_cap, p->counts + l0 + 1, p->cand_cap);
-            if (s != S3D_OK) return s;
+            if (s != S3D_OK) { ctx->cur = st; return s; }
         }
+        if (o > 0) CK(cudaEventRecord(ctx->ev_done[o], ctx->cur));
+        if (o == 0) mark(ctx, "oct0 detect x3");
     }
+    ctx->cur = st;
+    for (int o = 1; o < p->n_oct; o++) CK(cudaStreamWaitEvent(st, ctx->ev_done[o], 0));
+    mark(ctx, "join octaves>=1");
     // candidate stage: rank + validate + refine every candidate of every list, then ordered compaction
     ListDesc L{ p->n_lists, p->cand_cap, p->cand_raw, p->counts };
     cand_refine_kernel<<<dim3(p->n_lists, 4), 256, 0, st>>>(p->pyr, L, p->kp_stage, p->stage_flags, err);
+    mark(ctx, "cand_refine");
     compact_kernel<<<1, 1024, 0, st>>>(L, p->kp_stage, p->stage_flags, p->kps, kp_count, p->kp_cap, err);
+    mark(ctx, "compact");
     // orientation: per keypoint, then per (keypoint, primary direction)
     float eig = prm->eig_thres;
     orient_a_kernel<<<ctx->sm_count * 3, 256, sizeof(HistSmem), st>>>(p->pyr, p->kps, kp_count, eig, p->kp_nprim, p->kp_eigs,
                                                                      p->kp_ori0, p->kp_p1, p->kp_patch0);
+    mark(ctx, "orient_a");
     orient_b_kernel<<<ctx->sm_count * 3, 256, sizeof(HistSmem), st>>>(kp_count, p->kp_nprim, p->kp_p1, p->kp_patch0, p->kp_nsec, p->kp_rots);
+    mark(ctx, "orient_b");
     row_offsets_kernel<<<1, 1024, 0, st>>>(p->kp_nprim, p->kp_nsec, kp_count, p->nrows, p->row_off, n_features, p->row_cap, err);
     float size_factor = 1.0f;
     if (p->double_mode > 0) size_factor /= 2; else if (p->double_mode < 0) size_factor *= 2;
@@ -673,6 +749,7 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     describe_kernel<<<grid_d, 128, sizeof(DescribeSmem), st>>>(p->pyr, p->kps, kp_count, p->nrows, p->row_off, p->kp_nsec, p->kp_eigs,
                                                               p->kp_ori0, p->kp_rots, p->kp_patch0, prm->descriptor, size_factor,
                                                               p->row_cap, p->feats, p->dbg_patches, p->dbg_prerank);
+    mark(ctx, "row_offsets+describe");
     ctx->launches += 6;
     CK(cudaGetLastError());
     return S3D_OK;
@@ -704,6 +781,8 @@ static s3d_status run_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     if (!p->graph || p->graph_descriptor != prm->descriptor || p->graph_eig != prm->eig_thres) {
         if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }
         cudaGraph_t g = nullptr;
+        for (auto &m : ctx->marks) cudaEventDestroy(m.second);
+        ctx->marks.clear();
         CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
         ctx->launches = 0;
         s3d_status s = enqueue_pipeline(ctx, prm);
@@ -751,6 +830,7 @@ static s3d_status fetch_counts(s3d_ctx *ctx)
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(ctx->h_counts, p->counts + p->n_lists, 3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    report_marks(ctx);
     int err = ctx->h_counts[2];
     if (err) {
         char b[256];

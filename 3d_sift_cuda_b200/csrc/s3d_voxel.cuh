@@ -104,33 +104,67 @@ __global__ void __launch_bounds__(128) blur_march_kernel(const float *__restrict
     if (q >= n_cols) return;
     long long other = q / w_inner;
     long long col = other * other_stride + (q - other * w_inner);
-    int a0 = blockIdx.y * seg_len;
-    int a1 = min(len, a0 + seg_len);
-    int n_in = (a1 - a0) + 2 * R;
-    const float *src = in + col;
+    const int a0 = blockIdx.y * seg_len;
+    const int a1 = min(len, a0 + seg_len);
+    const int L = a1 - a0;
+    const int n_in = L + 2 * R;
     float acc[T];
 #pragma unroll
     for (int s = 0; s < T; s++) acc[s] = 0.0f;
-    for (int ub = 0; ub < n_in; ub += T) {
-        float v[T];
+    // Rounds of T input steps.  The loads of round k+1 (and, for DOG, the T values of `prev` that round
+    // k+1 will subtract from) are issued before round k is computed.  A round whose inputs / outputs
+    // are all inside the volume / segment takes the predicate-free path (uniform per block).
+    float nxt[T], pnx[T];
+    const float *pin = in + col + (long long)(a0 - R) * stride;     // input of step u = 0
+    const float *ppv = prev + col + (long long)(a0 - 2 * R) * stride;   // prev of the output completed at step 0
+    float *pout = out + col + (long long)(a0 - 2 * R) * stride;
+    float *pdog = dog + col + (long long)(a0 - 2 * R) * stride;
+    auto load_round = [&](int ub) {
+        const int i0 = a0 - R + ub;
+        if (i0 >= 0 && i0 + T <= len && ub + T <= n_in) {
 #pragma unroll
-        for (int s = 0; s < T; s++) {
-            int i = a0 - R + ub + s;
-            v[s] = (i >= 0 && i < len && ub + s < n_in) ? __ldg(src + (long long)i * stride) : 0.0f;
+            for (int s = 0; s < T; s++) nxt[s] = __ldg(pin + (long long)s * stride);
+        } else {
+#pragma unroll
+            for (int s = 0; s < T; s++) {
+                int i = i0 + s;
+                nxt[s] = (i >= 0 && i < len && ub + s < n_in) ? __ldg(pin + (long long)s * stride) : 0.0f;
+            }
         }
+        if (DOG) {
+            const int c0 = ub - 2 * R;          // output offsets c0 .. c0+T-1 relative to a0
+            if (c0 >= 0 && c0 + T <= L) {
+#pragma unroll
+                for (int s = 0; s < T; s++) pnx[s] = __ldg(ppv + (long long)s * stride);
+            } else {
+#pragma unroll
+                for (int s = 0; s < T; s++) pnx[s] = (c0 + s >= 0 && c0 + s < L) ? __ldg(ppv + (long long)s * stride) : 0.0f;
+            }
+            ppv += (long long)T * stride;
+        }
+        pin += (long long)T * stride;
+    };
+    load_round(0);
+    for (int ub = 0; ub < n_in; ub += T) {
+        float v[T], pv[T];
+#pragma unroll
+        for (int s = 0; s < T; s++) { v[s] = nxt[s]; if (DOG) pv[s] = pnx[s]; }
+        if (ub + T < n_in) load_round(ub + T);
+        const int c0 = ub - 2 * R;
+        const bool full = (c0 >= 0 && c0 + T <= L);
 #pragma unroll
         for (int s = 0; s < T; s++) {
             acc[s] = taps.w[0] * v[s];
 #pragma unroll
             for (int j = 1; j <= 2 * R; j++) acc[(s - j + 2 * T) % T] = acc[(s - j + 2 * T) % T] + taps.w[j] * v[s];
-            int c = a0 + ub + s - 2 * R;
-            if (c >= a0 && c < a1) {
+            if (full || (c0 + s >= 0 && c0 + s < L)) {
                 float g = acc[(s + 1) % T];
-                long long idx = col + (long long)c * stride;
-                out[idx] = g;
-                if (DOG) dog[idx] = __ldg(prev + idx) + (-1.0f) * g;
+                pout[(long long)s * stride] = g;
+                if (DOG) pdog[(long long)s * stride] = pv[s] - g;   // == prev + (-1)*g, fioMultSum
             }
         }
+        pout += (long long)T * stride;
+        if (DOG) pdog += (long long)T * stride;
     }
 }
 
@@ -260,14 +294,13 @@ __global__ void double_kernel(const float *__restrict__ in, int X, int Y, int Z,
     out[((long long)z * DY + y) * opitch + x] = r;
 }
 
-// dense (pitch == X) <-> pitched copies with zeroed padding
+// dense (pitch == X) <-> pitched copies with zeroed padding; grid.y = rows
 __global__ void pad_rows_kernel(const float *__restrict__ in, int X, long long rows, float *__restrict__ out, int pitch)
 {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * pitch) return;
-    long long row = i / pitch;
-    int x = (int)(i - row * pitch);
-    out[i] = (x < X) ? in[row * X + x] : 0.0f;
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= pitch) return;
+    for (long long row = blockIdx.y; row < rows; row += gridDim.y)
+        out[row * pitch + x] = (x < X) ? __ldg(in + row * X + x) : 0.0f;
 }
 
 __global__ void unpad_rows_kernel(const float *__restrict__ in, int pitch, long long rows, float *__restrict__ out, int X)
@@ -291,57 +324,70 @@ struct CandList {
     int *count;
 };
 
+constexpr int kDetectZ = 8;   // centre voxels per thread along z
+
 __global__ void __launch_bounds__(256) detect_kernel(const float *__restrict__ finer, const float *__restrict__ centre,
                                                      int X, int Y, int Z, int pitch,
                                                      CandList mins, CandList maxs, int cap)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x + 1;
     int y = blockIdx.y * blockDim.y + threadIdx.y + 1;
-    int z = blockIdx.z + 1;
-    if (x > X - 2 || y > Y - 2 || z > Z - 2) return;
+    int z0 = blockIdx.z * kDetectZ + 1;
+    if (x > X - 2 || y > Y - 2 || z0 > Z - 2) return;
     long long plane = (long long)pitch * Y;
-    long long i = (long long)z * plane + (long long)y * pitch + x;
-    float c = centre[i];
-    float l = centre[i - 1], r = centre[i + 1];
-    bool mx = (l < c) && (r < c);
-    bool mn = (l > c) && (r > c);
-    if (!(mx || mn)) return;
-    {   // face neighbours first: they reject almost everything that survived the x test
-        float a = centre[i - pitch], b = centre[i + pitch];
-        mx = mx && (a < c) && (b < c);
-        mn = mn && (a > c) && (b > c);
-        if (!(mx || mn)) return;
-        a = centre[i - plane]; b = centre[i + plane];
-        mx = mx && (a < c) && (b < c);
-        mn = mn && (a > c) && (b > c);
-        if (!(mx || mn)) return;
-        a = finer[i];
-        mx = mx && (a < c);
-        mn = mn && (a > c);
-        if (!(mx || mn)) return;
+    long long base = (long long)y * pitch + x;
+    // the column z0-1 .. z0+kDetectZ of the centre volume, all loads in flight together
+    float col[kDetectZ + 2];
+#pragma unroll
+    for (int k = 0; k < kDetectZ + 2; k++) {
+        int z = z0 - 1 + k;
+        col[k] = (z <= Z - 1) ? __ldg(centre + (long long)z * plane + base) : 0.0f;
     }
-#pragma unroll 1
-    for (int dz = -1; dz <= 1 && (mx || mn); dz++)
-#pragma unroll 1
-        for (int dy = -1; dy <= 1 && (mx || mn); dy++) {
-            const float *row = centre + i + dz * plane + dy * pitch;
-            float a = row[-1], b = row[0], d = row[1];
-            if (dz == 0 && dy == 0) b = a; // skip self
-            mx = mx && (a < c) && (b < c) && (d < c);
-            mn = mn && (a > c) && (b > c) && (d > c);
-            row = finer + i + dz * plane + dy * pitch;
-            a = row[-1]; b = row[0]; d = row[1];
-            mx = mx && (a < c) && (b < c) && (d < c);
-            mn = mn && (a > c) && (b > c) && (d > c);
+#pragma unroll
+    for (int k = 0; k < kDetectZ; k++) {
+        int z = z0 + k;
+        if (z > Z - 2) break;
+        float c = col[k + 1];
+        bool mx = (col[k] < c) && (col[k + 2] < c);
+        bool mn = (col[k] > c) && (col[k + 2] > c);
+        if (!(mx || mn)) continue;
+        long long i = (long long)z * plane + base;
+        {   // remaining face neighbours, then the finer centre: they reject almost everything
+            float a = centre[i - 1], b = centre[i + 1];
+            mx = mx && (a < c) && (b < c);
+            mn = mn && (a > c) && (b > c);
+            if (!(mx || mn)) continue;
+            a = centre[i - pitch]; b = centre[i + pitch];
+            mx = mx && (a < c) && (b < c);
+            mn = mn && (a > c) && (b > c);
+            if (!(mx || mn)) continue;
+            a = finer[i];
+            mx = mx && (a < c);
+            mn = mn && (a > c);
+            if (!(mx || mn)) continue;
         }
-    if (!(mx || mn)) return;
-    if (mx) {
-        int k = atomicAdd(maxs.count, 1);
-        if (k < cap) maxs.items[k] = s3d_cand{ x, y, z, c };
-    }
-    if (mn) {
-        int k = atomicAdd(mins.count, 1);
-        if (k < cap) mins.items[k] = s3d_cand{ x, y, z, c };
+#pragma unroll 1
+        for (int dz = -1; dz <= 1 && (mx || mn); dz++)
+#pragma unroll 1
+            for (int dy = -1; dy <= 1 && (mx || mn); dy++) {
+                const float *row = centre + i + dz * plane + dy * pitch;
+                float a = row[-1], b = row[0], d = row[1];
+                if (dz == 0 && dy == 0) b = a; // skip self
+                mx = mx && (a < c) && (b < c) && (d < c);
+                mn = mn && (a > c) && (b > c) && (d > c);
+                row = finer + i + dz * plane + dy * pitch;
+                a = row[-1]; b = row[0]; d = row[1];
+                mx = mx && (a < c) && (b < c) && (d < c);
+                mn = mn && (a > c) && (b > c) && (d > c);
+            }
+        if (mx) {
+            int kk = atomicAdd(maxs.count, 1);
+            if (kk < cap) maxs.items[kk] = s3d_cand{ x, y, z, c };
+        }
+        if (mn) {
+            int kk = atomicAdd(mins.count, 1);
+            if (kk < cap) mins.items[kk] = s3d_cand{ x, y, z, c };
+        }
     }
 }
 
