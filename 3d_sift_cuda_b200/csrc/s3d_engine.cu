@@ -141,7 +141,7 @@ struct Plan {
     s3d_keypoint *kps = nullptr;
     int *nrows = nullptr, *row_off = nullptr;
     float *kp_eigs = nullptr, *kp_ori0 = nullptr, *kp_rots = nullptr, *kp_patch0 = nullptr, *kp_p1 = nullptr;
-    int *kp_nprim = nullptr, *kp_nsec = nullptr;
+    int *kp_nprim = nullptr, *kp_nsec = nullptr, *work_b = nullptr, *row_map = nullptr;
     s3d_feature *feats = nullptr;
     float *dbg_patches = nullptr, *dbg_prerank = nullptr;
     PyramidDesc pyr;
@@ -239,7 +239,7 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
     const char *g = getenv("S3D_NO_GRAPH");
     if (g && g[0] == '1') ctx->use_graph = false;
     const char *tm = getenv("S3D_STAGE_TIMING");
-    if (tm && tm[0] == '1') ctx->timing = true;   // works in graph mode too: the marks become event-record nodes
+    if (tm && tm[0] == '1') { ctx->timing = true; ctx->use_graph = false; }   // event nodes inside graphs carry no timestamps
     const char *mt = getenv("S3D_MARCH_TARGET");
     ctx->march_target = mt ? atoi(mt) : 0;
     return S3D_OK;
@@ -616,6 +616,8 @@ static s3d_status plan_build(s3d_ctx *ctx, int X, int Y, int Z, const s3d_params
     PA(&p->kp_p1, (size_t)kp_cap * PD * 3);
     PA(&p->kp_nprim, kp_cap);
     PA(&p->kp_nsec, (size_t)kp_cap * PD);
+    PA(&p->work_b, (size_t)kp_cap * PD);
+    PA(&p->row_map, row_cap);
     PA(&p->kp_patch0, (size_t)kp_cap * PV);
     PA(&p->feats, row_cap);
     if (p->keep_patches) {
@@ -639,6 +641,10 @@ static s3d_status plan_build(s3d_ctx *ctx, int X, int Y, int Z, const s3d_params
 static void mark(s3d_ctx *ctx, const char *name)
 {
     if (!ctx->timing) return;
+    if (!strcmp(name, "start")) {     // keep only the latest extraction
+        for (auto &m : ctx->marks) cudaEventDestroy(m.second);
+        ctx->marks.clear();
+    }
     cudaEvent_t e;
     cudaEventCreate(&e);
     cudaEventRecord(e, ctx->stream);
@@ -737,16 +743,17 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     mark(ctx, "compact");
     // orientation: per keypoint, then per (keypoint, primary direction)
     float eig = prm->eig_thres;
+    int *work_b_count = kp_count + 3;
     orient_a_kernel<<<ctx->sm_count * 3, 256, sizeof(HistSmem), st>>>(p->pyr, p->kps, kp_count, eig, p->kp_nprim, p->kp_eigs,
-                                                                     p->kp_ori0, p->kp_p1, p->kp_patch0);
+                                                                     p->kp_ori0, p->kp_p1, p->kp_patch0, p->work_b, work_b_count);
     mark(ctx, "orient_a");
-    orient_b_kernel<<<ctx->sm_count * 3, 256, sizeof(HistSmem), st>>>(kp_count, p->kp_nprim, p->kp_p1, p->kp_patch0, p->kp_nsec, p->kp_rots);
+    orient_b_kernel<<<ctx->sm_count * 6, 256, sizeof(HistSmem), st>>>(p->work_b, work_b_count, p->kp_p1, p->kp_patch0, p->kp_nsec, p->kp_rots);
     mark(ctx, "orient_b");
-    row_offsets_kernel<<<1, 1024, 0, st>>>(p->kp_nprim, p->kp_nsec, kp_count, p->nrows, p->row_off, n_features, p->row_cap, err);
+    row_offsets_kernel<<<1, 1024, 0, st>>>(p->kp_nprim, p->kp_nsec, kp_count, p->nrows, p->row_off, p->row_map, n_features, p->row_cap, err);
     float size_factor = 1.0f;
     if (p->double_mode > 0) size_factor /= 2; else if (p->double_mode < 0) size_factor *= 2;
-    int grid_d = ctx->sm_count * 8;
-    describe_kernel<<<grid_d, 128, sizeof(DescribeSmem), st>>>(p->pyr, p->kps, kp_count, p->nrows, p->row_off, p->kp_nsec, p->kp_eigs,
+    int grid_d = ctx->sm_count * 10;
+    describe_kernel<<<grid_d, 128, sizeof(DescribeSmem), st>>>(p->pyr, p->kps, n_features, p->row_map, p->kp_nsec, p->kp_eigs,
                                                               p->kp_ori0, p->kp_rots, p->kp_patch0, prm->descriptor, size_factor,
                                                               p->row_cap, p->feats, p->dbg_patches, p->dbg_prerank);
     mark(ctx, "row_offsets+describe");

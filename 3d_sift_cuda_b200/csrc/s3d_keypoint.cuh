@@ -303,12 +303,11 @@ __device__ void blur_patch(const float *src, float *tmp, float *dst, const float
 #define S3D_SIGN(a, b) ((b) >= 0.0 ? fabs(a) : -fabs(a))
 #define S3D_PYTHAG(a, b) (sqrt((a) * (a) + (b) * (b)))
 
-__device__ void svd3(float mat[3][3], float w[3], float v[3][3])
+__device__ void svd3(float (*mat)[3], float *w, float (*v)[3], double *rv1)
 {
     const int m = 3, n = 3;
     int flag, i, its, j, jj, k, l = 0, nm = 0;
     double anorm, c, f, g, h, s, scale, x, y, z;
-    double rv1[3];
     g = scale = anorm = 0.0;
     for (i = 1; i <= n; i++) {
         l = i + 1;
@@ -480,7 +479,7 @@ __device__ void svd3(float mat[3][3], float w[3], float v[3][3])
     }
 }
 
-__device__ void sort_eigen(float w[3], float v[3][3])
+__device__ void sort_eigen(float *w, float (*v)[3])
 {
     for (int i = 0; i < 3; i++)
         for (int j = i + 1; j < 3; j++)
@@ -624,6 +623,8 @@ struct HistSmem {
     float ex[kMaxSphere], ey[kMaxSphere], ez[kMaxSphere];
     s3d_cand peaks[128], psort[128];
     unsigned char pflag[736];
+    float svd_mat[3][3], svd_v[3][3], svd_w[4];
+    double svd_rv1[4];
     float taps[12];
     float oriData[PD * 3];
     float inv[9];
@@ -638,6 +639,9 @@ struct HistSmem {
 // order: 8 lanes own the 8 corners of a voxel's 2x2x2 footprint (distinct bins), __syncwarp orders
 // successive voxels (fioIncPixelTrilinearInterp, reference FeatureIO.cpp:853-889).  Runs on warp
 // `warp`; the caller synchronises the block afterwards.
+// (A bin-owner variant that merges per-(z,y) bucket lists was measured 10x SLOWER on real patches:
+// orientation histograms are peaked by construction, so a few bins receive most of the ~485 voxels
+// and their owner threads serialise; the in-order warp walk costs ~40 cycles per voxel regardless.)
 __device__ void splat_histogram_warp(float *hist, const float *contrib, const int *cbase, int n_sphere, int warp)
 {
     if ((int)(threadIdx.x >> 5) == warp) {
@@ -757,7 +761,8 @@ __global__ void __launch_bounds__(256) orient_a_kernel(const __grid_constant__ P
                                                        const s3d_keypoint *__restrict__ kps, const int *__restrict__ kp_count,
                                                        float eig_thres,
                                                        int *__restrict__ kp_nprim, float *__restrict__ kp_eigs, float *__restrict__ kp_ori0,
-                                                       float *__restrict__ kp_p1, float *__restrict__ kp_patch0)
+                                                       float *__restrict__ kp_p1, float *__restrict__ kp_patch0,
+                                                       int *__restrict__ work_b, int *work_b_count)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HistSmem &S = *reinterpret_cast<HistSmem *>(smem_raw);
@@ -786,34 +791,50 @@ __global__ void __launch_bounds__(256) orient_a_kernel(const __grid_constant__ P
         // --- structure tensor over the sphere voxels, raster order (determineOrientation3D)
         patch_gradients(S.patch, S.dx, S.dy, S.dz);
         sphere_gradients(S, nsph);
-        if (threadIdx.x < 9) {
-            const float *ea = (threadIdx.x / 3 == 0) ? S.ex : (threadIdx.x / 3 == 1) ? S.ey : S.ez;
-            const float *eb = (threadIdx.x % 3 == 0) ? S.ex : (threadIdx.x % 3 == 1) ? S.ey : S.ez;
-            float m = 0.0f;
-            int n = 0;
-            for (; n + 4 <= nsph; n += 4) {
-                float4 a = *reinterpret_cast<const float4 *>(ea + n), b = *reinterpret_cast<const float4 *>(eb + n);
-                m = m + a.x * b.x; m = m + a.y * b.y; m = m + a.z * b.z; m = m + a.w * b.w;
-            }
-            for (; n < nsph; n++) m = m + ea[n] * eb[n];
-            S.fmat[threadIdx.x] = m;
-        }
-        __syncthreads();
         PHASE(3);
 
-        // --- warp 0 lane 0: SVD + eigenvalue test; the other warps meanwhile build the primary histogram
-        //     (determineCanonicalOrientation3D :2779-2817), whose result is simply dropped if the test fails
+        // --- warp 0: structure tensor over the sphere voxels in raster order (9 lanes, one accumulator
+        //     each), then lane 0 runs the SVD + eigenvalue test (determineOrientation3D).  The other warps
+        //     meanwhile build the primary direction histogram (determineCanonicalOrientation3D :2779-2817),
+        //     whose result is simply dropped if the test fails.
+        if (threadIdx.x < 32) {
+            if (threadIdx.x < 9) {
+                const float *ea = (threadIdx.x / 3 == 0) ? S.ex : (threadIdx.x / 3 == 1) ? S.ey : S.ez;
+                const float *eb = (threadIdx.x % 3 == 0) ? S.ex : (threadIdx.x % 3 == 1) ? S.ey : S.ez;
+                float m = 0.0f;
+                int n = 0;
+                for (; n + 4 <= nsph; n += 4) {
+                    float4 a = *reinterpret_cast<const float4 *>(ea + n), b = *reinterpret_cast<const float4 *>(eb + n);
+                    m = m + a.x * b.x; m = m + a.y * b.y; m = m + a.z * b.z; m = m + a.w * b.w;
+                }
+                for (; n < nsph; n++) m = m + ea[n] * eb[n];
+                S.fmat[threadIdx.x] = m;
+            }
+            __syncwarp();
+        }
         if (threadIdx.x == 0) {
-            float mat[3][3], w[3], v[3][3];
+#ifdef S3D_PHASE_TIMERS
+            long long t_svd = clock64();
+#endif
+            // the SVD's small arrays live in shared memory (dynamic indexing would otherwise spill to local
+            // memory, whose L1 traffic also slows the histogram warp running next to it)
+            float (*mat)[3] = S.svd_mat, (*v)[3] = S.svd_v;
+            float *w = S.svd_w;
             for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) mat[a][b] = S.fmat[a * 3 + b];
-            svd3(mat, w, v);
+            svd3(mat, w, v, S.svd_rv1);
             sort_eigen(w, v);
             for (int a = 0; a < 3; a++) { S.eigs[a] = w[a]; for (int b = 0; b < 3; b++) S.ori0[a * 3 + b] = v[a][b]; }
             float fEigSum = w[0] + w[1] + w[2];
             float fEigPrd = w[0] * w[1] * w[2];
             float fEigSumProd = fEigSum * fEigSum * fEigSum;
             S.keep = (fEigSumProd < eig_thres * fEigPrd || eig_thres < 0) ? 1 : 0;
+#ifdef S3D_PHASE_TIMERS
+            atomicAdd(&g_phase[14], (unsigned long long)(clock64() - t_svd));
+#endif
         } else if (threadIdx.x >= 32) {
+#ifdef S3D_PHASE_TIMERS
+            long long t_spl = clock64();
+#endif
             for (int n = threadIdx.x - 32; n < nsph; n += blockDim.x - 32) {
                 float e[3] = { S.ex[n], S.ey[n], S.ez[n] };
                 float fEdgeMagSqr = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
@@ -830,7 +851,13 @@ __global__ void __launch_bounds__(256) orient_a_kernel(const __grid_constant__ P
             }
             for (int i = threadIdx.x - 32; i < PVP; i += blockDim.x - 32) S.h0[i] = 0.0f;
             asm volatile("bar.sync 1, 224;" ::: "memory");    // warps 1..7 only
+#ifdef S3D_PHASE_TIMERS
+            if (threadIdx.x == 32) atomicAdd(&g_phase[5], (unsigned long long)(clock64() - t_spl));
+#endif
             splat_histogram_warp(S.h0, S.contrib, S.cbase, nsph, 1);
+#ifdef S3D_PHASE_TIMERS
+            if (threadIdx.x == 32) atomicAdd(&g_phase[15], (unsigned long long)(clock64() - t_spl));
+#endif
         }
         __syncthreads();
         PHASE(4);
@@ -860,7 +887,12 @@ __global__ void __launch_bounds__(256) orient_a_kernel(const __grid_constant__ P
             float *dst = kp_p1 + ((long long)kpi * PD + threadIdx.x) * 3;
             dst[0] = o3[0]; dst[1] = o3[1]; dst[2] = o3[2];
         }
-        if (threadIdx.x == 0) kp_nprim[kpi] = S.nprim;
+        if (threadIdx.x == 0) {
+            kp_nprim[kpi] = S.nprim;
+            // work items of orient_b: any order (its outputs are indexed by (keypoint, primary))
+            int w0 = atomicAdd(work_b_count, S.nprim);
+            for (int q = 0; q < S.nprim; q++) work_b[w0 + q] = kpi * PD + q;
+        }
         if (threadIdx.x < 3) kp_eigs[kpi * 3 + threadIdx.x] = S.eigs[threadIdx.x];
         if (threadIdx.x < 9) kp_ori0[kpi * 9 + threadIdx.x] = S.ori0[threadIdx.x];
         PHASE(13);
@@ -868,25 +900,20 @@ __global__ void __launch_bounds__(256) orient_a_kernel(const __grid_constant__ P
 }
 
 // one CTA per (keypoint, primary direction): secondary direction histogram (:2887-3033)
-__global__ void __launch_bounds__(256) orient_b_kernel(const int *__restrict__ kp_count, const int *__restrict__ kp_nprim,
+__global__ void __launch_bounds__(256) orient_b_kernel(const int *__restrict__ work_b, const int *__restrict__ work_b_count,
                                                        const float *__restrict__ kp_p1, const float *__restrict__ kp_patch0,
                                                        int *__restrict__ kp_nsec, float *__restrict__ kp_rots)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HistSmem &S = *reinterpret_cast<HistSmem *>(smem_raw);
-    const int nkp = *kp_count;
+    const int n_work = *work_b_count;
     const int nsph = c_tab.n_sphere;
     const float fRadius = 5.0f;
     if (threadIdx.x < 12) S.taps[threadIdx.x] = threadIdx.x < 9 ? c_tab.hist_taps[threadIdx.x] : 0.0f;
-    const long long n_work = (long long)nkp * PD;
     PHASE_INIT();
-    for (long long wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+    for (int it = blockIdx.x; it < n_work; it += gridDim.x) {
+        const long long wi = work_b[it];
         const int kpi = (int)(wi / PD), pi = (int)(wi % PD);
-        const int nprim = kp_nprim[kpi];
-        if (pi >= nprim) {
-            if (threadIdx.x == 0) kp_nsec[wi] = 0;
-            continue;
-        }
         __syncthreads();
         for (int i = threadIdx.x; i < PV; i += blockDim.x) S.patch[i] = kp_patch0[(long long)kpi * PV + i];
         __syncthreads();
@@ -957,7 +984,8 @@ __global__ void __launch_bounds__(256) orient_b_kernel(const int *__restrict__ k
 // their exclusive prefix sum -> first feature row of each keypoint; total -> n_features.
 __global__ void __launch_bounds__(1024) row_offsets_kernel(const int *__restrict__ kp_nprim, const int *__restrict__ kp_nsec,
                                                            const int *__restrict__ kp_count, int *__restrict__ nrows,
-                                                           int *__restrict__ row_off, int *n_features, int row_cap, int *err)
+                                                           int *__restrict__ row_off, int *__restrict__ row_map,
+                                                           int *n_features, int row_cap, int *err)
 {
     __shared__ int s_warp[32];
     __shared__ int s_run;
@@ -983,7 +1011,12 @@ __global__ void __launch_bounds__(1024) row_offsets_kernel(const int *__restrict
         __syncthreads();
         int woff = 0, tot = 0;
         for (int w = 0; w < 32; w++) { if (w < wid) woff += s_warp[w]; tot += s_warp[w]; }
-        if (k < n) row_off[k] = s_run + woff + inc - v;
+        if (k < n) {
+            int first = s_run + woff + inc - v;
+            row_off[k] = first;
+            for (int r = 0; r < v; r++)
+                if (first + r < row_cap) row_map[first + r] = k * kMaxRowsPerKp + r;
+        }
         __syncthreads();
         if (threadIdx.x == 0) s_run += tot;
         __syncthreads();
@@ -1012,8 +1045,8 @@ struct DescribeSmem {
 };
 
 __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ PyramidDesc pyr,
-                                                       const s3d_keypoint *__restrict__ kps, const int *__restrict__ kp_count,
-                                                       const int *__restrict__ nrows, const int *__restrict__ row_off,
+                                                       const s3d_keypoint *__restrict__ kps, const int *__restrict__ n_features,
+                                                       const int *__restrict__ row_map,
                                                        const int *__restrict__ kp_nsec,
                                                        const float *__restrict__ kp_eigs, const float *__restrict__ kp_ori0,
                                                        const float *__restrict__ kp_rots, const float *__restrict__ kp_patch0,
@@ -1023,18 +1056,15 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ P
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DescribeSmem &S = *reinterpret_cast<DescribeSmem *>(smem_raw);
-    const int nkp = *kp_count;
-    const long long n_work = (long long)nkp * kMaxRowsPerKp;
+    const int n_rows = min(*n_features, row_cap);
     if (threadIdx.x < 12) {
         S.taps[threadIdx.x] = threadIdx.x < 9 ? c_tab.brief_taps[threadIdx.x] : 0.0f;
         S.wlo[threadIdx.x] = threadIdx.x < PD ? c_tab.desc_w[threadIdx.x] : 0.0f;
     }
     PHASE_INIT();
-    for (long long wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
-        const int kpi = (int)(wi / kMaxRowsPerKp), r = (int)(wi % kMaxRowsPerKp);
-        if (r >= nrows[kpi]) continue;
-        const int row = row_off[kpi] + r;
-        if (row >= row_cap) continue;
+    for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        const int wi = row_map[row];
+        const int kpi = wi / kMaxRowsPerKp, r = wi % kMaxRowsPerKp;
         __syncthreads();
         const s3d_keypoint kp = kps[kpi];
         const OctaveDesc &o = pyr.oct[kp.octave];

@@ -59,3 +59,28 @@ def brain_phantom(shape_xyz=(182, 218, 182), seed=1, nblobs=400):
         a = 60.0 * rng.uniform(-1.0, 1.0)
         _add_blob(vol, cx, cy, cz, sigma, a, mask)
     return np.ascontiguousarray(vol.astype(np.float32))
+
+
+def write_nifti(path, vol, pixdim=(1.0, 1.0, 1.0), qoffset=None, quatern=(0.0, 0.0, 0.0)):
+    """Minimal single-file NIfTI-1 (.nii): 348-byte header + 4 pad bytes, float32, vox_offset 352.
+    With ``qoffset`` the qform (code 1) is written from ``quatern`` (b, c, d) and the offsets."""
+    import struct
+    vol = np.ascontiguousarray(vol, dtype=np.float32)
+    Z, Y, X = vol.shape
+    h = bytearray(348)
+    struct.pack_into("<i", h, 0, 348)
+    struct.pack_into("<8h", h, 40, 3, X, Y, Z, 1, 1, 1, 1)
+    struct.pack_into("<h", h, 70, 16)      # datatype float32
+    struct.pack_into("<h", h, 72, 32)      # bitpix
+    struct.pack_into("<8f", h, 76, 1.0, pixdim[0], pixdim[1], pixdim[2], 1.0, 1.0, 1.0, 1.0)
+    struct.pack_into("<f", h, 108, 352.0)  # vox_offset
+    struct.pack_into("<f", h, 112, 1.0)    # scl_slope
+    if qoffset is not None:
+        struct.pack_into("<h", h, 252, 1)  # qform_code
+        struct.pack_into("<3f", h, 256, *quatern)
+        struct.pack_into("<3f", h, 268, *qoffset)
+    h[344:348] = b"n+1\0"
+    with open(path, "wb") as f:
+        f.write(bytes(h))
+        f.write(b"\0\0\0\0")
+        f.write(vol.tobytes())

@@ -1,0 +1,66 @@
+"""GPU: the featExtract CLI (3d_sift_cuda_b200/featExtract, the kept host code + the CUDA library)
+against the reference's own CLI built from its sources (oracle/_ref/featExtract_ref, CPU path):
+the feature files must be byte-identical."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OURS = os.path.join(ROOT, "3d_sift_cuda_b200", "featExtract")
+REF = os.path.join(ROOT, "oracle", "_ref", "featExtract_ref")
+
+
+def run(exe, args, cwd):
+    r = subprocess.run([exe] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    assert r.returncode == 0, r.stdout.decode(errors="replace")[-2000:]
+
+
+CASES = [
+    ("plain", [], dict()),
+    ("double", ["-2+"], dict()),
+    ("halve", ["-2-"], dict()),
+    ("world_iso", ["-w"], dict(pixdim=(1.5, 1.5, 1.5), qoffset=(-40.0, 12.5, 7.0), quatern=(0.0, 0.0, 0.0))),
+    ("world_rot_aniso", ["-w"], dict(pixdim=(1.0, 1.0, 2.0), qoffset=(3.0, -2.0, 1.0), quatern=(0.1, 0.2, 0.3))),
+]
+
+
+@pytest.mark.parametrize("name,flags,hdr", CASES, ids=[c[0] for c in CASES])
+def test_cli_matches_reference_cli(pkg, engine, tmp_path, name, flags, hdr):
+    if not (os.path.exists(OURS) and os.path.exists(REF)):
+        pytest.skip("CLI binaries not built")
+    shape = (72, 64, 80) if name == "halve" else (40, 44, 36) if name == "double" else (56, 60, 52)
+    vol = pkg.phantom.blob_phantom(shape, 31, 45)
+    nii = str(tmp_path / "in.nii")
+    pkg.phantom.write_nifti(nii, vol, **hdr)
+    run(REF, flags + [nii, "ref.key"], str(tmp_path))
+    run(OURS, flags + [nii, "ours.key"], str(tmp_path))
+    a = open(tmp_path / "ref.key", "rb").read()
+    b = open(tmp_path / "ours.key", "rb").read()
+    assert a.count(b"\n") > 8, "reference produced no features"
+    assert a == b
+
+
+def test_cli_raw_input_and_brief_flags(pkg, oracle, engine, tmp_path):
+    if not os.path.exists(OURS):
+        pytest.skip("CLI not built")
+    vol = pkg.phantom.blob_phantom((64, 64, 64), 0, 60)
+    raw = str(tmp_path / "in.f32")
+    vol.tofile(raw)
+    for flag, desc in (([], 0), (["-b"], 1), (["-br"], 2), (["-bn"], 3)):
+        run(OURS, flag + ["-r", "64", "64", "64", raw, "o.key"], str(tmp_path))
+        want = str(tmp_path / "w.key")
+        pkg.api.write_features_text(want, oracle.extract(vol, 0, desc)["features"], (64, 64, 64))
+        assert open(tmp_path / "o.key", "rb").read() == open(want, "rb").read(), flag
+
+
+def test_cli_rejects_bad_arguments(tmp_path):
+    if not os.path.exists(OURS):
+        pytest.skip("CLI not built")
+    r = subprocess.run([OURS, "-q", "a", "b"], stdout=subprocess.PIPE)
+    assert r.returncode != 0 and b"unknown command line argument" in r.stdout
+    r = subprocess.run([OURS, str(tmp_path / "missing.nii"), "o.key"], stdout=subprocess.PIPE)
+    assert r.returncode != 0 and b"could not read input file" in r.stdout
