@@ -16,6 +16,7 @@
 
 #include "../../include/s3d.h"
 #include "s3d_voxel.cuh"
+#include "s3d_blur_fused.cuh"
 #include "s3d_keypoint.cuh"
 
 using namespace s3d;
@@ -166,6 +167,8 @@ struct s3d_ctx {
     bool has_result = false;
     int *h_counts = nullptr;     // pinned: kp_count, n_features, err
     cudaStream_t cur = nullptr;  // stream the stage launchers enqueue on (main stream or an octave branch)
+    bool fused = true;           // one-kernel TMA blur level (S3D_FUSED=0 selects the three-pass path)
+    int fused_ctas = 0;          // S3D_FUSED_CTAS: CTAs the fused blur aims for (0 = 2 per SM)
     bool timing = false;         // S3D_STAGE_TIMING=1: no graph, events at stage boundaries of the main stream
     std::vector<std::pair<std::string, cudaEvent_t>> marks;
     cudaStream_t side[kMaxOct] = {};
@@ -238,6 +241,10 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
     for (int o = 0; o < kMaxOct; o++) CK(cudaEventCreateWithFlags(&ctx->ev_fork[o], cudaEventDisableTiming));
     const char *g = getenv("S3D_NO_GRAPH");
     if (g && g[0] == '1') ctx->use_graph = false;
+    const char *fu = getenv("S3D_FUSED");
+    if (fu && fu[0] == '0') ctx->fused = false;
+    const char *fc = getenv("S3D_FUSED_CTAS");
+    ctx->fused_ctas = fc ? atoi(fc) : 0;
     const char *tm = getenv("S3D_STAGE_TIMING");
     if (tm && tm[0] == '1') { ctx->timing = true; ctx->use_graph = false; }   // event nodes inside graphs carry no timestamps
     const char *mt = getenv("S3D_MARCH_TARGET");
@@ -381,6 +388,25 @@ static s3d_status blur3d(s3d_ctx *ctx, const float *in, float *tmp, float *out, 
     if (in == out || in == tmp || tmp == out) return fail(ctx, S3D_ERR_INVALID, "s3d_blur3d: in/tmp/out must be distinct");
     int R = ntaps / 2;
     bool fast = fast_layout(in, tmp, out, pitch) && (!dog || ((uintptr_t)dog % 32) == 0) && R >= 1 && R <= kMaxFastR;
+    if (fast && ctx->fused && (!dog || dog != tmp)) {
+        CUtensorMap map;
+        if (make_volume_map(&map, in, Y, Z, pitch, R)) {
+            cudaError_t e = cudaSuccess;
+            switch (R) {
+            case 1: e = launch_blur_fused<1>(ctx->cur, map, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, ctx->fused_ctas); break;
+            case 2: e = launch_blur_fused<2>(ctx->cur, map, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, ctx->fused_ctas); break;
+            case 3: e = launch_blur_fused<3>(ctx->cur, map, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, ctx->fused_ctas); break;
+            case 4: e = launch_blur_fused<4>(ctx->cur, map, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, ctx->fused_ctas); break;
+            case 5: e = launch_blur_fused<5>(ctx->cur, map, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, ctx->fused_ctas); break;
+            case 6: e = launch_blur_fused<6>(ctx->cur, map, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, ctx->fused_ctas); break;
+            case 7: e = launch_blur_fused<7>(ctx->cur, map, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, ctx->fused_ctas); break;
+            default: e = launch_blur_fused<8>(ctx->cur, map, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, ctx->fused_ctas); break;
+            }
+            ctx->launches += 1;
+            CK(e);
+            return S3D_OK;
+        }
+    }
     if (fast) {
         switch (R) {
         case 1: launch_blur_fast<1>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog); break;
