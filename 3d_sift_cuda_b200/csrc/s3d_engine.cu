@@ -135,6 +135,9 @@ struct Plan {
     float *tmp1 = nullptr;            // scratch of the initial blur (octave-0 size)
     float *oct_tmp[kMaxOct] = {};     // per-octave blur scratch (octaves run on concurrent branches)
     s3d_cand *cand_raw = nullptr;     // [list][cand_cap], list = (oct*3 + (c-1))*2 + is_max (atomic order)
+    unsigned int *face[kMaxOct * 3] = {};   // per (octave, centre level): voxels passing the face test
+    int face_cap[kMaxOct * 3] = {};
+    int *face_counts = nullptr;
     s3d_keypoint *kp_stage = nullptr; // [list][cand_cap] refined candidates at their raster rank
     unsigned char *stage_flags = nullptr;
     int *counts = nullptr;       // [n_lists] candidate counts, then kp_count, n_features, err
@@ -167,12 +170,13 @@ struct s3d_ctx {
     bool has_result = false;
     int *h_counts = nullptr;     // pinned: kp_count, n_features, err
     cudaStream_t cur = nullptr;  // stream the stage launchers enqueue on (main stream or an octave branch)
-    bool fused = true;           // one-kernel TMA blur level (S3D_FUSED=0 selects the three-pass path)
+    bool fused = false;          // S3D_FUSED=1: one-kernel TMA blur level (12 B/voxel but ~2x the instructions of the
+                                 // three-pass path at MNI size, where the volume sits in L2; see profiles/README.md)
     int fused_ctas = 0;          // S3D_FUSED_CTAS: CTAs the fused blur aims for (0 = 2 per SM)
     bool timing = false;         // S3D_STAGE_TIMING=1: no graph, events at stage boundaries of the main stream
     std::vector<std::pair<std::string, cudaEvent_t>> marks;
-    cudaStream_t side[kMaxOct] = {};
-    cudaEvent_t ev_fork[kMaxOct] = {}, ev_done[kMaxOct] = {};
+    cudaStream_t side[kMaxOct] = {}, det[kMaxOct] = {};     // octave branch, detection/refinement branch
+    cudaEvent_t ev_fork[kMaxOct] = {}, ev_done[kMaxOct] = {}, ev_lvl[kMaxOct][4] = {};
 };
 
 #define CK(call)                                                                                     \
@@ -238,11 +242,16 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
         CK(cudaStreamCreateWithFlags(&ctx->side[o], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&ctx->ev_done[o], cudaEventDisableTiming));
     }
-    for (int o = 0; o < kMaxOct; o++) CK(cudaEventCreateWithFlags(&ctx->ev_fork[o], cudaEventDisableTiming));
+    for (int o = 0; o < kMaxOct; o++) {
+        CK(cudaEventCreateWithFlags(&ctx->ev_fork[o], cudaEventDisableTiming));
+        CK(cudaStreamCreateWithFlags(&ctx->det[o], cudaStreamNonBlocking));
+        if (!ctx->ev_done[o]) CK(cudaEventCreateWithFlags(&ctx->ev_done[o], cudaEventDisableTiming));
+        for (int k = 0; k < 4; k++) CK(cudaEventCreateWithFlags(&ctx->ev_lvl[o][k], cudaEventDisableTiming));
+    }
     const char *g = getenv("S3D_NO_GRAPH");
     if (g && g[0] == '1') ctx->use_graph = false;
     const char *fu = getenv("S3D_FUSED");
-    if (fu && fu[0] == '0') ctx->fused = false;
+    if (fu) ctx->fused = (fu[0] == '1');
     const char *fc = getenv("S3D_FUSED_CTAS");
     ctx->fused_ctas = fc ? atoi(fc) : 0;
     const char *tm = getenv("S3D_STAGE_TIMING");
@@ -275,6 +284,8 @@ extern "C" void s3d_ctx_destroy(s3d_ctx *ctx)
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     for (int o = 0; o < kMaxOct; o++) {
         if (ctx->side[o]) cudaStreamDestroy(ctx->side[o]);
+        if (ctx->det[o]) cudaStreamDestroy(ctx->det[o]);
+        for (int k = 0; k < 4; k++) if (ctx->ev_lvl[o][k]) cudaEventDestroy(ctx->ev_lvl[o][k]);
         if (ctx->ev_fork[o]) cudaEventDestroy(ctx->ev_fork[o]);
         if (ctx->ev_done[o]) cudaEventDestroy(ctx->ev_done[o]);
     }
@@ -496,6 +507,26 @@ static s3d_status detect_raw_launch(s3d_ctx *ctx, const float *finer, const floa
     return S3D_OK;
 }
 
+// two-pass detection used by the pipeline: face test over the volume, full test on the survivors
+static s3d_status detect_two_pass(s3d_ctx *ctx, const float *finer, const float *centre, int X, int Y, int Z, int pitch,
+                                  unsigned int *face, int *face_count, int face_cap,
+                                  s3d_cand *raw_min, int *n_min, s3d_cand *raw_max, int *n_max, int cap, int *err)
+{
+    if (X < 3 || Y < 3 || Z < 3) return S3D_OK;
+    if ((long long)pitch * Y * Z >= (1ll << 32))      // 32-bit voxel offsets
+        return detect_raw_launch(ctx, finer, centre, X, Y, Z, pitch, raw_min, n_min, raw_max, n_max, cap);
+    dim3 block(32, 8), grid((X - 2 + 31) / 32, (Y - 2 + 7) / 8, (Z - 2 + kDetectZ - 1) / kDetectZ);
+    detect_face_kernel<<<grid, block, 0, ctx->cur>>>(finer, centre, X, Y, Z, pitch, face, face_count, face_cap);
+    CandList lmin{ raw_min, n_min }, lmax{ raw_max, n_max };
+    int blocks = (int)(((long long)X * Y * Z / 64 + 255) / 256);
+    if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
+    if (blocks < 1) blocks = 1;
+    detect_full_kernel<<<blocks, 256, 0, ctx->cur>>>(finer, centre, X, Y, Z, pitch, face, face_count, face_cap, lmin, lmax, cap, err, ERR_CAND_OVERFLOW);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return S3D_OK;
+}
+
 // detection + raster ordering (stage-level API)
 static s3d_status detect_launch(s3d_ctx *ctx, const float *finer, const float *centre, int X, int Y, int Z, int pitch,
                                 s3d_cand *raw_min, s3d_cand *raw_max, s3d_cand *out_min, int *n_min,
@@ -633,6 +664,16 @@ static s3d_status plan_build(s3d_ctx *ctx, int X, int Y, int Z, const s3d_params
         PA(&p->stage_flags, (size_t)p->n_lists * p->cand_cap);
     }
     PA(&p->counts, p->n_lists + 8);
+    PA(&p->face_counts, kMaxOct * 3);
+    for (int o = 0; o < n_oct; o++) {
+        const OctaveDesc &od = p->pyr.oct[o];
+        long long nv = (long long)od.pitch * od.Y * od.Z;
+        for (int c = 0; c < 3; c++) {
+            long long fc = nv / 8 + 1024;
+            p->face_cap[o * 3 + c] = (int)(fc > (1 << 26) ? (1 << 26) : fc);
+            PA(&p->face[o * 3 + c], (size_t)p->face_cap[o * 3 + c]);
+        }
+    }
     PA(&p->kps, kp_cap);
     PA(&p->nrows, kp_cap);
     PA(&p->row_off, kp_cap);
@@ -732,10 +773,13 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     // Octave o+1 only needs level 3 of octave o, so every octave runs on its own branch (stream / graph
     // branch): the tail of an octave (levels 4, 5 and its three detection passes) overlaps the whole
     // chain of smaller octaves, which is launch-latency bound.
+    ListDesc L{ p->n_lists, p->cand_cap, p->cand_raw, p->counts };
+    CK(cudaMemsetAsync(p->face_counts, 0, sizeof(int) * kMaxOct * 3, st));
     for (int o = 0; o < p->n_oct; o++) {
         const OctaveDesc &od = p->pyr.oct[o];
-        ctx->cur = (o == 0) ? st : ctx->side[o];
-        if (o > 0) CK(cudaStreamWaitEvent(ctx->cur, ctx->ev_fork[o - 1], 0));
+        cudaStream_t so = (o == 0) ? st : ctx->side[o];
+        ctx->cur = so;
+        if (o > 0) CK(cudaStreamWaitEvent(so, ctx->ev_fork[o - 1], 0));
         for (int j = 1; j < 6; j++) {
             Vol &a = p->g[o * 6 + j - 1], &b = p->g[o * 6 + j], &dd = p->d[o * 5 + j - 1];
             s3d_status s = blur3d(ctx, a.p, p->oct_tmp[o], b.p, od.X, od.Y, od.Z, od.pitch, p->lvl_taps[j - 1], p->n_lvl_taps[j - 1], dd.p);
@@ -744,27 +788,40 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
                 const OctaveDesc &nx = p->pyr.oct[o + 1];
                 s = resize_launch(ctx, 0, b.p, od.X, od.Y, od.Z, od.pitch, p->g[(o + 1) * 6].p, nx.pitch);
                 if (s != S3D_OK) { ctx->cur = st; return s; }
-                CK(cudaEventRecord(ctx->ev_fork[o], ctx->cur));
+                CK(cudaEventRecord(ctx->ev_fork[o], so));
             }
             if (o == 0) { char nm[32]; snprintf(nm, sizeof(nm), "oct0 level %d", j); mark(ctx, nm); }
+            if (j >= 2) {
+                // Detection branch.  Level j completes DoG j-1, so centre level j-1 can be detected now (it
+                // needs DoG j-2 and j-1) and centre level j-2 can be validated / refined (it needs DoG j-1).
+                // The branch runs beside the blur of the next level; only the refinement of centre level 3
+                // (after level 5) is exposed.
+                CK(cudaEventRecord(ctx->ev_lvl[o][j - 2], so));
+                cudaStream_t sd = ctx->det[o];
+                CK(cudaStreamWaitEvent(sd, ctx->ev_lvl[o][j - 2], 0));
+                ctx->cur = sd;
+                int c_det = j - 1, c_ref = j - 2;
+                if (c_det <= 3) {
+                    int l0 = (o * 3 + (c_det - 1)) * 2;
+                    s = detect_two_pass(ctx, od.d[c_det - 1], od.d[c_det], od.X, od.Y, od.Z, od.pitch,
+                                        p->face[o * 3 + c_det - 1], p->face_counts + o * 3 + c_det - 1, p->face_cap[o * 3 + c_det - 1],
+                                        p->cand_raw + (size_t)l0 * p->cand_cap, p->counts + l0,
+                                        p->cand_raw + (size_t)(l0 + 1) * p->cand_cap, p->counts + l0 + 1, p->cand_cap, err);
+                    if (s != S3D_OK) { ctx->cur = st; return s; }
+                }
+                if (c_ref >= 1) {
+                    int l0 = (o * 3 + (c_ref - 1)) * 2;
+                    cand_refine_kernel<<<dim3(2, 4), 256, 0, sd>>>(p->pyr, L, l0, p->kp_stage, p->stage_flags, err);
+                    ctx->launches++;
+                }
+                if (j == 5) CK(cudaEventRecord(ctx->ev_done[o], sd));
+                ctx->cur = so;
+            }
         }
-        for (int c = 1; c <= 3; c++) {
-            int l0 = (o * 3 + (c - 1)) * 2;
-            s3d_status s = detect_raw_launch(ctx, od.d[c - 1], od.d[c], od.X, od.Y, od.Z, od.pitch,
-                                             p->cand_raw + (size_t)l0 * p->cand_cap, p->counts + l0,
-                                             p->cand_raw + (size_t)(l0 + 1) * p->cand_cap, p->counts + l0 + 1, p->cand_cap);
-            if (s != S3D_OK) { ctx->cur = st; return s; }
-        }
-        if (o > 0) CK(cudaEventRecord(ctx->ev_done[o], ctx->cur));
-        if (o == 0) mark(ctx, "oct0 detect x3");
     }
     ctx->cur = st;
-    for (int o = 1; o < p->n_oct; o++) CK(cudaStreamWaitEvent(st, ctx->ev_done[o], 0));
-    mark(ctx, "join octaves>=1");
-    // candidate stage: rank + validate + refine every candidate of every list, then ordered compaction
-    ListDesc L{ p->n_lists, p->cand_cap, p->cand_raw, p->counts };
-    cand_refine_kernel<<<dim3(p->n_lists, 4), 256, 0, st>>>(p->pyr, L, p->kp_stage, p->stage_flags, err);
-    mark(ctx, "cand_refine");
+    for (int o = 0; o < p->n_oct; o++) CK(cudaStreamWaitEvent(st, ctx->ev_done[o], 0));
+    mark(ctx, "join (detect+refine tails)");
     compact_kernel<<<1, 1024, 0, st>>>(L, p->kp_stage, p->stage_flags, p->kps, kp_count, p->kp_cap, err);
     mark(ctx, "compact");
     // orientation: per keypoint, then per (keypoint, primary direction)
@@ -783,7 +840,7 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
                                                               p->kp_ori0, p->kp_rots, p->kp_patch0, prm->descriptor, size_factor,
                                                               p->row_cap, p->feats, p->dbg_patches, p->dbg_prerank);
     mark(ctx, "row_offsets+describe");
-    ctx->launches += 6;
+    ctx->launches += 5;
     CK(cudaGetLastError());
     return S3D_OK;
 }

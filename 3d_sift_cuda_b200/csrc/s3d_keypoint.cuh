@@ -505,11 +505,11 @@ struct ListDesc {            // list = (octave*3 + (c-1))*2 + is_max
     const int *counts;       // [n_lists]
 };
 
-__global__ void __launch_bounds__(256) cand_refine_kernel(const __grid_constant__ PyramidDesc pyr, ListDesc L,
+__global__ void __launch_bounds__(256) cand_refine_kernel(const __grid_constant__ PyramidDesc pyr, ListDesc L, int list_begin,
                                                           s3d_keypoint *__restrict__ stage, unsigned char *__restrict__ flags,
                                                           int *err)
 {
-    const int list = blockIdx.x;
+    const int list = list_begin + blockIdx.x;
     const int octave = list / 6, c = (list / 2) % 3 + 1, is_max = list & 1;
     const OctaveDesc &o = pyr.oct[octave];
     const int X = o.X, Y = o.Y, Z = o.Z, pitch = o.pitch;

@@ -326,6 +326,96 @@ struct CandList {
 
 constexpr int kDetectZ = 8;   // centre voxels per thread along z
 
+// Pass 1: branch-free 6-face test of the centre DoG for every interior voxel.  All loads of a thread
+// (its z column and the x/y neighbours of its 8 voxels) are issued up front, so the pass runs at memory
+// speed; the few survivors (strict extrema along x, y and z) are appended to a list of linear voxel
+// offsets with one aggregated atomic per warp.
+__global__ void __launch_bounds__(256) detect_face_kernel(const float *__restrict__ finer, const float *__restrict__ centre,
+                                                          int X, int Y, int Z, int pitch,
+                                                          unsigned int *__restrict__ face, int *face_count, int face_cap)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    const int z0 = blockIdx.z * kDetectZ + 1;
+    const bool inside = (x <= X - 2 && y <= Y - 2);
+    const long long plane = (long long)pitch * Y;
+    const long long base = (long long)(inside ? y : 1) * pitch + (inside ? x : 1);
+    float col[kDetectZ + 2], xm[kDetectZ], xp[kDetectZ], ym[kDetectZ], yp[kDetectZ];
+#pragma unroll
+    for (int k = 0; k < kDetectZ + 2; k++) {
+        int z = min(z0 - 1 + k, Z - 1);
+        col[k] = __ldg(centre + (long long)z * plane + base);
+    }
+#pragma unroll
+    for (int k = 0; k < kDetectZ; k++) {
+        const float *p = centre + (long long)min(z0 + k, Z - 1) * plane + base;
+        xm[k] = __ldg(p - 1); xp[k] = __ldg(p + 1); ym[k] = __ldg(p - pitch); yp[k] = __ldg(p + pitch);
+    }
+    const int lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
+    unsigned livemask = 0;
+#pragma unroll
+    for (int k = 0; k < kDetectZ; k++) {
+        const float c = col[k + 1];
+        bool mx = (col[k] < c) && (col[k + 2] < c) && (xm[k] < c) && (xp[k] < c) && (ym[k] < c) && (yp[k] < c);
+        bool mn = (col[k] > c) && (col[k + 2] > c) && (xm[k] > c) && (xp[k] > c) && (ym[k] > c) && (yp[k] > c);
+        if (inside && (z0 + k <= Z - 2) && (mx || mn)) livemask |= 1u << k;
+    }
+    // one atomic per warp for all 8 z steps
+    int mine = __popc(livemask), incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    int start = 0;
+    if (lane == 31) start = atomicAdd(face_count, total);
+    start = __shfl_sync(0xffffffffu, start, 31);
+    int pos = start + incl - mine;
+#pragma unroll
+    for (int k = 0; k < kDetectZ; k++)
+        if (livemask & (1u << k)) {
+            if (pos < face_cap) face[pos] = (unsigned int)((long long)(z0 + k) * plane + base);
+            pos++;
+        }
+}
+
+// Pass 2: the full 26 + 27 neighbour test (reference MultiScale.cpp:2260-2524) on the survivors only.
+__global__ void __launch_bounds__(256) detect_full_kernel(const float *__restrict__ finer, const float *__restrict__ centre,
+                                                          int X, int Y, int Z, int pitch,
+                                                          const unsigned int *__restrict__ face, const int *__restrict__ face_count,
+                                                          int face_cap, CandList mins, CandList maxs, int cap, int *err, int err_bit)
+{
+    int n = *face_count;
+    if (n > face_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, err_bit); n = face_cap; }
+    const long long plane = (long long)pitch * Y;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const long long i = face[k];
+        const float c = centre[i];
+        bool mx = true, mn = true;
+#pragma unroll
+        for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++) {
+                const float *row = centre + i + dz * plane + dy * pitch;
+                float a = row[-1], b = row[0], d = row[1];
+                if (dz == 0 && dy == 0) b = a; // skip self
+                mx = mx && (a < c) && (b < c) && (d < c);
+                mn = mn && (a > c) && (b > c) && (d > c);
+                row = finer + i + dz * plane + dy * pitch;
+                a = row[-1]; b = row[0]; d = row[1];
+                mx = mx && (a < c) && (b < c) && (d < c);
+                mn = mn && (a > c) && (b > c) && (d > c);
+            }
+        if (mx || mn) {
+            int z = (int)(i / plane);
+            int rem = (int)(i - (long long)z * plane);
+            int y = rem / pitch, x = rem - y * pitch;
+            if (mx) { int kk = atomicAdd(maxs.count, 1); if (kk < cap) maxs.items[kk] = s3d_cand{ x, y, z, c }; }
+            if (mn) { int kk = atomicAdd(mins.count, 1); if (kk < cap) mins.items[kk] = s3d_cand{ x, y, z, c }; }
+        }
+    }
+}
+
+// single-kernel variant (kept for volumes too large for 32-bit voxel offsets)
 __global__ void __launch_bounds__(256) detect_kernel(const float *__restrict__ finer, const float *__restrict__ centre,
                                                      int X, int Y, int Z, int pitch,
                                                      CandList mins, CandList maxs, int cap)
@@ -336,7 +426,6 @@ __global__ void __launch_bounds__(256) detect_kernel(const float *__restrict__ f
     if (x > X - 2 || y > Y - 2 || z0 > Z - 2) return;
     long long plane = (long long)pitch * Y;
     long long base = (long long)y * pitch + x;
-    // the column z0-1 .. z0+kDetectZ of the centre volume, all loads in flight together
     float col[kDetectZ + 2];
 #pragma unroll
     for (int k = 0; k < kDetectZ + 2; k++) {
@@ -352,7 +441,7 @@ __global__ void __launch_bounds__(256) detect_kernel(const float *__restrict__ f
         bool mn = (col[k] > c) && (col[k + 2] > c);
         if (!(mx || mn)) continue;
         long long i = (long long)z * plane + base;
-        {   // remaining face neighbours, then the finer centre: they reject almost everything
+        {
             float a = centre[i - 1], b = centre[i + 1];
             mx = mx && (a < c) && (b < c);
             mn = mn && (a > c) && (b > c);

@@ -156,3 +156,27 @@ def test_tiny_and_empty_volumes(pkg, oracle, engine):
     assert len(engine.extract(flat)) == 0 == len(oracle.extract(flat)["features"])
     tiny = pkg.phantom.blob_phantom((2, 5, 5), 1, 1)
     assert len(engine.extract(tiny)) == 0
+
+
+def test_fused_blur_path_bit_exact(pkg, oracle, monkeypatch):
+    """The optional one-kernel TMA blur (S3D_FUSED=1) must produce the same bits as the default path."""
+    import torch
+    monkeypatch.setenv("S3D_FUSED", "1")
+    eng = pkg.Engine(0)
+    try:
+        for shape_xyz in [(48, 40, 36), (37, 29, 23), (70, 66, 41)]:
+            vol = pkg.phantom.blob_phantom(shape_xyz, seed=3, nblobs=20)
+            X = shape_xyz[0]
+            for sigma in (0.5, 0.95, 1.2263, 1.5199, 1.9466, 2.4525, 3.09):
+                want = oracle.blur(vol, sigma)
+                d_in = to_dev(vol)
+                d_tmp, d_out, d_dog = torch.zeros_like(d_in), torch.zeros_like(d_in), torch.zeros_like(d_in)
+                eng.blur3d(d_in, d_tmp, d_out, X, pkg.gaussian_taps(sigma), d_dog)
+                eng.sync()
+                assert (bits(from_dev(d_out, X)) == bits(want)).all(), (shape_xyz, sigma)
+                assert (bits(from_dev(d_dog, X)) == bits(oracle.dog(vol, want))).all(), (shape_xyz, sigma)
+                assert float(d_out[:, :, X:].abs().sum()) == 0.0
+        vol = pkg.phantom.blob_phantom((64, 64, 64), 0, 60)
+        assert eng.extract(vol).tobytes() == oracle.extract(vol)["features"].tobytes()
+    finally:
+        eng.close()
