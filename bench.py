@@ -75,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -123,24 +123,30 @@ def run_reference(args):
     import cpu_baseline as cb
     procs = cb.usable_cores()
     pool = cb.CpuPool(SHAPE, 1, NBLOBS, os.path.join(ROOT, "3d_sift_cuda_b200", "phantom.py"), procs)
-    for _ in range(args.warmup):
+    # bounded sample: one MNI volume per worker per step (~3 s); stop early once ~150 s have been spent
+    budget, t_start = 150.0, time.perf_counter()
+    for _ in range(min(args.warmup, 1)):
         pool.step(1)
-    vols, secs, rows = 0, 0.0, 0
+    vols, secs, rows, timed = 0, 0.0, 0, 0
     for _ in range(args.steps):
         n, dt, rows = pool.step(1)
         vols += n
         secs += dt
+        timed += 1
+        if time.perf_counter() - t_start > budget:
+            break
     pool.close()
     value = vols / secs
     line = {
         "impl": "reference", "metric": "volumes/sec (pyramid+detect+describe)", "value": value, "unit": "volumes/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / timed,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "gvoxels_per_s": value * N0 / 1e9,
-        "config": {"workload": WORKLOAD, "shape_xyz": list(SHAPE), "rows_per_volume": rows,
-                   "note": "reference CPU path (featExtract without -d): %d worker processes, one volume each per step" % procs},
+        "config": {"workload": WORKLOAD, "shape_xyz": list(SHAPE), "rows_per_volume": rows, "timed_steps": timed,
+                   "note": "reference CPU path (featExtract without -d): %d worker processes, one volume each per step "
+                           "(a step = %d volumes); bounded sample: %d of the %d requested steps were timed" % (procs, procs, timed, args.steps)},
         "cpu_baseline": {"value": value, "unit": "volumes/s", "cores": procs, "kind": cb.kind(),
-                         "sample": "%d steps x %d volumes (one per worker process)" % (args.steps, procs)},
+                         "sample": "%d steps x %d volumes (one per worker process)" % (timed, procs)},
         "e2e": {"value": value, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -217,27 +223,69 @@ def run_ours(args):
             evs.append((e0, e1))
     eng.sync()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
     total_ms = dmod.max_over_ranks(total_ms, device=dev)
     ms_per_step = total_ms / args.steps
     value = world * 1e3 / ms_per_step
 
     # ---- end to end through the public call with host buffers (e2e) ----
-    for i in range(args.warmup):
-        eng.extract_host_async(h_vols[i % npool], params)
-        eng.fetch_features()
+    # Every step = s3d_extract_host_async (H2D of the 28.9 MB volume from pinned memory + the whole path)
+    # followed by s3d_fetch_features (D2H of the rows).  Two engine contexts alternate so that the H2D
+    # copy of step i+1 overlaps the kernels of step i (the public API is one context per stream).
+    eng2 = pkg.Engine(local)
+    engines = [eng, eng2]
+    for i in range(max(args.warmup, 4)):
+        engines[i % 2].extract_host_async(h_vols[i % npool], params)
+        engines[i % 2].fetch_features()
     barrier()
     t0 = time.perf_counter()
     d2h = 0
+    pending = None
     for i in range(args.steps):
-        eng.extract_host_async(h_vols[i % npool], params)
-        f = eng.fetch_features()
-        d2h += f.nbytes + 12
+        e_i = engines[i % 2]
+        e_i.extract_host_async(h_vols[i % npool], params)
+        if pending is not None:
+            f = pending.fetch_features()
+            d2h += f.nbytes + 12
+        pending = e_i
+    f = pending.fetch_features()
+    d2h += f.nbytes + 12
     torch.cuda.synchronize()
     e2e_s = dmod.max_over_ranks(time.perf_counter() - t0, device=dev)
     e2e = {"value": world * args.steps / e2e_s, "unit": "volumes/s", "h2d_bytes_per_step": N0 * 4,
-           "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * e2e_s / args.steps}
+           "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * e2e_s / args.steps,
+           "note": "2 contexts alternate: H2D of step i+1 overlaps compute of step i; every step's H2D and D2H are inside the timed region"}
+    # same thing strictly one step at a time (latency of a single featExtract call with host buffers)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        eng.extract_host_async(h_vols[i % npool], params)
+        eng.fetch_features()
+    torch.cuda.synchronize()
+    e2e["serial_ms_per_step"] = 1e3 * dmod.max_over_ranks(time.perf_counter() - t0, device=dev) / args.steps
+
+    # ---- batch throughput: several volumes in flight on one GPU (BASELINE.json config 4 per GPU) ----
+    batch = None
+    if rank == 0 or world > 1:
+        nctx = 4
+        pool_e = engines + [pkg.Engine(local) for _ in range(nctx - 2)]
+        for i in range(2 * nctx):
+            pool_e[i % nctx].extract_device(d_vols[i % npool], SHAPE, params)
+        for e_ in pool_e:
+            e_.sync()
+        nb = max(args.steps, 2 * nctx)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(nb):
+            pool_e[i % nctx].extract_device(d_vols[i % npool], SHAPE, params)
+        for e_ in pool_e:
+            e_.sync()
+        bs = dmod.max_over_ranks(time.perf_counter() - t0, device=dev)
+        batch = {"value": world * nb / bs, "unit": "volumes/s", "contexts_per_gpu": nctx, "volumes": nb,
+                 "note": "device-resident volumes, %d contexts (streams) per GPU in flight, wall clock" % nctx}
+        for e_ in pool_e[2:]:
+            e_.close()
+    clocks = sampler.stop() if rank == 0 else None   # sampled across all timed regions (value, e2e, batch)
 
     # ---- roofline of the dominant stage: the 17-tap blur level at octave-0 size with fused DoG ----
     roof = None
@@ -283,21 +331,22 @@ def run_ours(args):
                        "l2": "256 MiB buffer written between timed steps (L2 flush, untimed)",
                        "keypoints_per_volume": nk, "rows_per_volume": nf},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "launches_per_step": launches_per_step, "roofline": roof, "cpu_baseline": cpu,
+            "launches_per_step": launches_per_step, "roofline": roof, "cpu_baseline": cpu, "batch": batch,
         }
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     eng.close()
+    eng2.close()
     return 0
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
