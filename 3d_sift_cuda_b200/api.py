@@ -33,6 +33,7 @@ EXPORTS = [
     "s3d_double_size", "s3d_halve_size", "s3d_extract", "s3d_extract_device", "s3d_extract_host_async",
     "s3d_fetch_features", "s3d_fetch_counts", "s3d_result_device", "s3d_free", "s3d_num_octaves",
     "s3d_get_level", "s3d_get_keypoints", "s3d_get_patches", "s3d_last_launch_count", "s3d_write_features_text",
+    "s3d_copy_level_device", "s3d_get_row_keypoints",
 ]
 
 
@@ -42,15 +43,22 @@ class S3DError(RuntimeError):
 
 class _Params(C.Structure):
     _fields_ = [("double_mode", C.c_int), ("descriptor", C.c_int), ("eig_thres", C.c_float),
-                ("max_keypoints", C.c_int), ("max_features", C.c_int), ("keep_patches", C.c_int)]
+                ("max_keypoints", C.c_int), ("max_features", C.c_int), ("keep_patches", C.c_int),
+                ("input_is_g0", C.c_int), ("octave_base", C.c_int), ("max_octaves", C.c_int), ("slab", C.c_int),
+                ("z_off", C.c_int), ("z_global", C.c_int), ("own_z0", C.c_int), ("own_z1", C.c_int),
+                ("pre_step_done", C.c_int)]
 
 
 class Params:
     """featExtract's options (featExtract.cpp:299-350 plus the README's -b/-br/-bn)."""
 
     def __init__(self, double_mode=0, descriptor=DESC_SIFT, eig_thres=140.0, max_keypoints=0, max_features=0,
-                 keep_patches=False):
-        self.c = _Params(double_mode, descriptor, eig_thres, max_keypoints, max_features, 1 if keep_patches else 0)
+                 keep_patches=False, input_is_g0=False, octave_base=0, max_octaves=0, slab=None, pre_step_done=0):
+        """``slab`` = (z_off, z_global, own_z0, own_z1) in planes of the octave being run (see include/s3d.h)."""
+        z_off, z_global, own_z0, own_z1 = slab if slab is not None else (0, 0, 0, 0)
+        self.c = _Params(double_mode, descriptor, eig_thres, max_keypoints, max_features, 1 if keep_patches else 0,
+                         1 if input_is_g0 else 0, octave_base, max_octaves, 1 if slab is not None else 0,
+                         z_off, z_global, own_z0, own_z1, pre_step_done)
 
 
 def library_path():
@@ -102,6 +110,8 @@ def load_library():
     L.s3d_get_keypoints.argtypes = [vp, C.POINTER(vp), C.POINTER(i)]
     L.s3d_get_patches.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i)]
     L.s3d_last_launch_count.argtypes = [vp]
+    L.s3d_copy_level_device.argtypes = [vp, i, i, i, i, i, vp]
+    L.s3d_get_row_keypoints.argtypes = [vp, C.POINTER(vp), C.POINTER(i)]
     L.s3d_write_features_text.argtypes = [C.c_char_p, vp, i, f, i, C.POINTER(C.c_char_p)]
     _LIB = L
     return L
@@ -244,6 +254,17 @@ class Engine:
     def launch_count(self):
         return self.L.s3d_last_launch_count(self.ctx)
 
+    def copy_level_device(self, octave, level, z0, z1, d_dst, dog=False):
+        """Planes [z0, z1) of a level of the last extraction -> dense device tensor (z1-z0, Y, X)."""
+        self._ck(self.L.s3d_copy_level_device(self.ctx, octave, 1 if dog else 0, level, z0, z1, _dptr(d_dst)),
+                 "s3d_copy_level_device")
+
+    def row_keypoints(self):
+        """For every feature row of the last extraction, the index of its keypoint."""
+        out, n = C.c_void_p(), C.c_int()
+        self._ck(self.L.s3d_get_row_keypoints(self.ctx, C.byref(out), C.byref(n)), "s3d_get_row_keypoints")
+        return _copy_out(out, n.value, np.int32, self.L.s3d_free)
+
     # ---- stage level (torch CUDA tensors shaped (Z, Y, pitch), float32) ------------------------------
     def blur3d(self, d_in, d_tmp, d_out, X, taps, d_dog=None):
         Z, Y, pitch = d_in.shape
@@ -277,6 +298,7 @@ class Engine:
         mins = torch.zeros(cap * 4, dtype=torch.int32, device=dev)
         maxs = torch.zeros(cap * 4, dtype=torch.int32, device=dev)
         cnt = torch.zeros(2, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)   # the engine has its own stream
         self._ck(self.L.s3d_detect(self.ctx, _dptr(d_finer), _dptr(d_centre), X, Y, Z, pitch,
                                    _dptr(mins), C.c_void_p(cnt.data_ptr()), _dptr(maxs), C.c_void_p(cnt.data_ptr() + 4), cap),
                  "s3d_detect")

@@ -127,6 +127,7 @@ struct Vol {
 
 struct Plan {
     int X = 0, Y = 0, Z = 0, double_mode = 0;      // input dims and pre-step
+    int input_is_g0 = 0, octave_base = 0, max_octaves = 0, slab = 0, z_off = 0, z_global = 0, own_z0 = 0, own_z1 = 0, pre_step_done = 0;
     int kp_cap = 0, row_cap = 0, cand_cap = 0, keep_patches = 0;
     int n_oct = 0;
     Vol stage;                   // dense copy of the input (pitch == X)
@@ -496,12 +497,13 @@ extern "C" s3d_status s3d_double_size(s3d_ctx *ctx, const float *d_in, int X, in
 
 // detection into raw (atomic-order) lists
 static s3d_status detect_raw_launch(s3d_ctx *ctx, const float *finer, const float *centre, int X, int Y, int Z, int pitch,
-                                    s3d_cand *raw_min, int *n_min, s3d_cand *raw_max, int *n_max, int cap)
+                                    s3d_cand *raw_min, int *n_min, s3d_cand *raw_max, int *n_max, int cap,
+                                    int own0 = 0, int own1 = 0x7fffffff)
 {
     if (X < 3 || Y < 3 || Z < 3) return S3D_OK;   // no interior voxel
     dim3 block(32, 8), grid((X - 2 + 31) / 32, (Y - 2 + 7) / 8, (Z - 2 + kDetectZ - 1) / kDetectZ);
     CandList lmin{ raw_min, n_min }, lmax{ raw_max, n_max };
-    detect_kernel<<<grid, block, 0, ctx->cur>>>(finer, centre, X, Y, Z, pitch, lmin, lmax, cap);
+    detect_kernel<<<grid, block, 0, ctx->cur>>>(finer, centre, X, Y, Z, pitch, lmin, lmax, cap, own0, own1);
     ctx->launches += 1;
     CK(cudaGetLastError());
     return S3D_OK;
@@ -510,18 +512,19 @@ static s3d_status detect_raw_launch(s3d_ctx *ctx, const float *finer, const floa
 // two-pass detection used by the pipeline: face test over the volume, full test on the survivors
 static s3d_status detect_two_pass(s3d_ctx *ctx, const float *finer, const float *centre, int X, int Y, int Z, int pitch,
                                   unsigned int *face, int *face_count, int face_cap,
-                                  s3d_cand *raw_min, int *n_min, s3d_cand *raw_max, int *n_max, int cap, int *err)
+                                  s3d_cand *raw_min, int *n_min, s3d_cand *raw_max, int *n_max, int cap, int *err,
+                                  int own0, int own1)
 {
     if (X < 3 || Y < 3 || Z < 3) return S3D_OK;
     if ((long long)pitch * Y * Z >= (1ll << 32))      // 32-bit voxel offsets
-        return detect_raw_launch(ctx, finer, centre, X, Y, Z, pitch, raw_min, n_min, raw_max, n_max, cap);
+        return detect_raw_launch(ctx, finer, centre, X, Y, Z, pitch, raw_min, n_min, raw_max, n_max, cap, own0, own1);
     dim3 block(32, 8), grid((X - 2 + 31) / 32, (Y - 2 + 7) / 8, (Z - 2 + kDetectZ - 1) / kDetectZ);
     detect_face_kernel<<<grid, block, 0, ctx->cur>>>(finer, centre, X, Y, Z, pitch, face, face_count, face_cap);
     CandList lmin{ raw_min, n_min }, lmax{ raw_max, n_max };
     int blocks = (int)(((long long)X * Y * Z / 64 + 255) / 256);
     if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
     if (blocks < 1) blocks = 1;
-    detect_full_kernel<<<blocks, 256, 0, ctx->cur>>>(finer, centre, X, Y, Z, pitch, face, face_count, face_cap, lmin, lmax, cap, err, ERR_CAND_OVERFLOW);
+    detect_full_kernel<<<blocks, 256, 0, ctx->cur>>>(finer, centre, X, Y, Z, pitch, face, face_count, face_cap, lmin, lmax, cap, err, ERR_CAND_OVERFLOW, own0, own1);
     ctx->launches += 2;
     CK(cudaGetLastError());
     return S3D_OK;
@@ -580,13 +583,18 @@ static s3d_status plan_build(s3d_ctx *ctx, int X, int Y, int Z, const s3d_params
     int row_cap = prm->max_features > 0 ? prm->max_features : 8 * kp_cap;
     Plan *old = ctx->plan;
     if (old && old->X == X && old->Y == Y && old->Z == Z && old->double_mode == prm->double_mode &&
-        old->kp_cap == kp_cap && old->row_cap == row_cap && old->keep_patches == (prm->keep_patches ? 1 : 0))
+        old->kp_cap == kp_cap && old->row_cap == row_cap && old->keep_patches == (prm->keep_patches ? 1 : 0) &&
+        old->input_is_g0 == prm->input_is_g0 && old->octave_base == prm->octave_base && old->max_octaves == prm->max_octaves &&
+        old->slab == prm->slab && old->z_off == prm->z_off && old->z_global == prm->z_global &&
+        old->own_z0 == prm->own_z0 && old->own_z1 == prm->own_z1 && old->pre_step_done == prm->pre_step_done)
         return S3D_OK;
     plan_free(ctx);
     Plan *p = new Plan();
     ctx->plan = p;
     p->X = X; p->Y = Y; p->Z = Z; p->double_mode = prm->double_mode;
     p->kp_cap = kp_cap; p->row_cap = row_cap; p->keep_patches = prm->keep_patches ? 1 : 0;
+    p->input_is_g0 = prm->input_is_g0; p->octave_base = prm->octave_base; p->max_octaves = prm->max_octaves;
+    p->slab = prm->slab; p->z_off = prm->z_off; p->z_global = prm->z_global; p->own_z0 = prm->own_z0; p->own_z1 = prm->own_z1; p->pre_step_done = prm->pre_step_done;
 
     int X0 = X, Y0 = Y, Z0 = Z;
     if (prm->double_mode == 1) { X0 *= 2; Y0 *= 2; Z0 *= 2; }
@@ -609,9 +617,14 @@ static s3d_status plan_build(s3d_ctx *ctx, int X, int Y, int Z, const s3d_params
     // octaves (reference MultiScale.cpp:359: stop when any dimension <= 2)
     int ox = X0, oy = Y0, oz = Z0, n_oct = 0;
     memset(&p->pyr, 0, sizeof(p->pyr));
-    while (!(ox <= 2 || oy <= 2 || oz <= 2) && n_oct < kMaxOct) {
+    while (!(ox <= 2 || oy <= 2 || oz <= 2) && n_oct < kMaxOct && (prm->max_octaves <= 0 || n_oct < prm->max_octaves)) {
         OctaveDesc &od = p->pyr.oct[n_oct];
         od.X = ox; od.Y = oy; od.Z = oz; od.pitch = round_up(ox, 8);
+        od.z_off = 0; od.Zg = oz; od.own0 = 0; od.own1 = oz;
+        if (prm->slab) {      // one octave per call in slab mode (halos are refreshed between octaves)
+            od.z_off = prm->z_off; od.Zg = prm->z_global;
+            od.own0 = prm->own_z0 - prm->z_off; od.own1 = prm->own_z1 - prm->z_off;
+        }
         for (int j = 0; j < 6; j++) {
             Vol v; v.X = ox; v.Y = oy; v.Z = oz; v.pitch = od.pitch;
             PA(&v.p, v.elems());
@@ -633,7 +646,7 @@ static s3d_status plan_build(s3d_ctx *ctx, int X, int Y, int Z, const s3d_params
 
     // schedule (reference MultiScale.cpp:288-294, 337-371, 526-527)
     {
-        float fInitialImageScale = prm->double_mode == 1 ? 0.5f : 1.0f;
+        float fInitialImageScale = (prm->double_mode == 1 || prm->pre_step_done == 1) ? 0.5f : 1.0f;
         float fSigmaInit = 0.5f;
         if (fInitialImageScale > 0) fSigmaInit /= fInitialImageScale;
         float fSigma = 1.6f;
@@ -745,34 +758,41 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     mark(ctx, "start");
     CK(cudaMemsetAsync(p->counts, 0, sizeof(int) * (p->n_lists + 8), st));
 
-    // pre-step: -2+ / -2- / plain copy into the pitched pyramid input
-    if (p->double_mode == 1) {
-        s3d_status s = resize_launch(ctx, 2, p->stage.p, p->X, p->Y, p->Z, p->X, p->img0.p, p->img0.pitch);
-        if (s != S3D_OK) return s;
-    } else if (p->double_mode == -1) {
-        s3d_status s = resize_launch(ctx, 1, p->stage.p, p->X, p->Y, p->Z, p->X, p->img0.p, p->img0.pitch);
-        if (s != S3D_OK) return s;
-    } else {
+    // pre-step: -2+ / -2- / plain copy into the pitched pyramid input (or straight into level 0)
+    if (p->input_is_g0) {
+        if (p->n_oct == 0) { ctx->has_result = true; return S3D_OK; }
+        Vol &g0 = p->g[0];
         long long rows = (long long)p->Y * p->Z;
-        dim3 grid((p->img0.pitch + 255) / 256, (unsigned)(rows < 8192 ? rows : 8192));
-        pad_rows_kernel<<<grid, 256, 0, st>>>(p->stage.p, p->X, rows, p->img0.p, p->img0.pitch);
+        dim3 grid((g0.pitch + 255) / 256, (unsigned)(rows < 8192 ? rows : 8192));
+        pad_rows_kernel<<<grid, 256, 0, st>>>(p->stage.p, p->X, rows, g0.p, g0.pitch);
         ctx->launches++;
-    }
-    if (p->n_oct == 0) {
-        ctx->has_result = true;
-        return S3D_OK;
-    }
-    mark(ctx, "pre-step/pad");
-    // initial blur (MultiScale.cpp:298)
-    {
+        mark(ctx, "level 0 copy");
+    } else {
+        if (p->double_mode == 1) {
+            s3d_status s = resize_launch(ctx, 2, p->stage.p, p->X, p->Y, p->Z, p->X, p->img0.p, p->img0.pitch);
+            if (s != S3D_OK) return s;
+        } else if (p->double_mode == -1) {
+            s3d_status s = resize_launch(ctx, 1, p->stage.p, p->X, p->Y, p->Z, p->X, p->img0.p, p->img0.pitch);
+            if (s != S3D_OK) return s;
+        } else {
+            long long rows = (long long)p->Y * p->Z;
+            dim3 grid((p->img0.pitch + 255) / 256, (unsigned)(rows < 8192 ? rows : 8192));
+            pad_rows_kernel<<<grid, 256, 0, st>>>(p->stage.p, p->X, rows, p->img0.p, p->img0.pitch);
+            ctx->launches++;
+        }
+        if (p->n_oct == 0) {
+            ctx->has_result = true;
+            return S3D_OK;
+        }
+        mark(ctx, "pre-step/pad");
+        // initial blur (MultiScale.cpp:298)
         Vol &g0 = p->g[0];
         s3d_status s = blur3d(ctx, p->img0.p, p->tmp1, g0.p, g0.X, g0.Y, g0.Z, g0.pitch, p->init_taps, p->n_init_taps, nullptr);
         if (s != S3D_OK) return s;
+        mark(ctx, "initial blur");
     }
-    mark(ctx, "initial blur");
     // Octave o+1 only needs level 3 of octave o, so every octave runs on its own branch (stream / graph
-    // branch): the tail of an octave (levels 4, 5 and its three detection passes) overlaps the whole
-    // chain of smaller octaves, which is launch-latency bound.
+    // branch): the tail of an octave overlaps the whole chain of smaller octaves, which is launch-latency bound.
     ListDesc L{ p->n_lists, p->cand_cap, p->cand_raw, p->counts };
     CK(cudaMemsetAsync(p->face_counts, 0, sizeof(int) * kMaxOct * 3, st));
     for (int o = 0; o < p->n_oct; o++) {
@@ -806,7 +826,7 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
                     s = detect_two_pass(ctx, od.d[c_det - 1], od.d[c_det], od.X, od.Y, od.Z, od.pitch,
                                         p->face[o * 3 + c_det - 1], p->face_counts + o * 3 + c_det - 1, p->face_cap[o * 3 + c_det - 1],
                                         p->cand_raw + (size_t)l0 * p->cand_cap, p->counts + l0,
-                                        p->cand_raw + (size_t)(l0 + 1) * p->cand_cap, p->counts + l0 + 1, p->cand_cap, err);
+                                        p->cand_raw + (size_t)(l0 + 1) * p->cand_cap, p->counts + l0 + 1, p->cand_cap, err, od.own0, od.own1);
                     if (s != S3D_OK) { ctx->cur = st; return s; }
                 }
                 if (c_ref >= 1) {
@@ -834,10 +854,10 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     mark(ctx, "orient_b");
     row_offsets_kernel<<<1, 1024, 0, st>>>(p->kp_nprim, p->kp_nsec, kp_count, p->nrows, p->row_off, p->row_map, n_features, p->row_cap, err);
     float size_factor = 1.0f;
-    if (p->double_mode > 0) size_factor /= 2; else if (p->double_mode < 0) size_factor *= 2;
+    if (p->double_mode > 0 || p->pre_step_done > 0) size_factor /= 2; else if (p->double_mode < 0 || p->pre_step_done < 0) size_factor *= 2;
     int grid_d = ctx->sm_count * 10;
     describe_kernel<<<grid_d, 128, sizeof(DescribeSmem), st>>>(p->pyr, p->kps, n_features, p->row_map, p->kp_nsec, p->kp_eigs,
-                                                              p->kp_ori0, p->kp_rots, p->kp_patch0, prm->descriptor, size_factor,
+                                                              p->kp_ori0, p->kp_rots, p->kp_patch0, prm->descriptor, size_factor, p->octave_base,
                                                               p->row_cap, p->feats, p->dbg_patches, p->dbg_prerank);
     mark(ctx, "row_offsets+describe");
     ctx->launches += 5;
@@ -853,6 +873,15 @@ static s3d_status check_params(s3d_ctx *ctx, const float *vol, int X, int Y, int
     if (prm->double_mode < -1 || prm->double_mode > 1) return fail(ctx, S3D_ERR_INVALID, "double_mode must be -1, 0 or +1");
     if (prm->descriptor < 0 || prm->descriptor > 3) return fail(ctx, S3D_ERR_INVALID, "unknown descriptor");
     if (prm->double_mode != 0 && (X < 2 || Y < 2 || Z < 2)) return fail(ctx, S3D_ERR_INVALID, "volume too small for -2+/-2-");
+    if (prm->input_is_g0 && prm->double_mode != 0) return fail(ctx, S3D_ERR_INVALID, "input_is_g0 excludes -2+/-2-");
+    if (prm->pre_step_done < -1 || prm->pre_step_done > 1 || (prm->pre_step_done != 0 && prm->double_mode != 0))
+        return fail(ctx, S3D_ERR_INVALID, "pre_step_done must be -1, 0 or +1 and excludes double_mode");
+    if (prm->octave_base < 0 || prm->octave_base > 20 || prm->max_octaves < 0) return fail(ctx, S3D_ERR_INVALID, "bad octave_base / max_octaves");
+    if (prm->slab) {
+        if (prm->max_octaves != 1 || prm->double_mode != 0) return fail(ctx, S3D_ERR_INVALID, "slab mode runs one octave per call, without pre-step");
+        if (prm->z_off < 0 || prm->z_off + Z > prm->z_global || prm->own_z0 < prm->z_off || prm->own_z1 > prm->z_off + Z || prm->own_z0 > prm->own_z1)
+            return fail(ctx, S3D_ERR_INVALID, "slab ranges are inconsistent");
+    }
     return S3D_OK;
 }
 
@@ -996,6 +1025,35 @@ extern "C" s3d_status s3d_get_level(s3d_ctx *ctx, int octave, int is_dog, int le
                              cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
+    return S3D_OK;
+}
+
+extern "C" s3d_status s3d_copy_level_device(s3d_ctx *ctx, int octave, int is_dog, int level, int z0, int z1, float *d_dst)
+{
+    if (!ctx || !ctx->plan || !ctx->has_result || !d_dst) return S3D_ERR_INVALID;
+    Plan *p = ctx->plan;
+    if (octave < 0 || octave >= p->n_oct || level < 0 || level >= (is_dog ? 5 : 6)) return fail(ctx, S3D_ERR_INVALID, "no such level");
+    Vol &v = is_dog ? p->d[octave * 5 + level] : p->g[octave * 6 + level];
+    if (z0 < 0 || z1 > v.Z || z0 >= z1) return fail(ctx, S3D_ERR_INVALID, "bad plane range");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy2DAsync(d_dst, sizeof(float) * v.X, v.p + (size_t)z0 * v.Y * v.pitch, sizeof(float) * v.pitch, sizeof(float) * v.X,
+                         (size_t)v.Y * (z1 - z0), cudaMemcpyDeviceToDevice, ctx->stream));
+    return S3D_OK;
+}
+
+extern "C" s3d_status s3d_get_row_keypoints(s3d_ctx *ctx, int **row_kp, int *n_out)
+{
+    if (!ctx || !row_kp || !n_out) return S3D_ERR_INVALID;
+    s3d_status s = fetch_counts(ctx);
+    if (s != S3D_OK) return s;
+    int n = ctx->h_counts[1];
+    int *h = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    if (n > 0) {
+        CK(cudaMemcpyAsync(h, ctx->plan->row_map, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < n; i++) h[i] /= kMaxRowsPerKp;
+    }
+    *row_kp = h; *n_out = n;
     return S3D_OK;
 }
 

@@ -23,6 +23,8 @@ constexpr int kMaxSphere = 640;
 
 struct OctaveDesc {
     int X, Y, Z, pitch;
+    int z_off, Zg, own0, own1;   // slab mode: buffer plane 0 = global plane z_off of an octave of depth Zg;
+                                 // candidates only from local planes [own0, own1).  Whole volume: 0, Z, 0, Z.
     const float *g[6];
     const float *d[5];
     float sigma[6];
@@ -171,7 +173,7 @@ constexpr int PVP = 1332;   // patch arrays are padded to a multiple of 4 floats
 // sampleImage3D (reference MultiScale.cpp:2614-2714): inv = inverse orientation, already in smem.
 // Each thread owns up to 6 samples; the loop is fully unrolled and branch-light so the 8 corner loads of
 // all of a thread's samples are in flight together (the gather is pure latency otherwise).
-__device__ void gather_patch(const float *__restrict__ img, int X, int Y, int Z, int pitch,
+__device__ void gather_patch(const float *__restrict__ img, int X, int Y, int Zg, int z_off, int pitch,
                              float fx, float fy, float fz, float scale, const float *inv, float *patch)
 {
     const float fImageRad = 2.0f * scale;
@@ -197,9 +199,9 @@ __device__ void gather_patch(const float *__restrict__ img, int X, int Y, int Z,
             int iX, iY, iZ;
             interp_coord(p0, (float)X, iX, w[u][0]);
             interp_coord(p1, (float)Y, iY, w[u][1]);
-            interp_coord(p2, (float)Z, iZ, w[u][2]);
+            interp_coord(p2, (float)Zg, iZ, w[u][2]);      // global depth; the buffer starts at global plane z_off
             if (!inside[u]) iX = 0;   // value unused; keep the address legal
-            const float *p = img + ((long long)iZ * Y + iY) * pitch + iX;
+            const float *p = img + ((long long)(iZ - z_off) * Y + iY) * pitch + iX;
             v[u][0] = __ldg(p); v[u][1] = __ldg(p + 1); v[u][2] = __ldg(p + pitch); v[u][3] = __ldg(p + pitch + 1);
             v[u][4] = __ldg(p + plane); v[u][5] = __ldg(p + plane + 1); v[u][6] = __ldg(p + plane + pitch); v[u][7] = __ldg(p + plane + pitch + 1);
         }
@@ -512,7 +514,7 @@ __global__ void __launch_bounds__(256) cand_refine_kernel(const __grid_constant_
     const int list = list_begin + blockIdx.x;
     const int octave = list / 6, c = (list / 2) % 3 + 1, is_max = list & 1;
     const OctaveDesc &o = pyr.oct[octave];
-    const int X = o.X, Y = o.Y, Z = o.Z, pitch = o.pitch;
+    const int X = o.X, Y = o.Y, pitch = o.pitch;
     const long long plane = (long long)pitch * Y;
     int n = L.counts[list];
     if (n > L.cap) { if (threadIdx.x == 0 && blockIdx.y == 0) atomicOr(err, ERR_CAND_OVERFLOW); n = L.cap; }
@@ -538,19 +540,22 @@ __global__ void __launch_bounds__(256) cand_refine_kernel(const __grid_constant_
         bool valid = false;
         s3d_keypoint kp;
         if (ok) {
+            // geometry is computed in GLOBAL plane coordinates (slab mode: local z + z_off), because the
+            // parabola arithmetic and later float sums depend on the magnitude of z
+            const int gz = cd.z + o.z_off;
             float fx = (float)interp_quadratic(cd.x - 1, cd.x, cd.x + 1, dC[i - 1], dC[i], dC[i + 1]);
             float fy = (float)interp_quadratic(cd.y - 1, cd.y, cd.y + 1, dC[i - pitch], dC[i], dC[i + pitch]);
-            float fz = (float)interp_quadratic(cd.z - 1, cd.z, cd.z + 1, dC[i - plane], dC[i], dC[i + plane]);
+            float fz = (float)interp_quadratic(gz - 1, gz, gz + 1, dC[i - plane], dC[i], dC[i + plane]);
             float scale = (float)(2 * interp_quadratic(o.sigma[c - 1], o.sigma[c], o.sigma[c + 1], dH[i], dC[i], dL[i]));
             fx += 0.5f; fy += 0.5f; fz += 0.5f;
             float fImageRad = 2.0f * scale;
             int iRadMax = (int)(fImageRad + 2);
             bool oob = (fx - iRadMax < 0 || fy - iRadMax < 0 || fz - iRadMax < 0 ||
-                        fx + iRadMax >= X || fy + iRadMax >= Y || fz + iRadMax >= Z);
+                        fx + iRadMax >= X || fy + iRadMax >= Y || fz + iRadMax >= o.Zg);
             if (!oob) {
                 valid = true;
                 kp.octave = octave; kp.level = c; kp.is_max = is_max;
-                kp.ix = cd.x; kp.iy = cd.y; kp.iz = cd.z;
+                kp.ix = cd.x; kp.iy = cd.y; kp.iz = gz;
                 kp.x = fx; kp.y = fy; kp.z = fz; kp.scale = scale;
             }
         }
@@ -781,7 +786,7 @@ __global__ void __launch_bounds__(256) orient_a_kernel(const __grid_constant__ P
         // --- identity patch, normalised (generateFeature3D :1721-1739)
         if (threadIdx.x == 0) { float id[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 }; invert3(id, S.inv); }
         __syncthreads();
-        gather_patch(img, o.X, o.Y, o.Z, o.pitch, kp.x, kp.y, kp.z, kp.scale, S.inv, S.patch);
+        gather_patch(img, o.X, o.Y, o.Zg, o.z_off, o.pitch, kp.x, kp.y, kp.z, kp.scale, S.inv, S.patch);
         __syncthreads();
         PHASE(1);
         normalize_patch(S.patch, S.h0, S.red);
@@ -1050,7 +1055,7 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ P
                                                        const int *__restrict__ kp_nsec,
                                                        const float *__restrict__ kp_eigs, const float *__restrict__ kp_ori0,
                                                        const float *__restrict__ kp_rots, const float *__restrict__ kp_patch0,
-                                                       int descriptor, float size_factor, int row_cap,
+                                                       int descriptor, float size_factor, int octave_base, int row_cap,
                                                        s3d_feature *__restrict__ feats,
                                                        float *__restrict__ dbg_patches, float *__restrict__ dbg_prerank)
 {
@@ -1088,7 +1093,7 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ P
             for (int i = threadIdx.x; i < PV; i += blockDim.x) S.patch[i] = kp_patch0[(long long)kpi * PV + i];
         } else {
             __syncthreads();
-            gather_patch(o.g[kp.level], o.X, o.Y, o.Z, o.pitch, kp.x, kp.y, kp.z, kp.scale, S.inv, S.patch);
+            gather_patch(o.g[kp.level], o.X, o.Y, o.Zg, o.z_off, o.pitch, kp.x, kp.y, kp.z, kp.scale, S.inv, S.patch);
         }
         __syncthreads();
         if (dbg_patches) for (int i = threadIdx.x; i < PV; i += blockDim.x) dbg_patches[(long long)row * PV + i] = S.patch[i];
@@ -1187,7 +1192,7 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ P
         s3d_feature *f = feats + row;
         if (threadIdx.x == 0) {
             float fFactor = 1.0f;
-            for (int q = 0; q < kp.octave; q++) fFactor = fFactor * 2.0f;
+            for (int q = 0; q < kp.octave + octave_base; q++) fFactor = fFactor * 2.0f;
             float sc = kp.scale * fFactor;
             float x = kp.x * fFactor + 0.0f, y = kp.y * fFactor + 0.0f, z = kp.z * fFactor + 0.0f;
             f->flag = (kp.is_max ? 0x10u : 0u) | (r > 0 ? 0x20u : 0u);

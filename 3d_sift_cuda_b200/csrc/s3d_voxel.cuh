@@ -382,7 +382,8 @@ __global__ void __launch_bounds__(256) detect_face_kernel(const float *__restric
 __global__ void __launch_bounds__(256) detect_full_kernel(const float *__restrict__ finer, const float *__restrict__ centre,
                                                           int X, int Y, int Z, int pitch,
                                                           const unsigned int *__restrict__ face, const int *__restrict__ face_count,
-                                                          int face_cap, CandList mins, CandList maxs, int cap, int *err, int err_bit)
+                                                          int face_cap, CandList mins, CandList maxs, int cap, int *err, int err_bit,
+                                                          int own0, int own1)
 {
     int n = *face_count;
     if (n > face_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, err_bit); n = face_cap; }
@@ -407,6 +408,7 @@ __global__ void __launch_bounds__(256) detect_full_kernel(const float *__restric
             }
         if (mx || mn) {
             int z = (int)(i / plane);
+            if (z < own0 || z >= own1) continue;       // slab mode: halo planes belong to the neighbour
             int rem = (int)(i - (long long)z * plane);
             int y = rem / pitch, x = rem - y * pitch;
             if (mx) { int kk = atomicAdd(maxs.count, 1); if (kk < cap) maxs.items[kk] = s3d_cand{ x, y, z, c }; }
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(256) detect_full_kernel(const float *__restric
 // single-kernel variant (kept for volumes too large for 32-bit voxel offsets)
 __global__ void __launch_bounds__(256) detect_kernel(const float *__restrict__ finer, const float *__restrict__ centre,
                                                      int X, int Y, int Z, int pitch,
-                                                     CandList mins, CandList maxs, int cap)
+                                                     CandList mins, CandList maxs, int cap, int own0, int own1)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x + 1;
     int y = blockIdx.y * blockDim.y + threadIdx.y + 1;
@@ -436,6 +438,7 @@ __global__ void __launch_bounds__(256) detect_kernel(const float *__restrict__ f
     for (int k = 0; k < kDetectZ; k++) {
         int z = z0 + k;
         if (z > Z - 2) break;
+        if (z < own0 || z >= own1) continue;
         float c = col[k + 1];
         bool mx = (col[k] < c) && (col[k + 2] < c);
         bool mn = (col[k] > c) && (col[k + 2] > c);

@@ -53,3 +53,235 @@ def max_over_ranks(value, device=None, group=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------------------
+# Single large volume: z-slab decomposition (BASELINE.json config 5)
+# ------------------------------------------------------------------------------------------------------
+# Every rank owns a contiguous range of z planes.  Per octave it runs the engine on [halo | own | halo]
+# (s3d_params.slab): candidates are only taken from owned planes, zero padding / support-box test /
+# trilinear clamp use the global depth, so with a halo deeper than the dependency reach of one octave
+# (blur radii 3+4+5+6+8 = 26 planes, +1 for detection/validation, + the 11^3 patch reach of about
+# 3.46 * scale <= 30 planes on level 3) every owned keypoint is bit-identical to the whole-volume run.
+# Between octaves each rank subsamples its own part of level 3 and refreshes the halos from its two
+# neighbours (NCCL send/recv over NVLink) -- one exchange per octave, no collective in the voxel
+# stages.  When slabs get thinner than the halo the remaining (small) octaves collapse onto rank 0.
+SLAB_HALO = 48          # planes of level 0 kept valid around the owned range, per octave
+INIT_BLUR_RADIUS = 4    # initial blur: 9 taps (7 after -2+), reference MultiScale.cpp:288-298
+
+
+def slab_plan(z0_planes, world, halo=SLAB_HALO, max_octaves=12):
+    """Plane ownership for ``world`` ranks of an octave-0 volume of depth ``z0_planes``.
+
+    Returns (K, bounds): K = number of octaves run in slab mode, bounds[r] .. bounds[r+1] = planes of
+    octave 0 owned by rank r (multiples of 2**K, so every 2x subsample stays inside a rank).  K is the
+    largest count for which every rank still owns >= halo planes at octave K-1."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    best = (0, [0] + [z0_planes] * world)
+    for K in range(1, max_octaves + 1):
+        step = 1 << K
+        bounds = [0]
+        for r in range(1, world):
+            bounds.append(int(round(r * z0_planes / world / step)) * step)
+        bounds.append(z0_planes)
+        if any(b1 <= b0 for b0, b1 in zip(bounds[:-1], bounds[1:])):
+            break
+        own_min = min((b1 >> (K - 1)) - (b0 >> (K - 1)) for b0, b1 in zip(bounds[:-1], bounds[1:]))
+        depth = z0_planes >> (K - 1)
+        if own_min < halo or depth <= 2:
+            break
+        best = (K, bounds)
+    return best
+
+
+def merge_slab_rows(per_rank, n_slab_octaves):
+    """Restore the reference's output order from per-rank, per-octave results.
+
+    per_rank[r][o] = (features, level, is_max) with one level / is_max entry per feature row, rows in the
+    engine's order (level up, minima then maxima, raster).  Order of the merged list: octave, level,
+    minima then maxima, then ranks in z order (= raster order, slabs are z-contiguous)."""
+    out = []
+    for o in range(n_slab_octaves):
+        for level in (1, 2, 3):
+            for is_max in (0, 1):
+                for r in range(len(per_rank)):
+                    feats, lv, mx = per_rank[r][o]
+                    sel = (lv == level) & (mx == is_max)
+                    if sel.any():
+                        out.append(feats[sel])
+    return out
+
+
+def _run_slab_octave(engine, api, d_buf, o, z_off, z_global, own0, own1, base_params):
+    """One octave of one slab on the engine; returns (features, level, is_max) per row."""
+    nz, Y, X = d_buf.shape
+    prm = api.Params(descriptor=base_params["descriptor"], eig_thres=base_params["eig_thres"],
+                     input_is_g0=(o > 0), octave_base=o, max_octaves=1,
+                     slab=(z_off, z_global, own0, own1), pre_step_done=base_params["double_mode"])
+    engine.extract_device(d_buf, (X, Y, nz), prm)
+    feats = engine.fetch_features()
+    kps = engine.keypoints()
+    rk = engine.row_keypoints()
+    return feats, kps["level"][rk], kps["is_max"][rk]
+
+
+def _next_own_level0(engine, torch, z_off, own0, own1, dims_xyz):
+    """2x2x2 mean of this rank's own part of level 3 -> its own part of the next octave's level 0."""
+    X, Y, _ = dims_xyz
+    n_next = (own1 >> 1) - (own0 >> 1)
+    g3 = torch.empty((2 * n_next, Y, X), dtype=torch.float32, device="cuda")
+    engine.copy_level_device(0, 3, own0 - z_off, own0 - z_off + 2 * n_next, g3)
+    nxt = torch.empty((n_next, Y // 2, X // 2), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    engine.subsample2(g3, X, nxt)
+    engine.sync()
+    return nxt
+
+
+def _octave0_image_slab(engine, torch, volume, double_mode, lo, hi):
+    """Planes [lo, hi) of the pre-stepped (octave-0 resolution) image, as a dense device tensor."""
+    Z, Y, X = volume.shape
+    if double_mode == 0:
+        return torch.from_numpy(np.ascontiguousarray(volume[lo:hi])).cuda()
+    if double_mode == 1:     # fioDoubleSize: doubled plane 2z+dz needs original planes z, z+1 (clamped at the end)
+        o0, o1 = lo // 2, min(Z, (hi - 1) // 2 + 2)
+        src = torch.from_numpy(np.ascontiguousarray(volume[o0:o1])).cuda()
+        dst = torch.empty((2 * (o1 - o0), 2 * Y, 2 * X), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        engine.double_size(src, X, dst)
+        engine.sync()
+        return dst[lo - 2 * o0: hi - 2 * o0].contiguous()
+    o0, o1 = 2 * lo, 2 * hi  # fioSubSample2DCenterPixel
+    src = torch.from_numpy(np.ascontiguousarray(volume[o0:o1])).cuda()
+    dst = torch.empty((hi - lo, Y // 2, X // 2), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    engine.halve_size(src, X, dst)
+    engine.sync()
+    return dst
+
+
+def _pre_stepped_dims(shape_zyx, double_mode):
+    Z, Y, X = shape_zyx
+    if double_mode == 1:
+        return 2 * X, 2 * Y, 2 * Z
+    if double_mode == -1:
+        return X // 2, Y // 2, Z // 2
+    return X, Y, Z
+
+
+def extract_slab(engine, volume, rank=0, world=1, group=None, double_mode=0, descriptor=0, eig_thres=140.0,
+                 halo=SLAB_HALO, emulate_ranks=None):
+    """featExtract of ONE volume split into z slabs over ``world`` ranks; rank 0 returns the feature rows
+    in the reference's order (bit-identical to the whole-volume engine), other ranks return None.
+
+    ``volume``: numpy (Z, Y, X) float32 visible to every rank (only the rank's slab + halo is uploaded).
+    ``emulate_ranks=N`` runs N virtual ranks one after the other on this process' GPU (no
+    torch.distributed): same code path except that halos are handed over in memory.
+    """
+    import importlib
+    import torch
+    api = importlib.import_module("3d_sift_cuda_b200.api")
+    base = {"descriptor": descriptor, "eig_thres": eig_thres, "double_mode": double_mode}
+    X0, Y0, Z0 = _pre_stepped_dims(volume.shape, double_mode)
+    emu = emulate_ranks is not None
+    nranks = emulate_ranks if emu else world
+    K, bounds = slab_plan(Z0, nranks, halo)
+    my_ranks = list(range(nranks)) if emu else [rank]
+    if nranks == 1 or K == 0:
+        if emu or rank == 0:
+            return engine.extract(volume, api.Params(double_mode=double_mode, descriptor=descriptor, eig_thres=eig_thres))
+        return None
+    if not emu:
+        import torch.distributed as dist
+
+    own_g0 = {}      # rank -> dense device tensor of its own planes of the current octave's level 0
+    results = {r: [] for r in my_ranks}
+    dims = (X0, Y0, Z0)
+    for o in range(K):
+        Xo, Yo, Zo = dims
+        own = {r: (bounds[r] >> o, (bounds[r + 1] >> o) if r + 1 < nranks else Zo) for r in range(nranks)}
+        # ---- assemble [halo | own | halo] per rank
+        bufs = {}
+        if o == 0:
+            hi_ = halo + INIT_BLUR_RADIUS
+            for r in my_ranks:
+                lo, hi = max(0, own[r][0] - hi_), min(Zo, own[r][1] + hi_)
+                bufs[r] = (lo, _octave0_image_slab(engine, torch, volume, double_mode, lo, hi))
+        else:
+            if emu:
+                for r in my_ranks:
+                    parts, lo = [], own[r][0]
+                    if r > 0:
+                        parts.append(own_g0[r - 1][-halo:]); lo -= halo
+                    parts.append(own_g0[r])
+                    if r + 1 < nranks:
+                        parts.append(own_g0[r + 1][:halo])
+                    bufs[r] = (lo, torch.cat(parts).contiguous())
+            else:
+                r = rank
+                mine = own_g0[r]
+                lo_t = torch.empty((halo,) + tuple(mine.shape[1:]), dtype=torch.float32, device="cuda") if r > 0 else None
+                hi_t = torch.empty((halo,) + tuple(mine.shape[1:]), dtype=torch.float32, device="cuda") if r + 1 < nranks else None
+                ops = []
+                if r > 0:
+                    ops += [dist.P2POp(dist.isend, mine[:halo].contiguous(), r - 1, group), dist.P2POp(dist.irecv, lo_t, r - 1, group)]
+                if r + 1 < nranks:
+                    ops += [dist.P2POp(dist.isend, mine[-halo:].contiguous(), r + 1, group), dist.P2POp(dist.irecv, hi_t, r + 1, group)]
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+                parts, lo = [], own[r][0]
+                if lo_t is not None:
+                    parts.append(lo_t); lo -= halo
+                parts.append(mine)
+                if hi_t is not None:
+                    parts.append(hi_t)
+                bufs[r] = (lo, torch.cat(parts).contiguous())
+        # ---- run the octave, keep the own part of the next octave's level 0
+        nxt = {}
+        for r in my_ranks:
+            z_off, d_buf = bufs[r]
+            torch.cuda.synchronize()
+            results[r].append(_run_slab_octave(engine, api, d_buf, o, z_off, Zo, own[r][0], own[r][1], base))
+            nxt[r] = _next_own_level0(engine, torch, z_off, own[r][0], own[r][1], dims)
+        own_g0 = nxt
+        dims = (Xo // 2, Yo // 2, Zo // 2)
+
+    # ---- collapse: the remaining octaves run on rank 0 from the gathered level 0 of octave K
+    tail = None
+    if emu:
+        full = torch.cat([own_g0[r] for r in range(nranks)]).contiguous()
+    else:
+        full = None
+        if rank == 0:
+            parts = [own_g0[0]]
+            for r in range(1, nranks):
+                n_r = (bounds[r + 1] >> K if r + 1 < nranks else dims[2]) - (bounds[r] >> K)
+                t = torch.empty((n_r, dims[1], dims[0]), dtype=torch.float32, device="cuda")
+                dist.recv(t, r, group)
+                parts.append(t)
+            full = torch.cat(parts).contiguous()
+        else:
+            dist.send(own_g0[rank].contiguous(), 0, group)
+    if full is not None and min(dims) > 2:
+        assert tuple(full.shape) == (dims[2], dims[1], dims[0]), (full.shape, dims)
+        torch.cuda.synchronize()
+        engine.extract_device(full, dims, api.Params(descriptor=descriptor, eig_thres=eig_thres, input_is_g0=True,
+                                                     octave_base=K, pre_step_done=double_mode))
+        tail = engine.fetch_features()
+
+    # ---- rank 0 merges (small: feature rows only)
+    if emu:
+        per_rank = [results[r] for r in range(nranks)]
+    else:
+        gathered = [None] * nranks if rank == 0 else None
+        dist.gather_object(results[rank], gathered, dst=0, group=group)
+        if rank != 0:
+            return None
+        per_rank = gathered
+    rows = merge_slab_rows(per_rank, K)
+    if tail is not None and len(tail):
+        rows.append(tail)
+    if not rows:
+        return np.zeros(0, api.FEATURE_DTYPE)
+    return np.concatenate(rows)

@@ -77,6 +77,21 @@ typedef struct s3d_params {
     int max_keypoints;   /* 0 = default (16384) */
     int max_features;    /* 0 = default (8 * max_keypoints) */
     int keep_patches;    /* debug: keep the 11^3 patch of every feature row (s3d_get_patches) */
+    /* --- octave-run / z-slab mode (multi-GPU single-volume decomposition; all zero = whole-volume mode) ---
+     * input_is_g0 : the volume passed in already IS Gaussian level 0 of an octave (sigma 1.6): no pre-step,
+     *               no initial blur.  octave_base = index of that octave in the full pyramid (features are
+     *               scaled by 2^(octave_base + o)); max_octaves > 0 limits how many octaves are built.
+     * slab        : the buffer holds global planes [z_off, z_off + Z) of an octave whose true depth is
+     *               z_global; candidates are only taken from global planes [own_z0, own_z1).  Zero padding,
+     *               the support-box test and the trilinear clamp use the GLOBAL depth, so with deep enough
+     *               halos every owned keypoint is bit-identical to the whole-volume run. */
+    int input_is_g0;
+    int octave_base;
+    int max_octaves;
+    int slab;
+    int z_off, z_global, own_z0, own_z1;
+    int pre_step_done;   /* +1 / -1: the caller already applied -2+ / -2- to the volume (slab mode resizes each
+                            slab itself); only the initial-blur sigma and the final size factor follow it */
 } s3d_params;
 
 /* ---- context ------------------------------------------------------------------------------------
@@ -168,6 +183,12 @@ s3d_status s3d_get_keypoints(s3d_ctx *ctx, s3d_keypoint **out, int *n_out);
 /* With params.keep_patches: n_features * 1331 floats, the 11^3 patch of each row as the pyramid
  * stage leaves it (before the descriptor loop's NormalizeData), and the 64 pre-rank values. */
 s3d_status s3d_get_patches(s3d_ctx *ctx, float **patches, float **prerank, int *n_out);
+/* Copy planes [z0, z1) of a pyramid level of the last extraction into a dense DEVICE buffer
+ * (X*Y*(z1-z0) floats, the reference's layout).  Used by the slab orchestration to hand level 3 to the
+ * next octave. */
+s3d_status s3d_copy_level_device(s3d_ctx *ctx, int octave, int is_dog, int level, int z0, int z1, float *d_dst);
+/* Per feature row of the last extraction: index of its keypoint (s3d_get_keypoints order). */
+s3d_status s3d_get_row_keypoints(s3d_ctx *ctx, int **row_kp, int *n_out);
 /* Number of kernel launches (graph nodes included) issued by the last extraction. */
 int s3d_last_launch_count(s3d_ctx *ctx);
 

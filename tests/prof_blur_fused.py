@@ -8,6 +8,7 @@ pitch = (X + 7) // 8 * 8
 vol = pkg.phantom.brain_phantom()
 a = torch.zeros((Z, Y, pitch), dtype=torch.float32, device="cuda"); a[:, :, :X] = torch.from_numpy(vol).cuda()
 tmp, out, dog = torch.empty_like(a), torch.empty_like(a), torch.empty_like(a)
+torch.cuda.synchronize()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 sigmas = [1.5199, 1.2263, 1.5450, 1.9466, 2.4525, 3.0900]
 N0 = X * Y * Z

@@ -9,6 +9,7 @@ pitch = (X + 7) // 8 * 8
 sigma = float(sys.argv[1]) if len(sys.argv) > 1 else 3.09
 a = torch.zeros((Z, Y, pitch), dtype=torch.float32, device="cuda"); a[:, :, :X] = torch.from_numpy(pkg.phantom.brain_phantom()).cuda()
 tmp, out, dog = torch.empty_like(a), torch.empty_like(a), torch.empty_like(a)
+torch.cuda.synchronize()
 e = pkg.Engine(0)
 taps = pkg.gaussian_taps(sigma)
 for _ in range(4):

@@ -60,3 +60,22 @@ def test_extract_sharded_single_rank(pkg):
     d = importlib.import_module("3d_sift_cuda_b200.dist")
     out = d.extract_sharded(lambda v: v * 2, [np.ones(2), np.zeros(2)])
     assert out[0].tolist() == [2, 2] and out[1].tolist() == [0, 0]
+
+
+def test_slab_plan_and_merge(pkg):
+    d = importlib.import_module("3d_sift_cuda_b200.dist")
+    K, b = d.slab_plan(1024, 8)            # config 5: 512^3 with -2+ -> 1024 planes over 8 GPUs
+    assert K == 2 and b == [0, 128, 256, 384, 512, 640, 768, 896, 1024]
+    K, b = d.slab_plan(364, 2)             # MNI with -2+
+    assert K == 2 and b[0] == 0 and b[-1] == 364 and b[1] % 4 == 0
+    assert all((b1 >> (K - 1)) - (b0 >> (K - 1)) >= d.SLAB_HALO for b0, b1 in zip(b[:-1], b[1:]))
+    assert d.slab_plan(60, 4)[0] == 0      # too thin to split: whole-volume mode
+    assert d.slab_plan(500, 1)[0] >= 1
+    # merge order: octave, level, min/max, rank (= z order)
+    def mk(tag, levels, maxs):
+        f = np.zeros(len(levels), pkg.FEATURE_DTYPE)
+        f["x"] = [tag * 100 + i for i in range(len(levels))]
+        return f, np.array(levels), np.array(maxs)
+    per_rank = [[mk(1, [1, 1, 2], [0, 1, 0])], [mk(2, [1, 2, 2], [0, 0, 1])]]
+    merged = np.concatenate(d.merge_slab_rows(per_rank, 1))["x"].tolist()
+    assert merged == [100, 200, 101, 102, 201, 202]

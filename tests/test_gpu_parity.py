@@ -23,6 +23,12 @@ def to_dev(vol, pitch=None):
     return torch.from_numpy(buf).cuda()
 
 
+def ready():
+    """The engine runs on its own stream: finish torch's pending fills before handing tensors over."""
+    import torch
+    torch.cuda.synchronize()
+
+
 def from_dev(t, X):
     return t.cpu().numpy()[:, :, :X].copy()
 
@@ -41,6 +47,7 @@ def test_blur_bit_exact(pkg, oracle, engine, shape_xyz, sigma):
     want = oracle.blur(vol, sigma)
     d_in = to_dev(vol)
     d_tmp, d_out, d_dog = torch.zeros_like(d_in), torch.zeros_like(d_in), torch.zeros_like(d_in)
+    ready()
     engine.blur3d(d_in, d_tmp, d_out, X, pkg.gaussian_taps(sigma), d_dog)
     engine.sync()
     assert (bits(from_dev(d_out, X)) == bits(want)).all()
@@ -54,6 +61,7 @@ def test_blur_unaligned_pitch_takes_scalar_path(pkg, oracle, engine):
     vol = pkg.phantom.blob_phantom((21, 17, 13), seed=5, nblobs=8)
     d_in = torch.from_numpy(vol).cuda()   # pitch == X == 21: the reference's dense layout
     d_tmp, d_out = torch.zeros_like(d_in), torch.zeros_like(d_in)
+    ready()
     engine.blur3d(d_in, d_tmp, d_out, 21, pkg.gaussian_taps(1.5199))
     engine.sync()
     assert (bits(d_out.cpu().numpy()) == bits(oracle.blur(vol, 1.5199))).all()
@@ -66,6 +74,7 @@ def test_dog_subsample_resize_bit_exact(pkg, oracle, engine):
     X = 45
     a, b = to_dev(vol), to_dev(vol2)
     out = torch.zeros_like(a)
+    ready()
     engine.dog(a, b, out, X)
     engine.sync()
     assert (bits(from_dev(out, X)) == bits(oracle.dog(vol, vol2))).all()
@@ -73,6 +82,7 @@ def test_dog_subsample_resize_bit_exact(pkg, oracle, engine):
         want = getattr(oracle, {"subsample2": "subsample", "halve_size": "halve_size", "double_size": "double_size"}[name])(vol)
         oz, oy, ox = want.shape
         d_out = torch.full((oz, oy, (ox + 7) // 8 * 8), 7.0, dtype=torch.float32, device="cuda")
+        ready()
         getattr(engine, name)(a, X, d_out)
         engine.sync()
         assert (bits(from_dev(d_out, ox)) == bits(want)).all(), name
@@ -171,6 +181,7 @@ def test_fused_blur_path_bit_exact(pkg, oracle, monkeypatch):
                 want = oracle.blur(vol, sigma)
                 d_in = to_dev(vol)
                 d_tmp, d_out, d_dog = torch.zeros_like(d_in), torch.zeros_like(d_in), torch.zeros_like(d_in)
+                ready()
                 eng.blur3d(d_in, d_tmp, d_out, X, pkg.gaussian_taps(sigma), d_dog)
                 eng.sync()
                 assert (bits(from_dev(d_out, X)) == bits(want)).all(), (shape_xyz, sigma)
@@ -180,3 +191,35 @@ def test_fused_blur_path_bit_exact(pkg, oracle, monkeypatch):
         assert eng.extract(vol).tobytes() == oracle.extract(vol)["features"].tobytes()
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("double_mode,nranks,shape", [(0, 2, (64, 56, 230)), (0, 3, (48, 52, 330)), (1, 2, (40, 36, 120))])
+def test_slab_decomposition_bit_exact(pkg, engine, double_mode, nranks, shape):
+    """z-slab mode (emulated ranks on one GPU) against the whole-volume engine: identical rows, same order."""
+    import importlib
+    d = importlib.import_module("3d_sift_cuda_b200.dist")
+    vol = pkg.phantom.blob_phantom(shape, 17, 160)
+    whole = engine.extract(vol, pkg.Params(double_mode=double_mode))
+    Z0 = shape[2] * (2 if double_mode == 1 else 1)
+    K, bounds = d.slab_plan(Z0, nranks)
+    assert K >= 1, "test volume too thin to exercise slab mode"
+    slab = d.extract_slab(engine, vol, double_mode=double_mode, emulate_ranks=nranks)
+    assert len(whole) > 50
+    assert len(slab) == len(whole)
+    assert slab.tobytes() == whole.tobytes()
+
+
+def test_octave_run_from_level0_matches_whole(pkg, engine):
+    """input_is_g0 + octave_base: running octaves >= 1 from the engine's own level 0 reproduces their rows."""
+    import torch
+    vol = pkg.phantom.blob_phantom((96, 88, 80), 23, 120)
+    whole = engine.extract(vol)
+    kps = engine.keypoints()
+    rk = engine.row_keypoints()
+    g0 = torch.from_numpy(engine.level(1, 0)).cuda()
+    Z, Y, X = g0.shape
+    ready()
+    engine.extract_device(g0, (X, Y, Z), pkg.Params(input_is_g0=True, octave_base=1))
+    tail = engine.fetch_features()
+    want = whole[kps["octave"][rk] >= 1]
+    assert len(want) > 0 and tail.tobytes() == want.tobytes()
