@@ -18,6 +18,7 @@
 #include "s3d_voxel.cuh"
 #include "s3d_blur_fused.cuh"
 #include "s3d_keypoint.cuh"
+#include "s3d_small_octaves.cuh"
 
 using namespace s3d;
 
@@ -173,6 +174,10 @@ struct s3d_ctx {
     cudaStream_t cur = nullptr;  // stream the stage launchers enqueue on (main stream or an octave branch)
     bool fused = false;          // S3D_FUSED=1: one-kernel TMA blur level (12 B/voxel but ~2x the instructions of the
                                  // three-pass path at MNI size, where the volume sits in L2; see profiles/README.md)
+    long long fused_small_voxels = 0;   // S3D_FUSED_SMALL: volumes up to this many voxels use the one-kernel level
+    bool small_kernel = false;   // S3D_SMALL=1: octaves of a few thousand voxels in one cluster kernel.  Measured no faster than
+                                 // the per-level launches (each pass is an L2 round trip + a cluster barrier either way), so off.
+    bool xy_fused = true;        // x and y passes in one TMA-tiled kernel (S3D_XY=0: separate passes)
     int fused_ctas = 0;          // S3D_FUSED_CTAS: CTAs the fused blur aims for (0 = 2 per SM)
     bool timing = false;         // S3D_STAGE_TIMING=1: no graph, events at stage boundaries of the main stream
     std::vector<std::pair<std::string, cudaEvent_t>> marks;
@@ -239,13 +244,18 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
     CK(cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DescribeSmem)));
     CK(cudaMallocHost((void **)&ctx->h_counts, 4 * sizeof(int)));
     ctx->cur = ctx->stream;
+    // The branches of the smaller octaves and the detection/refinement branches are chains of short,
+    // latency-bound kernels: give them priority over octave 0's long blur kernels so they are not queued
+    // behind them (stream priorities are kept by the captured graph nodes).
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     for (int o = 1; o < kMaxOct; o++) {
-        CK(cudaStreamCreateWithFlags(&ctx->side[o], cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithPriority(&ctx->side[o], cudaStreamNonBlocking, prio_hi));
         CK(cudaEventCreateWithFlags(&ctx->ev_done[o], cudaEventDisableTiming));
     }
     for (int o = 0; o < kMaxOct; o++) {
         CK(cudaEventCreateWithFlags(&ctx->ev_fork[o], cudaEventDisableTiming));
-        CK(cudaStreamCreateWithFlags(&ctx->det[o], cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithPriority(&ctx->det[o], cudaStreamNonBlocking, prio_hi));
         if (!ctx->ev_done[o]) CK(cudaEventCreateWithFlags(&ctx->ev_done[o], cudaEventDisableTiming));
         for (int k = 0; k < 4; k++) CK(cudaEventCreateWithFlags(&ctx->ev_lvl[o][k], cudaEventDisableTiming));
     }
@@ -253,6 +263,12 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
     if (g && g[0] == '1') ctx->use_graph = false;
     const char *fu = getenv("S3D_FUSED");
     if (fu) ctx->fused = (fu[0] == '1');
+    const char *fs = getenv("S3D_FUSED_SMALL");
+    if (fs) ctx->fused_small_voxels = atoll(fs);
+    const char *sk = getenv("S3D_SMALL");
+    if (sk) ctx->small_kernel = (sk[0] != '0');
+    const char *xy = getenv("S3D_XY");
+    if (xy) ctx->xy_fused = (xy[0] != '0');
     const char *fc = getenv("S3D_FUSED_CTAS");
     ctx->fused_ctas = fc ? atoi(fc) : 0;
     const char *tm = getenv("S3D_STAGE_TIMING");
@@ -345,17 +361,22 @@ static void launch_blur_fast(s3d_ctx *ctx, const float *in, float *tmp, float *o
     memset(&t, 0, sizeof(t));
     for (int j = 0; j < 2 * R + 1; j++) t.w[j] = taps[j];
     long long plane = (long long)pitch * Y;
-    long long n_chunks = plane * Z / 8;
-    // x: in -> out
-    blur_x_kernel<R><<<(unsigned)((n_chunks + 255) / 256), 256, 0, ctx->cur>>>(in, out, pitch, X, n_chunks, t);
-    // y: out -> tmp
     int target = ctx->march_target > 0 ? ctx->march_target : ctx->sm_count * 1024;
-    {
+    // x and y: one TMA-tiled kernel (in -> tmp); fall back to the two separate passes if the driver
+    // cannot encode a tensor map (or S3D_XY=0)
+    CUtensorMap map;
+    if (ctx->xy_fused && Z <= 65535 && make_volume_map_xy(&map, in, Y, Z, pitch, R)) {
+        launch_blur_xy<R>(ctx->cur, map, tmp, X, Y, Z, pitch, taps);
+        ctx->launches += 1;
+    } else {
+        long long n_chunks = plane * Z / 8;
+        blur_x_kernel<R><<<(unsigned)((n_chunks + 255) / 256), 256, 0, ctx->cur>>>(in, out, pitch, X, n_chunks, t);
         long long cols = (long long)pitch * Z;
         int seg_len, n_seg;
         march_segments(target, cols, Y, seg_len, n_seg);
         dim3 grid((unsigned)((cols + 127) / 128), (unsigned)n_seg);
         blur_march_kernel<R, false><<<grid, 128, 0, ctx->cur>>>(out, tmp, nullptr, nullptr, cols, pitch, plane, pitch, Y, seg_len, t);
+        ctx->launches += 2;
     }
     // z: tmp -> out (+ DoG)
     {
@@ -365,8 +386,8 @@ static void launch_blur_fast(s3d_ctx *ctx, const float *in, float *tmp, float *o
         dim3 grid((unsigned)((cols + 127) / 128), (unsigned)n_seg);
         if (dog) blur_march_kernel<R, true><<<grid, 128, 0, ctx->cur>>>(tmp, out, in, dog, cols, plane, 0, plane, Z, seg_len, t);
         else blur_march_kernel<R, false><<<grid, 128, 0, ctx->cur>>>(tmp, out, nullptr, nullptr, cols, plane, 0, plane, Z, seg_len, t);
+        ctx->launches += 1;
     }
-    ctx->launches += 3;
 }
 
 static void launch_blur_generic(s3d_ctx *ctx, const float *in, float *tmp, float *out, int X, int Y, int Z, int pitch,
@@ -400,7 +421,10 @@ static s3d_status blur3d(s3d_ctx *ctx, const float *in, float *tmp, float *out, 
     if (in == out || in == tmp || tmp == out) return fail(ctx, S3D_ERR_INVALID, "s3d_blur3d: in/tmp/out must be distinct");
     int R = ntaps / 2;
     bool fast = fast_layout(in, tmp, out, pitch) && (!dog || ((uintptr_t)dog % 32) == 0) && R >= 1 && R <= kMaxFastR;
-    if (fast && ctx->fused && (!dog || dog != tmp)) {
+    // one-kernel level: always when asked for (S3D_FUSED=1), and for small octaves, whose cost is launch
+    // latency on a dependent chain rather than instructions
+    bool small = (long long)pitch * Y * Z <= ctx->fused_small_voxels;
+    if (fast && (ctx->fused || small)) {
         CUtensorMap map;
         if (make_volume_map(&map, in, Y, Z, pitch, R)) {
             cudaError_t e = cudaSuccess;
@@ -676,8 +700,8 @@ static s3d_status plan_build(s3d_ctx *ctx, int X, int Y, int Z, const s3d_params
         PA(&p->kp_stage, (size_t)p->n_lists * p->cand_cap);
         PA(&p->stage_flags, (size_t)p->n_lists * p->cand_cap);
     }
-    PA(&p->counts, p->n_lists + 8);
-    PA(&p->face_counts, kMaxOct * 3);
+    PA(&p->counts, p->n_lists + 8 + kMaxOct * 3);
+    p->face_counts = p->counts + p->n_lists + 8;
     for (int o = 0; o < n_oct; o++) {
         const OctaveDesc &od = p->pyr.oct[o];
         long long nv = (long long)od.pitch * od.Y * od.Z;
@@ -756,17 +780,13 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     int *kp_count = p->counts + p->n_lists, *n_features = kp_count + 1, *err = kp_count + 2;
     ctx->cur = st;
     mark(ctx, "start");
-    CK(cudaMemsetAsync(p->counts, 0, sizeof(int) * (p->n_lists + 8), st));
+    zero_ints_kernel<<<1, 256, 0, st>>>(p->counts, p->n_lists + 8 + kMaxOct * 3);
+    ctx->launches++;
 
     // pre-step: -2+ / -2- / plain copy into the pitched pyramid input (or straight into level 0)
+    // (the plain / level-0 input was already laid out in its pitched buffer by stage_input())
     if (p->input_is_g0) {
         if (p->n_oct == 0) { ctx->has_result = true; return S3D_OK; }
-        Vol &g0 = p->g[0];
-        long long rows = (long long)p->Y * p->Z;
-        dim3 grid((g0.pitch + 255) / 256, (unsigned)(rows < 8192 ? rows : 8192));
-        pad_rows_kernel<<<grid, 256, 0, st>>>(p->stage.p, p->X, rows, g0.p, g0.pitch);
-        ctx->launches++;
-        mark(ctx, "level 0 copy");
     } else {
         if (p->double_mode == 1) {
             s3d_status s = resize_launch(ctx, 2, p->stage.p, p->X, p->Y, p->Z, p->X, p->img0.p, p->img0.pitch);
@@ -774,11 +794,6 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
         } else if (p->double_mode == -1) {
             s3d_status s = resize_launch(ctx, 1, p->stage.p, p->X, p->Y, p->Z, p->X, p->img0.p, p->img0.pitch);
             if (s != S3D_OK) return s;
-        } else {
-            long long rows = (long long)p->Y * p->Z;
-            dim3 grid((p->img0.pitch + 255) / 256, (unsigned)(rows < 8192 ? rows : 8192));
-            pad_rows_kernel<<<grid, 256, 0, st>>>(p->stage.p, p->X, rows, p->img0.p, p->img0.pitch);
-            ctx->launches++;
         }
         if (p->n_oct == 0) {
             ctx->has_result = true;
@@ -794,8 +809,13 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     // Octave o+1 only needs level 3 of octave o, so every octave runs on its own branch (stream / graph
     // branch): the tail of an octave overlaps the whole chain of smaller octaves, which is launch-latency bound.
     ListDesc L{ p->n_lists, p->cand_cap, p->cand_raw, p->counts };
-    CK(cudaMemsetAsync(p->face_counts, 0, sizeof(int) * kMaxOct * 3, st));
-    for (int o = 0; o < p->n_oct; o++) {
+    // octaves [o_small, n_oct) are small enough for the single cluster kernel (never octave 0, never in slab mode)
+    int o_small = p->n_oct;
+    if (ctx->small_kernel && !p->slab) {
+        while (o_small > 1 && (long long)p->pyr.oct[o_small - 1].pitch * p->pyr.oct[o_small - 1].Y * p->pyr.oct[o_small - 1].Z <= kSmallMaxVoxels) o_small--;
+        for (int j = 0; j < 5; j++) if (p->n_lvl_taps[j] > 2 * kMaxFastR + 1) o_small = p->n_oct;
+    }
+    for (int o = 0; o < o_small; o++) {
         const OctaveDesc &od = p->pyr.oct[o];
         cudaStream_t so = (o == 0) ? st : ctx->side[o];
         ctx->cur = so;
@@ -809,6 +829,23 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
                 s = resize_launch(ctx, 0, b.p, od.X, od.Y, od.Z, od.pitch, p->g[(o + 1) * 6].p, nx.pitch);
                 if (s != S3D_OK) { ctx->cur = st; return s; }
                 CK(cudaEventRecord(ctx->ev_fork[o], so));
+                if (o + 1 == o_small) {
+                    // all remaining octaves: one cluster kernel (levels, DoGs, subsamples, detection), then one
+                    // refinement launch over their candidate lists
+                    cudaStream_t ss = ctx->side[o_small];
+                    CK(cudaStreamWaitEvent(ss, ctx->ev_fork[o], 0));
+                    SmallOctArgs sa;
+                    memset(&sa, 0, sizeof(sa));
+                    sa.o_first = o_small; sa.n_oct = p->n_oct;
+                    for (int q = 0; q < 5; q++) { sa.n_taps[q] = p->n_lvl_taps[q]; for (int t = 0; t < p->n_lvl_taps[q]; t++) sa.taps[q][t] = p->lvl_taps[q][t]; }
+                    for (int q = 0; q < p->n_oct; q++) sa.tmp[q] = p->oct_tmp[q];
+                    sa.cand_raw = p->cand_raw; sa.counts = p->counts; sa.cand_cap = p->cand_cap;
+                    small_octaves_kernel<<<kSmallClusterCtas, kSmallThreads, 0, ss>>>(p->pyr, sa);
+                    int nl = (p->n_oct - o_small) * 6;
+                    cand_refine_kernel<<<dim3(nl, 2), 256, 0, ss>>>(p->pyr, L, o_small * 6, p->kp_stage, p->stage_flags, err);
+                    ctx->launches += 2;
+                    CK(cudaEventRecord(ctx->ev_done[o_small], ss));
+                }
             }
             if (o == 0) { char nm[32]; snprintf(nm, sizeof(nm), "oct0 level %d", j); mark(ctx, nm); }
             if (j >= 2) {
@@ -840,7 +877,8 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
         }
     }
     ctx->cur = st;
-    for (int o = 0; o < p->n_oct; o++) CK(cudaStreamWaitEvent(st, ctx->ev_done[o], 0));
+    for (int o = 0; o < o_small; o++) CK(cudaStreamWaitEvent(st, ctx->ev_done[o], 0));
+    if (o_small < p->n_oct) CK(cudaStreamWaitEvent(st, ctx->ev_done[o_small], 0));
     mark(ctx, "join (detect+refine tails)");
     compact_kernel<<<1, 1024, 0, st>>>(L, p->kp_stage, p->stage_flags, p->kps, kp_count, p->kp_cap, err);
     mark(ctx, "compact");
@@ -920,6 +958,29 @@ static s3d_status run_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     return S3D_OK;
 }
 
+// Bring the caller's dense volume into the plan: straight into the pitched pyramid input (or level 0)
+// with a strided copy when no resize pre-step is needed, else into the dense staging buffer.
+static s3d_status stage_input(s3d_ctx *ctx, const float *src, bool from_host)
+{
+    Plan *p = ctx->plan;
+    size_t row = sizeof(float) * (size_t)p->X, rows = (size_t)p->Y * p->Z;
+    if (p->double_mode != 0) {
+        CK(cudaMemcpyAsync(p->stage.p, src, row * rows, from_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+        return S3D_OK;
+    }
+    Vol &dst = p->input_is_g0 ? (p->n_oct > 0 ? p->g[0] : p->img0) : p->img0;
+    if (from_host) {   // one contiguous PCIe transfer, then the re-pitch on the device
+        CK(cudaMemcpyAsync(p->stage.p, src, row * rows, cudaMemcpyHostToDevice, ctx->stream));
+        src = p->stage.p;
+    }
+    // dense -> pitched in one pass straight from the caller's buffer (outside the graph: the source
+    // pointer changes from call to call)
+    dim3 grid((dst.pitch + 255) / 256, (unsigned)(rows < 8192 ? rows : 8192));
+    pad_rows_kernel<<<grid, 256, 0, ctx->stream>>>(src, p->X, (long long)rows, dst.p, dst.pitch);
+    CK(cudaGetLastError());
+    return S3D_OK;
+}
+
 extern "C" s3d_status s3d_extract_device(s3d_ctx *ctx, const float *d_volume, int X, int Y, int Z, const s3d_params *prm)
 {
     s3d_status s = check_params(ctx, d_volume, X, Y, Z, prm);
@@ -927,7 +988,8 @@ extern "C" s3d_status s3d_extract_device(s3d_ctx *ctx, const float *d_volume, in
     CK(cudaSetDevice(ctx->device));
     s = plan_build(ctx, X, Y, Z, prm);
     if (s != S3D_OK) return s;
-    CK(cudaMemcpyAsync(ctx->plan->stage.p, d_volume, sizeof(float) * (size_t)X * Y * Z, cudaMemcpyDeviceToDevice, ctx->stream));
+    s = stage_input(ctx, d_volume, false);
+    if (s != S3D_OK) return s;
     return run_pipeline(ctx, prm);
 }
 
@@ -938,7 +1000,8 @@ extern "C" s3d_status s3d_extract_host_async(s3d_ctx *ctx, const float *h_volume
     CK(cudaSetDevice(ctx->device));
     s = plan_build(ctx, X, Y, Z, prm);
     if (s != S3D_OK) return s;
-    CK(cudaMemcpyAsync(ctx->plan->stage.p, h_volume, sizeof(float) * (size_t)X * Y * Z, cudaMemcpyHostToDevice, ctx->stream));
+    s = stage_input(ctx, h_volume, true);
+    if (s != S3D_OK) return s;
     return run_pipeline(ctx, prm);
 }
 

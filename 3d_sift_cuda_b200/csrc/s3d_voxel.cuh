@@ -193,6 +193,13 @@ __global__ void blur_march_generic_kernel(const float *__restrict__ in, float *_
     }
 }
 
+// counters are cleared by a kernel, not a memset node: inside a CUDA graph a memset node costs a hop to
+// the copy engine (~60-80 us of idle time measured before the next kernel node)
+__global__ void zero_ints_kernel(int *p, int n)
+{
+    for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = 0;
+}
+
 // out = a + (-1)*b   (fioMultSum, reference FeatureIO.cpp:1950-1987)
 __global__ void dog_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, long long n)
 {
