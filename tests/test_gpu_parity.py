@@ -223,3 +223,14 @@ def test_octave_run_from_level0_matches_whole(pkg, engine):
     tail = engine.fetch_features()
     want = whole[kps["octave"][rk] >= 1]
     assert len(want) > 0 and tail.tobytes() == want.tobytes()
+
+
+def test_small_octaves_cluster_kernel_bit_exact(pkg, oracle, monkeypatch):
+    """The optional one-kernel path for the small octaves (S3D_SMALL=1) gives the same rows."""
+    monkeypatch.setenv("S3D_SMALL", "1")
+    eng = pkg.Engine(0)
+    try:
+        for vol in (pkg.phantom.blob_phantom((96, 88, 80), 23, 120), pkg.phantom.brain_phantom((91, 109, 91), 1, 100)):
+            assert eng.extract(vol).tobytes() == oracle.extract(vol)["features"].tobytes()
+    finally:
+        eng.close()
