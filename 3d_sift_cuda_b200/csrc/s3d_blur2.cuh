@@ -1,0 +1,357 @@
+// s3d_blur2.cuh -- second-generation blur level for sm_100a (default path): two kernels per level,
+//   blur_xy2_kernel : x pass + y pass on a TMA-staged (x,y) tile of one z plane           (in  -> tmp)
+//   blur_z2_kernel  : z pass as a register march over column pairs, DoG fused              (tmp -> out, dog)
+// Both are bounded by FP32 issue (bit parity forbids FMA: every tap is one FMUL and one FADD, see
+// s3d_voxel.cuh), so the design goal is the fewest instructions per voxel:
+//   * symmetric taps: w[j] == w[2R-j] bit for bit (Gaussian taps are generated that way, the host checks
+//     it), so the product w[j]*v feeds two outputs -- R+1 multiplies per input instead of 2R+1.  The sums
+//     still receive their taps left to right, one rounding per product and per sum, exactly like
+//     filter_1d of the reference (GaussBlur3D.cpp:43-61);
+//   * "static scatter" segments: a work item is K consecutive outputs along the blur axis computed from a
+//     register window of K+2R inputs with fully unrolled code -- no loop overhead, no predicates, products
+//     shared inside the segment, 128-/64-bit shared memory accesses only;
+//   * the z march keeps the 2R+1 partial sums of a column pair in registers (float2, 64-bit global
+//     accesses), prefetches inputs a few planes ahead, peels the warm-up round (outputs in front of the
+//     segment do not exist, their taps are never issued) and runs interior rounds without predicates.
+// Shared-memory rows are padded so that 8 lanes reading 16 bytes from 8 consecutive rows hit 8 different
+// bank groups (row pitch / 4 odd).
+#pragma once
+#include "s3d_blur_fused.cuh"
+
+namespace s3d {
+
+__device__ __forceinline__ float mulw(float w, float v) { return w * v; }
+__device__ __forceinline__ float2 mulw(float w, float2 v) { return make_float2(w * v.x, w * v.y); }
+__device__ __forceinline__ float addv(float a, float b) { return a + b; }
+__device__ __forceinline__ float2 addv(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+
+// K outputs from a window of K+2R inputs (win[c + j] is tap j of output c).  Inputs are visited in
+// increasing order, so every output accumulates its taps j = 0..2R in order.
+template <int R, int K, typename F>
+__device__ __forceinline__ void conv_segment(const F *win, F *acc, const TapsSmall &taps)
+{
+#pragma unroll
+    for (int m = 0; m < K + 2 * R; m++) {
+        F p[R + 1];
+#pragma unroll
+        for (int k = 0; k <= R; k++) p[k] = mulw(taps.w[k], win[m]);     // unused products are dead code
+#pragma unroll
+        for (int c = 0; c < K; c++) {
+            const int j = m - c;
+            if (j == 0) acc[c] = p[0];
+            else if (j > 0 && j <= 2 * R) acc[c] = addv(acc[c], p[j <= R ? j : 2 * R - j]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// x + y passes on one tile.  Tile size (TX x TY) is chosen by the host per volume shape.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kKX = 16, kKY = 16, kXY2Threads = 256;
+
+struct XY2Tile {
+    int TX, TY;          // outputs per tile: TX % 32 == 0, TY % kKY == 0
+    int W_in, W_xb;      // shared-memory row pitches (floats), pitch/4 odd
+    int rows, rows8;     // TY + 2R, rounded up to 8
+    unsigned tile_bytes; // bytes one TMA box brings in
+    size_t smem;
+};
+
+template <int R>
+__global__ void __launch_bounds__(kXY2Threads, 2)
+blur_xy2_kernel(const __grid_constant__ CUtensorMap in_map, float *__restrict__ out, int X, int Y, int pitch,
+                const __grid_constant__ XY2Tile tile, const __grid_constant__ TapsSmall taps)
+{
+    constexpr int RP = (R + 3) & ~3;
+    extern __shared__ __align__(128) float xy2_smem[];          // TMA destination: 128-byte aligned
+    float *IN = xy2_smem;                                        // [rows8][W_in]
+    float *XB = IN + tile.rows8 * tile.W_in;                     // [rows8][W_xb]
+    uint64_t *full = reinterpret_cast<uint64_t *>(XB + tile.rows8 * tile.W_xb);
+    const int t = threadIdx.x;
+    const int x0 = blockIdx.x * tile.TX, y0 = blockIdx.y * tile.TY, z = blockIdx.z;
+    if (t == 0) {
+        mbar_init(full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(full, tile.tile_bytes);
+        tma_load_3d(IN, &in_map, x0 - RP, y0 - R, z, full);
+    }
+    __syncthreads();
+    mbar_wait(full, 0);
+
+    // ---- x pass: item = (group of 8 rows, segment of kKX outputs); lane & 7 = row inside the group
+    {
+        const int n_xseg = tile.TX / kKX;
+        const int n_items = (tile.rows8 >> 3) * n_xseg;
+        for (int it = t >> 3; it < n_items; it += kXY2Threads / 8) {
+            const int rg = it / n_xseg, xs = it - rg * n_xseg;
+            const int row = rg * 8 + (t & 7);
+            const float *src = IN + row * tile.W_in + xs * kKX;
+            float win[kKX + 2 * RP];
+#pragma unroll
+            for (int q = 0; q < (kKX + 2 * RP) / 4; q++) {
+                float4 u = *reinterpret_cast<const float4 *>(src + 4 * q);
+                win[4 * q] = u.x; win[4 * q + 1] = u.y; win[4 * q + 2] = u.z; win[4 * q + 3] = u.w;
+            }
+            float acc[kKX];
+            conv_segment<R, kKX, float>(win + (RP - R), acc, taps);
+            const int xg = x0 + xs * kKX;
+            if (xg + kKX > X) {       // padding columns (x >= X) stay zero in every pass
+#pragma unroll
+                for (int k = 0; k < kKX; k++) if (xg + k >= X) acc[k] = 0.0f;
+            }
+            float *dst = XB + row * tile.W_xb + xs * kKX;
+#pragma unroll
+            for (int q = 0; q < kKX / 4; q++)
+                *reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        }
+    }
+    __syncthreads();
+
+    // ---- y pass: item = (column pair, segment of kKY outputs); consecutive lanes = consecutive pairs
+    {
+        const int n_pairs = tile.TX >> 1;
+        const int n_items = n_pairs * (tile.TY / kKY);
+        for (int it = t; it < n_items; it += kXY2Threads) {
+            const int ys = it / n_pairs, cp = it - ys * n_pairs;
+            const float *col = XB + (ys * kKY) * tile.W_xb + 2 * cp;
+            float2 win[kKY + 2 * R];
+#pragma unroll
+            for (int m = 0; m < kKY + 2 * R; m++) win[m] = *reinterpret_cast<const float2 *>(col + m * tile.W_xb);
+            float2 acc[kKY];
+            conv_segment<R, kKY, float2>(win, acc, taps);
+            const int gx = x0 + 2 * cp, gy = y0 + ys * kKY;
+            if (gx < pitch) {
+                float *dst = out + ((long long)z * Y + gy) * pitch + gx;
+                if (gy + kKY <= Y) {
+#pragma unroll
+                    for (int k = 0; k < kKY; k++) *reinterpret_cast<float2 *>(dst + (long long)k * pitch) = acc[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kKY; k++) if (gy + k < Y) *reinterpret_cast<float2 *>(dst + (long long)k * pitch) = acc[k];
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// z pass: register march over column pairs (see s3d_voxel.cuh blur_march_kernel for the scatter form).
+// ---------------------------------------------------------------------------------------------------
+// S (slot of the output started by this step) is a literal after the caller's loop is unrolled, so
+// every accumulator index below is static and acc[] stays in registers.
+template <int R, bool FIRST>
+__device__ __forceinline__ void z2_step(float2 (&acc)[2 * R + 1], const int S, const float2 v, const TapsSmall &taps)
+{
+    constexpr int T = 2 * R + 1;
+    float2 p[R + 1];
+#pragma unroll
+    for (int k = 0; k <= R; k++) p[k] = mulw(taps.w[k], v);
+    acc[S] = p[0];
+#pragma unroll
+    for (int j = 1; j <= 2 * R; j++)
+        if (!FIRST || j <= S) {      // warm-up round: output S - j of the segment does not exist for j > S
+            const int sl = (S - j + 2 * T) % T;
+            acc[sl] = addv(acc[sl], p[j <= R ? j : 2 * R - j]);
+        }
+}
+
+__device__ __forceinline__ float2 ldg2(const float *p) { return __ldg(reinterpret_cast<const float2 *>(p)); }
+
+template <int R, bool DOG, bool FIRST, bool FAST>
+__device__ __forceinline__ void z2_round(float2 (&acc)[2 * R + 1], float2 (&vin)[2 * R + 1], float2 (&pv)[2 * R + 1],
+                                         const int ub, const int n_in, const int i_base, const int len,
+                                         const float *&pin, const float *&ppv, float *&pout, float *&pdog,
+                                         const long long plane, const TapsSmall &taps)
+{
+    constexpr int T = 2 * R + 1;
+    constexpr int P = (T < 6) ? T - 1 : 6;      // prefetch distance in steps
+#pragma unroll
+    for (int S = 0; S < T; S++) {
+        const int u = ub + S;
+        if (!FAST && u >= n_in) break;          // uniform over the block
+        const float2 v = vin[S];
+        float2 pvv = make_float2(0.f, 0.f);
+        if (DOG) pvv = pv[S];
+        {   // prefetch the input (and the DoG minuend) of step u + P
+            const int up = u + P, sl = (S + P) % T;
+            if (FAST) {
+                vin[sl] = ldg2(pin);
+                if (DOG) pv[sl] = ldg2(ppv);
+            } else {
+                const int i = i_base + up;
+                vin[sl] = (i >= 0 && i < len && up < n_in) ? ldg2(pin) : make_float2(0.f, 0.f);
+                if (DOG) pv[sl] = (up >= 2 * R && up < n_in) ? ldg2(ppv) : make_float2(0.f, 0.f);
+            }
+            pin += plane;
+            if (DOG) ppv += plane;
+        }
+        z2_step<R, FIRST>(acc, S, v, taps);
+        if (!FIRST || S == 2 * R) {             // step u completes output u - 2R
+            if (FAST || u >= 2 * R) {
+                const float2 g = acc[(S + 1) % T];
+                *reinterpret_cast<float2 *>(pout) = g;
+                if (DOG) *reinterpret_cast<float2 *>(pdog) = make_float2(pvv.x - g.x, pvv.y - g.y);   // prev + (-1)*g, fioMultSum
+            }
+        }
+        pout += plane;
+        if (DOG) pdog += plane;
+    }
+}
+
+template <int R, bool DOG>
+__global__ void __launch_bounds__(128) blur_z2_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                      const float *__restrict__ prev, float *__restrict__ dog,
+                                                      int n_pairs, long long plane, int len, int seg_len,
+                                                      const __grid_constant__ TapsSmall taps)
+{
+    constexpr int T = 2 * R + 1;
+    constexpr int P = (T < 6) ? T - 1 : 6;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_pairs) return;
+    const int a0 = blockIdx.y * seg_len;
+    const int a1 = min(len, a0 + seg_len);
+    const int n_in = (a1 - a0) + 2 * R;          // input steps u = 0 .. n_in-1, input plane a0 - R + u
+    const int i_base = a0 - R;
+    float2 acc[T], vin[T], pv[T];
+#pragma unroll
+    for (int s = 0; s < T; s++) { acc[s] = make_float2(0.f, 0.f); vin[s] = make_float2(0.f, 0.f); pv[s] = make_float2(0.f, 0.f); }
+    const float *pin = in + 2 * (long long)q + (long long)i_base * plane;            // input of step 0
+    const float *ppv = prev + 2 * (long long)q + (long long)(a0 - 2 * R) * plane;     // minuend of the output completed at step 0
+    float *pout = out + 2 * (long long)q + (long long)(a0 - 2 * R) * plane;
+    float *pdog = dog + 2 * (long long)q + (long long)(a0 - 2 * R) * plane;
+    // prologue: inputs of steps 0 .. P-1
+#pragma unroll
+    for (int s = 0; s < P; s++) {
+        const int i = i_base + s;
+        vin[s] = (i >= 0 && i < len && s < n_in) ? ldg2(pin) : make_float2(0.f, 0.f);
+        if (DOG) pv[s] = (s >= 2 * R && s < n_in) ? ldg2(ppv) : make_float2(0.f, 0.f);
+        pin += plane;
+        if (DOG) ppv += plane;
+    }
+    z2_round<R, DOG, true, false>(acc, vin, pv, 0, n_in, i_base, len, pin, ppv, pout, pdog, plane, taps);
+    for (int ub = T; ub < n_in; ub += T) {
+        // interior round: every prefetch [ub+P, ub+P+T) is inside the volume and the segment, every store is valid
+        const bool fast = (i_base + ub + P >= 0) && (i_base + ub + P + T <= len) && (ub + P + T <= n_in) && (ub >= 2 * R);
+        if (fast) z2_round<R, DOG, false, true>(acc, vin, pv, ub, n_in, i_base, len, pin, ppv, pout, pdog, plane, taps);
+        else z2_round<R, DOG, false, false>(acc, vin, pv, ub, n_in, i_base, len, pin, ppv, pout, pdog, plane, taps);
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+static inline bool taps_symmetric(const float *taps, int n)
+{
+    for (int j = 0; j < n / 2; j++)
+        if (memcmp(&taps[j], &taps[n - 1 - j], sizeof(float)) != 0) return false;
+    return true;
+}
+
+// shared-memory pitch >= w with pitch % 4 == 0 and (pitch / 4) odd
+static inline int odd_pitch(int w) { int p = (w + 3) & ~3; if (((p >> 2) & 1) == 0) p += 4; return p; }
+
+static inline XY2Tile make_xy2_tile(int TX, int TY, int R)
+{
+    XY2Tile t;
+    int RP = (R + 3) & ~3;
+    t.TX = TX; t.TY = TY;
+    t.W_in = odd_pitch(TX + 2 * RP);
+    t.W_xb = odd_pitch(TX);
+    t.rows = TY + 2 * R;
+    t.rows8 = (t.rows + 7) & ~7;
+    t.tile_bytes = (unsigned)((size_t)t.rows * t.W_in * sizeof(float));
+    t.smem = sizeof(float) * ((size_t)t.rows8 * t.W_in + (size_t)t.rows8 * t.W_xb) + 128 + 16;
+    return t;
+}
+
+// Tile choice: minimise (rounds of CTAs per SM) x (work per CTA); work = x-pass rows + y-pass rows, both
+// TX wide.  Tiles are limited to 2 resident CTAs per SM (<= ~110 KB of shared memory each).
+static inline XY2Tile choose_xy2_tile(int pitch, int Y, int Z, int R, int sm_count)
+{
+    XY2Tile best = make_xy2_tile(32, kKY, R);
+    double best_cost = 1e300;
+    static int max_kb = -1;          // S3D_XY2_SMEM_KB: cap on the tile's shared memory (experiments)
+    if (max_kb < 0) { const char *e = getenv("S3D_XY2_SMEM_KB"); max_kb = e ? atoi(e) : 75; if (max_kb < 16 || max_kb > 112) max_kb = 75; }
+    for (int TX = 32; TX <= 128; TX += 32)
+        for (int TY = kKY; TY <= 128; TY += kKY) {
+            XY2Tile t = make_xy2_tile(TX, TY, R);
+            if (t.smem > (size_t)max_kb * 1024 || t.W_in > 256 || t.rows > 256) continue;
+            long long ctas = (long long)((pitch + TX - 1) / TX) * ((Y + TY - 1) / TY) * Z;
+            long long rounds = (ctas + sm_count - 1) / sm_count;
+            double work = (double)TX * (t.rows8 + TY) + 600.0;      // + fixed cost per CTA (TMA round trip, barriers)
+            double cost = (double)rounds * work;
+            if (cost < best_cost) { best_cost = cost; best = t; }
+        }
+    return best;
+}
+
+static bool make_volume_map_box(CUtensorMap *map, const float *vol, int Y, int Z, int pitch, int box_w, int box_h)
+{
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return false;
+    cuuint64_t gdim[3] = { (cuuint64_t)pitch, (cuuint64_t)Y, (cuuint64_t)Z };
+    cuuint64_t gstr[2] = { (cuuint64_t)pitch * 4, (cuuint64_t)pitch * Y * 4 };
+    cuuint32_t box[3] = { (cuuint32_t)box_w, (cuuint32_t)box_h, 1 };
+    cuuint32_t estr[3] = { 1, 1, 1 };
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)vol, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int R>
+static cudaError_t set_xy2_attr_r()
+{
+    return cudaFuncSetAttribute(blur_xy2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+}
+// opt-in to > 48 KB of dynamic shared memory for every radius (once per device, from s3d_ctx_create)
+static cudaError_t init_blur2_attrs()
+{
+    cudaError_t e;
+    if ((e = set_xy2_attr_r<1>()) != cudaSuccess) return e;
+    if ((e = set_xy2_attr_r<2>()) != cudaSuccess) return e;
+    if ((e = set_xy2_attr_r<3>()) != cudaSuccess) return e;
+    if ((e = set_xy2_attr_r<4>()) != cudaSuccess) return e;
+    if ((e = set_xy2_attr_r<5>()) != cudaSuccess) return e;
+    if ((e = set_xy2_attr_r<6>()) != cudaSuccess) return e;
+    if ((e = set_xy2_attr_r<7>()) != cudaSuccess) return e;
+    return set_xy2_attr_r<8>();
+}
+
+// x+y: in -> tmp.  Returns false (nothing launched) when the tensor map cannot be encoded.
+template <int R>
+static bool launch_blur_xy2(cudaStream_t st, const float *in, float *tmp, int X, int Y, int Z, int pitch, const float *taps,
+                            int sm_count, cudaError_t *err)
+{
+    XY2Tile tile = choose_xy2_tile(pitch, Y, Z, R, sm_count);
+    CUtensorMap map;
+    if (Z > 65535 || !make_volume_map_box(&map, in, Y, Z, pitch, tile.W_in, tile.rows)) return false;
+    TapsSmall t;
+    memset(&t, 0, sizeof(t));
+    for (int j = 0; j < 2 * R + 1; j++) t.w[j] = taps[j];
+    dim3 grid((pitch + tile.TX - 1) / tile.TX, (Y + tile.TY - 1) / tile.TY, Z);
+    blur_xy2_kernel<R><<<grid, kXY2Threads, tile.smem, st>>>(map, tmp, X, Y, pitch, tile, t);
+    *err = cudaGetLastError();
+    return true;
+}
+
+// z (+DoG): tmp -> out.  `target` = threads wanted in flight (segments along z are added to reach it).
+template <int R>
+static cudaError_t launch_blur_z2(cudaStream_t st, const float *tmp, float *out, const float *prev, float *dog,
+                                  int Y, int Z, int pitch, const float *taps, int target)
+{
+    TapsSmall t;
+    memset(&t, 0, sizeof(t));
+    for (int j = 0; j < 2 * R + 1; j++) t.w[j] = taps[j];
+    long long plane = (long long)pitch * Y;
+    int n_pairs = (int)(plane / 2);
+    int n_seg = (int)((target + n_pairs - 1) / n_pairs);
+    int max_seg = (Z + 31) / 32;            // segments re-read 2R planes of halo: keep them >= 32 planes
+    if (n_seg > max_seg) n_seg = max_seg;
+    if (n_seg < 1) n_seg = 1;
+    int seg_len = (Z + n_seg - 1) / n_seg;
+    n_seg = (Z + seg_len - 1) / seg_len;
+    dim3 grid((unsigned)((n_pairs + 127) / 128), (unsigned)n_seg);
+    if (dog) blur_z2_kernel<R, true><<<grid, 128, 0, st>>>(tmp, out, prev, dog, n_pairs, plane, Z, seg_len, t);
+    else blur_z2_kernel<R, false><<<grid, 128, 0, st>>>(tmp, out, tmp, out, n_pairs, plane, Z, seg_len, t);
+    return cudaGetLastError();
+}
+
+} // namespace s3d

@@ -17,6 +17,7 @@
 #include "../../include/s3d.h"
 #include "s3d_voxel.cuh"
 #include "s3d_blur_fused.cuh"
+#include "s3d_blur2.cuh"
 #include "s3d_keypoint.cuh"
 #include "s3d_small_octaves.cuh"
 
@@ -178,6 +179,7 @@ struct s3d_ctx {
     bool small_kernel = false;   // S3D_SMALL=1: octaves of a few thousand voxels in one cluster kernel.  Measured no faster than
                                  // the per-level launches (each pass is an L2 round trip + a cluster barrier either way), so off.
     bool xy_fused = true;        // x and y passes in one TMA-tiled kernel (S3D_XY=0: separate passes)
+    bool blur2 = true;           // second-generation level kernels (s3d_blur2.cuh); S3D_BLUR2=0: first generation
     int fused_ctas = 0;          // S3D_FUSED_CTAS: CTAs the fused blur aims for (0 = 2 per SM)
     bool timing = false;         // S3D_STAGE_TIMING=1: no graph, events at stage boundaries of the main stream
     std::vector<std::pair<std::string, cudaEvent_t>> marks;
@@ -269,6 +271,9 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
     if (sk) ctx->small_kernel = (sk[0] != '0');
     const char *xy = getenv("S3D_XY");
     if (xy) ctx->xy_fused = (xy[0] != '0');
+    const char *b2 = getenv("S3D_BLUR2");
+    if (b2) ctx->blur2 = (b2[0] != '0');
+    CK(init_blur2_attrs());
     const char *fc = getenv("S3D_FUSED_CTAS");
     ctx->fused_ctas = fc ? atoi(fc) : 0;
     const char *tm = getenv("S3D_STAGE_TIMING");
@@ -361,6 +366,15 @@ static void launch_blur_fast(s3d_ctx *ctx, const float *in, float *tmp, float *o
     memset(&t, 0, sizeof(t));
     for (int j = 0; j < 2 * R + 1; j++) t.w[j] = taps[j];
     long long plane = (long long)pitch * Y;
+    if (ctx->blur2 && taps_symmetric(taps, 2 * R + 1) && plane * Z < (1ll << 31)) {
+        cudaError_t e = cudaSuccess;
+        if (launch_blur_xy2<R>(ctx->cur, in, tmp, X, Y, Z, pitch, taps, ctx->sm_count, &e)) {
+            int target2 = ctx->march_target > 0 ? ctx->march_target : ctx->sm_count * 256;
+            launch_blur_z2<R>(ctx->cur, tmp, out, in, dog, Y, Z, pitch, taps, target2);
+            ctx->launches += 2;
+            return;
+        }
+    }
     int target = ctx->march_target > 0 ? ctx->march_target : ctx->sm_count * 1024;
     // x and y: one TMA-tiled kernel (in -> tmp); fall back to the two separate passes if the driver
     // cannot encode a tensor map (or S3D_XY=0)

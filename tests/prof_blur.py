@@ -12,6 +12,10 @@ tmp, out, dog = torch.empty_like(a), torch.empty_like(a), torch.empty_like(a)
 torch.cuda.synchronize()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 sigmas = [1.5199, 1.2263, 1.5450, 1.9466, 2.4525, 3.0900]
+if os.environ.get("PROF_SIGMAS"):
+    sigmas = [float(v) for v in os.environ["PROF_SIGMAS"].split(",")]
+REPS = int(os.environ.get("PROF_REPS", "10"))
+WARM = int(os.environ.get("PROF_WARM", "3"))
 targets = [int(t) for t in sys.argv[1:]] or [0]
 N0 = X * Y * Z
 for tgt in targets:
@@ -21,11 +25,11 @@ for tgt in targets:
     row = []
     for s in sigmas:
         taps = pkg.gaussian_taps(s)
-        for _ in range(3):
+        for _ in range(WARM):
             e.blur3d(a, tmp, out, X, taps, dog)
         e.sync()
         ms = 0.0
-        reps = 10
+        reps = REPS
         with torch.cuda.stream(st):
             for _ in range(reps):
                 flush.zero_()
