@@ -34,6 +34,8 @@ EXPORTS = [
     "s3d_fetch_features", "s3d_fetch_counts", "s3d_result_device", "s3d_free", "s3d_num_octaves",
     "s3d_get_level", "s3d_get_keypoints", "s3d_get_patches", "s3d_last_launch_count", "s3d_write_features_text",
     "s3d_copy_level_device", "s3d_get_row_keypoints",
+    "s3d_batch_create", "s3d_batch_destroy", "s3d_batch_last_error", "s3d_batch_extract", "s3d_batch_extract_device",
+    "s3d_batch_launches_per_volume", "s3d_host_alloc", "s3d_host_free",
 ]
 
 
@@ -113,6 +115,18 @@ def load_library():
     L.s3d_copy_level_device.argtypes = [vp, i, i, i, i, i, vp]
     L.s3d_get_row_keypoints.argtypes = [vp, C.POINTER(vp), C.POINTER(i)]
     L.s3d_write_features_text.argtypes = [C.c_char_p, vp, i, f, i, C.POINTER(C.c_char_p)]
+    L.s3d_batch_create.argtypes = [i, i, C.POINTER(vp)]
+    L.s3d_batch_destroy.argtypes = [vp]
+    L.s3d_batch_destroy.restype = None
+    L.s3d_batch_last_error.argtypes = [vp]
+    L.s3d_batch_last_error.restype = C.c_char_p
+    L.s3d_batch_extract.argtypes = [vp, C.POINTER(vp), i, i, i, i, vp, C.POINTER(vp), C.POINTER(i)]
+    L.s3d_batch_extract_device.argtypes = [vp, C.POINTER(vp), i, i, i, i, vp, C.POINTER(i), C.POINTER(i)]
+    L.s3d_batch_launches_per_volume.argtypes = [vp]
+    L.s3d_host_alloc.argtypes = [C.c_size_t]
+    L.s3d_host_alloc.restype = vp
+    L.s3d_host_free.argtypes = [vp]
+    L.s3d_host_free.restype = None
     _LIB = L
     return L
 
@@ -309,6 +323,68 @@ class Engine:
         a = mins.cpu().numpy().view(CAND_DTYPE)[:n[0]].copy()
         b = maxs.cpu().numpy().view(CAND_DTYPE)[:n[1]].copy()
         return a, b
+
+
+class Batch:
+    """Several extraction contexts on one GPU fed round-robin (s3d_batch, BASELINE.json config 4 per GPU)."""
+
+    def __init__(self, device=0, n_contexts=4):
+        self.L = load_library()
+        self.b = C.c_void_p()
+        st = self.L.s3d_batch_create(device, n_contexts, C.byref(self.b))
+        if st != 0:
+            raise S3DError("s3d_batch_create(%d, %d): %s" % (device, n_contexts, _STATUS.get(st, st)))
+        self.n_contexts = n_contexts
+
+    def close(self):
+        if getattr(self, "b", None):
+            self.L.s3d_batch_destroy(self.b)
+            self.b = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st, what):
+        if st != 0:
+            raise S3DError("%s: %s (%s)" % (what, _STATUS.get(st, st), self.L.s3d_batch_last_error(self.b).decode()))
+
+    @staticmethod
+    def _ptrs(vols):
+        arr = (C.c_void_p * len(vols))()
+        for k, v in enumerate(vols):
+            arr[k] = v.data_ptr() if hasattr(v, "data_ptr") else v.ctypes.data
+        return arr
+
+    def extract(self, h_volumes, params=None):
+        """List of host volumes ((Z, Y, X) float32 numpy arrays or pinned torch tensors of one shape) ->
+        list of feature-row arrays, in input order."""
+        params = params or Params()
+        n = len(h_volumes)
+        if n == 0:
+            return []
+        Z, Y, X = h_volumes[0].shape
+        rows = (C.c_void_p * n)()
+        cnt = (C.c_int * n)()
+        self._ck(self.L.s3d_batch_extract(self.b, self._ptrs(h_volumes), n, X, Y, Z, C.byref(params.c), rows, cnt),
+                 "s3d_batch_extract")
+        return [_copy_out(C.c_void_p(rows[k]), cnt[k], FEATURE_DTYPE, self.L.s3d_free) for k in range(n)]
+
+    def extract_device(self, d_volumes, shape_xyz, params=None):
+        """List of dense device volumes -> (n_keypoints, n_rows) per volume; rows stay on the device."""
+        params = params or Params()
+        n = len(d_volumes)
+        X, Y, Z = shape_xyz
+        nk = (C.c_int * n)()
+        nr = (C.c_int * n)()
+        self._ck(self.L.s3d_batch_extract_device(self.b, self._ptrs(d_volumes), n, X, Y, Z, C.byref(params.c), nk, nr),
+                 "s3d_batch_extract_device")
+        return list(nk), list(nr)
+
+    def launches_per_volume(self):
+        return self.L.s3d_batch_launches_per_volume(self.b)
 
 
 def write_features_text(path, feats, shape_xyz, eig_thres=140.0, comments=None):

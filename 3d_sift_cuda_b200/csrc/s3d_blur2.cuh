@@ -22,8 +22,16 @@ namespace s3d {
 
 __device__ __forceinline__ float mulw(float w, float v) { return w * v; }
 __device__ __forceinline__ float2 mulw(float w, float2 v) { return make_float2(w * v.x, w * v.y); }
+__device__ __forceinline__ float4 mulw(float w, float4 v) { return make_float4(w * v.x, w * v.y, w * v.z, w * v.w); }
 __device__ __forceinline__ float addv(float a, float b) { return a + b; }
 __device__ __forceinline__ float2 addv(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float4 addv(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float2 subv(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float4 subv(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+template <typename VT> __device__ __forceinline__ VT zerov();
+template <> __device__ __forceinline__ float2 zerov<float2>() { return make_float2(0.f, 0.f); }
+template <> __device__ __forceinline__ float4 zerov<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+template <typename VT> __device__ __forceinline__ VT ldgv(const float *p) { return __ldg(reinterpret_cast<const VT *>(p)); }
 
 // K outputs from a window of K+2R inputs (win[c + j] is tap j of output c).  Inputs are visited in
 // increasing order, so every output accumulates its taps j = 0..2R in order.
@@ -57,80 +65,109 @@ struct XY2Tile {
     size_t smem;
 };
 
+// Persistent: a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (x fastest, then y, then z); the
+// staged input is double buffered, so the TMA load of the CTA's next tile is in flight while it computes
+// the current one (with one tile per CTA the TMA round trip was exposed: ncu showed the warps parked on
+// the mbarrier 3.4 cycles per issued instruction).
 template <int R>
 __global__ void __launch_bounds__(kXY2Threads, 2)
 blur_xy2_kernel(const __grid_constant__ CUtensorMap in_map, float *__restrict__ out, int X, int Y, int pitch,
-                const __grid_constant__ XY2Tile tile, const __grid_constant__ TapsSmall taps)
+                const __grid_constant__ XY2Tile tile, int n_tx, int n_ty, int n_tiles, const __grid_constant__ TapsSmall taps)
 {
     constexpr int RP = (R + 3) & ~3;
     extern __shared__ __align__(128) float xy2_smem[];          // TMA destination: 128-byte aligned
-    float *IN = xy2_smem;                                        // [rows8][W_in]
-    float *XB = IN + tile.rows8 * tile.W_in;                     // [rows8][W_xb]
-    uint64_t *full = reinterpret_cast<uint64_t *>(XB + tile.rows8 * tile.W_xb);
+    const int stage_floats = tile.rows8 * tile.W_in;
+    float *IN = xy2_smem;                                        // [2][rows8][W_in]
+    float *XB = IN + 2 * stage_floats;                           // [rows8][W_xb]
+    uint64_t *full = reinterpret_cast<uint64_t *>(XB + tile.rows8 * tile.W_xb);   // [2]
     const int t = threadIdx.x;
-    const int x0 = blockIdx.x * tile.TX, y0 = blockIdx.y * tile.TY, z = blockIdx.z;
+    const int stride = gridDim.x;
     if (t == 0) {
-        mbar_init(full, 1);
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(full, tile.tile_bytes);
-        tma_load_3d(IN, &in_map, x0 - RP, y0 - R, z, full);
-    }
-    __syncthreads();
-    mbar_wait(full, 0);
-
-    // ---- x pass: item = (group of 8 rows, segment of kKX outputs); lane & 7 = row inside the group
-    {
-        const int n_xseg = tile.TX / kKX;
-        const int n_items = (tile.rows8 >> 3) * n_xseg;
-        for (int it = t >> 3; it < n_items; it += kXY2Threads / 8) {
-            const int rg = it / n_xseg, xs = it - rg * n_xseg;
-            const int row = rg * 8 + (t & 7);
-            const float *src = IN + row * tile.W_in + xs * kKX;
-            float win[kKX + 2 * RP];
 #pragma unroll
-            for (int q = 0; q < (kKX + 2 * RP) / 4; q++) {
-                float4 u = *reinterpret_cast<const float4 *>(src + 4 * q);
-                win[4 * q] = u.x; win[4 * q + 1] = u.y; win[4 * q + 2] = u.z; win[4 * q + 3] = u.w;
+        for (int s = 0; s < 2; s++) {
+            const int id = blockIdx.x + s * stride;
+            if (id < n_tiles) {
+                const int tx = id % n_tx, ty = (id / n_tx) % n_ty, tz = id / (n_tx * n_ty);
+                mbar_expect_tx(&full[s], tile.tile_bytes);
+                tma_load_3d(IN + s * stage_floats, &in_map, tx * tile.TX - RP, ty * tile.TY - R, tz, &full[s]);
             }
-            float acc[kKX];
-            conv_segment<R, kKX, float>(win + (RP - R), acc, taps);
-            const int xg = x0 + xs * kKX;
-            if (xg + kKX > X) {       // padding columns (x >= X) stay zero in every pass
-#pragma unroll
-                for (int k = 0; k < kKX; k++) if (xg + k >= X) acc[k] = 0.0f;
-            }
-            float *dst = XB + row * tile.W_xb + xs * kKX;
-#pragma unroll
-            for (int q = 0; q < kKX / 4; q++)
-                *reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
         }
     }
     __syncthreads();
 
-    // ---- y pass: item = (column pair, segment of kKY outputs); consecutive lanes = consecutive pairs
-    {
-        const int n_pairs = tile.TX >> 1;
-        const int n_items = n_pairs * (tile.TY / kKY);
-        for (int it = t; it < n_items; it += kXY2Threads) {
-            const int ys = it / n_pairs, cp = it - ys * n_pairs;
-            const float *col = XB + (ys * kKY) * tile.W_xb + 2 * cp;
-            float2 win[kKY + 2 * R];
+    int k = 0;
+    for (int id = blockIdx.x; id < n_tiles; id += stride, k++) {
+        const int s = k & 1;
+        const float *in_t = IN + s * stage_floats;
+        const int x0 = (id % n_tx) * tile.TX, y0 = ((id / n_tx) % n_ty) * tile.TY, z = id / (n_tx * n_ty);
+        mbar_wait(&full[s], (k >> 1) & 1);
+
+        // ---- x pass: item = (group of 8 rows, segment of kKX outputs); lane & 7 = row inside the group
+        {
+            const int n_xseg = tile.TX / kKX;
+            const int n_items = (tile.rows8 >> 3) * n_xseg;
+            for (int it = t >> 3; it < n_items; it += kXY2Threads / 8) {
+                const int rg = it / n_xseg, xs = it - rg * n_xseg;
+                const int row = rg * 8 + (t & 7);
+                const float *src = in_t + row * tile.W_in + xs * kKX;
+                float win[kKX + 2 * RP];
 #pragma unroll
-            for (int m = 0; m < kKY + 2 * R; m++) win[m] = *reinterpret_cast<const float2 *>(col + m * tile.W_xb);
-            float2 acc[kKY];
-            conv_segment<R, kKY, float2>(win, acc, taps);
-            const int gx = x0 + 2 * cp, gy = y0 + ys * kKY;
-            if (gx < pitch) {
-                float *dst = out + ((long long)z * Y + gy) * pitch + gx;
-                if (gy + kKY <= Y) {
+                for (int q = 0; q < (kKX + 2 * RP) / 4; q++) {
+                    float4 u = *reinterpret_cast<const float4 *>(src + 4 * q);
+                    win[4 * q] = u.x; win[4 * q + 1] = u.y; win[4 * q + 2] = u.z; win[4 * q + 3] = u.w;
+                }
+                float acc[kKX];
+                conv_segment<R, kKX, float>(win + (RP - R), acc, taps);
+                const int xg = x0 + xs * kKX;
+                if (xg + kKX > X) {       // padding columns (x >= X) stay zero in every pass
 #pragma unroll
-                    for (int k = 0; k < kKY; k++) *reinterpret_cast<float2 *>(dst + (long long)k * pitch) = acc[k];
-                } else {
+                    for (int q = 0; q < kKX; q++) if (xg + q >= X) acc[q] = 0.0f;
+                }
+                float *dst = XB + row * tile.W_xb + xs * kKX;
 #pragma unroll
-                    for (int k = 0; k < kKY; k++) if (gy + k < Y) *reinterpret_cast<float2 *>(dst + (long long)k * pitch) = acc[k];
+                for (int q = 0; q < kKX / 4; q++)
+                    *reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            }
+        }
+        __syncthreads();      // XB complete, stage s free: refill it with the tile after next
+        if (t == 0) {
+            const int nid = id + 2 * stride;
+            if (nid < n_tiles) {
+                const int tx = nid % n_tx, ty = (nid / n_tx) % n_ty, tz = nid / (n_tx * n_ty);
+                mbar_expect_tx(&full[s], tile.tile_bytes);
+                tma_load_3d(IN + s * stage_floats, &in_map, tx * tile.TX - RP, ty * tile.TY - R, tz, &full[s]);
+            }
+        }
+
+        // ---- y pass: item = (column pair, segment of kKY outputs); consecutive lanes = consecutive pairs
+        {
+            const int n_pairs = tile.TX >> 1;
+            const int n_items = n_pairs * (tile.TY / kKY);
+            for (int it = t; it < n_items; it += kXY2Threads) {
+                const int ys = it / n_pairs, cp = it - ys * n_pairs;
+                const float *col = XB + (ys * kKY) * tile.W_xb + 2 * cp;
+                float2 win[kKY + 2 * R];
+#pragma unroll
+                for (int m = 0; m < kKY + 2 * R; m++) win[m] = *reinterpret_cast<const float2 *>(col + m * tile.W_xb);
+                float2 acc[kKY];
+                conv_segment<R, kKY, float2>(win, acc, taps);
+                const int gx = x0 + 2 * cp, gy = y0 + ys * kKY;
+                if (gx < pitch) {
+                    float *dst = out + ((long long)z * Y + gy) * pitch + gx;
+                    if (gy + kKY <= Y) {
+#pragma unroll
+                        for (int q = 0; q < kKY; q++) *reinterpret_cast<float2 *>(dst + (long long)q * pitch) = acc[q];
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < kKY; q++) if (gy + q < Y) *reinterpret_cast<float2 *>(dst + (long long)q * pitch) = acc[q];
+                    }
                 }
             }
         }
+        __syncthreads();      // XB free for the next tile's x pass
     }
 }
 
@@ -139,11 +176,11 @@ blur_xy2_kernel(const __grid_constant__ CUtensorMap in_map, float *__restrict__ 
 // ---------------------------------------------------------------------------------------------------
 // S (slot of the output started by this step) is a literal after the caller's loop is unrolled, so
 // every accumulator index below is static and acc[] stays in registers.
-template <int R, bool FIRST>
-__device__ __forceinline__ void z2_step(float2 (&acc)[2 * R + 1], const int S, const float2 v, const TapsSmall &taps)
+template <int R, bool FIRST, typename VT>
+__device__ __forceinline__ void z2_step(VT (&acc)[2 * R + 1], const int S, const VT v, const TapsSmall &taps)
 {
     constexpr int T = 2 * R + 1;
-    float2 p[R + 1];
+    VT p[R + 1];
 #pragma unroll
     for (int k = 0; k <= R; k++) p[k] = mulw(taps.w[k], v);
     acc[S] = p[0];
@@ -155,42 +192,42 @@ __device__ __forceinline__ void z2_step(float2 (&acc)[2 * R + 1], const int S, c
         }
 }
 
-__device__ __forceinline__ float2 ldg2(const float *p) { return __ldg(reinterpret_cast<const float2 *>(p)); }
+template <int R> struct Z2Cfg { static constexpr int T = 2 * R + 1; static constexpr int P = (T < 6) ? T - 1 : 6; };   // P: prefetch distance (steps)
 
-template <int R, bool DOG, bool FIRST, bool FAST>
-__device__ __forceinline__ void z2_round(float2 (&acc)[2 * R + 1], float2 (&vin)[2 * R + 1], float2 (&pv)[2 * R + 1],
+template <int R, bool DOG, bool FIRST, bool FAST, typename VT>
+__device__ __forceinline__ void z2_round(VT (&acc)[2 * R + 1], VT (&vin)[2 * R + 1], VT (&pv)[2 * R + 1],
                                          const int ub, const int n_in, const int i_base, const int len,
                                          const float *&pin, const float *&ppv, float *&pout, float *&pdog,
                                          const long long plane, const TapsSmall &taps)
 {
     constexpr int T = 2 * R + 1;
-    constexpr int P = (T < 6) ? T - 1 : 6;      // prefetch distance in steps
+    constexpr int P = Z2Cfg<R>::P;
 #pragma unroll
     for (int S = 0; S < T; S++) {
         const int u = ub + S;
         if (!FAST && u >= n_in) break;          // uniform over the block
-        const float2 v = vin[S];
-        float2 pvv = make_float2(0.f, 0.f);
+        const VT v = vin[S];
+        VT pvv = zerov<VT>();
         if (DOG) pvv = pv[S];
         {   // prefetch the input (and the DoG minuend) of step u + P
             const int up = u + P, sl = (S + P) % T;
             if (FAST) {
-                vin[sl] = ldg2(pin);
-                if (DOG) pv[sl] = ldg2(ppv);
+                vin[sl] = ldgv<VT>(pin);
+                if (DOG) pv[sl] = ldgv<VT>(ppv);
             } else {
                 const int i = i_base + up;
-                vin[sl] = (i >= 0 && i < len && up < n_in) ? ldg2(pin) : make_float2(0.f, 0.f);
-                if (DOG) pv[sl] = (up >= 2 * R && up < n_in) ? ldg2(ppv) : make_float2(0.f, 0.f);
+                vin[sl] = (i >= 0 && i < len && up < n_in) ? ldgv<VT>(pin) : zerov<VT>();
+                if (DOG) pv[sl] = (up >= 2 * R && up < n_in) ? ldgv<VT>(ppv) : zerov<VT>();
             }
             pin += plane;
             if (DOG) ppv += plane;
         }
-        z2_step<R, FIRST>(acc, S, v, taps);
+        z2_step<R, FIRST, VT>(acc, S, v, taps);
         if (!FIRST || S == 2 * R) {             // step u completes output u - 2R
             if (FAST || u >= 2 * R) {
-                const float2 g = acc[(S + 1) % T];
-                *reinterpret_cast<float2 *>(pout) = g;
-                if (DOG) *reinterpret_cast<float2 *>(pdog) = make_float2(pvv.x - g.x, pvv.y - g.y);   // prev + (-1)*g, fioMultSum
+                const VT g = acc[(S + 1) % T];
+                *reinterpret_cast<VT *>(pout) = g;
+                if (DOG) *reinterpret_cast<VT *>(pdog) = subv(pvv, g);   // prev + (-1)*g, fioMultSum
             }
         }
         pout += plane;
@@ -198,42 +235,44 @@ __device__ __forceinline__ void z2_round(float2 (&acc)[2 * R + 1], float2 (&vin)
     }
 }
 
-template <int R, bool DOG>
+// VT = float2 / float4: a thread owns 2 / 4 adjacent columns (64- / 128-bit global accesses)
+template <int R, bool DOG, typename VT>
 __global__ void __launch_bounds__(128) blur_z2_kernel(const float *__restrict__ in, float *__restrict__ out,
                                                       const float *__restrict__ prev, float *__restrict__ dog,
-                                                      int n_pairs, long long plane, int len, int seg_len,
+                                                      int n_vec, long long plane, int len, int seg_len,
                                                       const __grid_constant__ TapsSmall taps)
 {
     constexpr int T = 2 * R + 1;
-    constexpr int P = (T < 6) ? T - 1 : 6;
+    constexpr int P = Z2Cfg<R>::P;
+    constexpr int V = (int)(sizeof(VT) / sizeof(float));
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n_pairs) return;
+    if (q >= n_vec) return;
     const int a0 = blockIdx.y * seg_len;
     const int a1 = min(len, a0 + seg_len);
     const int n_in = (a1 - a0) + 2 * R;          // input steps u = 0 .. n_in-1, input plane a0 - R + u
     const int i_base = a0 - R;
-    float2 acc[T], vin[T], pv[T];
+    VT acc[T], vin[T], pv[T];
 #pragma unroll
-    for (int s = 0; s < T; s++) { acc[s] = make_float2(0.f, 0.f); vin[s] = make_float2(0.f, 0.f); pv[s] = make_float2(0.f, 0.f); }
-    const float *pin = in + 2 * (long long)q + (long long)i_base * plane;            // input of step 0
-    const float *ppv = prev + 2 * (long long)q + (long long)(a0 - 2 * R) * plane;     // minuend of the output completed at step 0
-    float *pout = out + 2 * (long long)q + (long long)(a0 - 2 * R) * plane;
-    float *pdog = dog + 2 * (long long)q + (long long)(a0 - 2 * R) * plane;
+    for (int s = 0; s < T; s++) { acc[s] = zerov<VT>(); vin[s] = zerov<VT>(); pv[s] = zerov<VT>(); }
+    const float *pin = in + V * (long long)q + (long long)i_base * plane;            // input of step 0
+    const float *ppv = prev + V * (long long)q + (long long)(a0 - 2 * R) * plane;     // minuend of the output completed at step 0
+    float *pout = out + V * (long long)q + (long long)(a0 - 2 * R) * plane;
+    float *pdog = dog + V * (long long)q + (long long)(a0 - 2 * R) * plane;
     // prologue: inputs of steps 0 .. P-1
 #pragma unroll
     for (int s = 0; s < P; s++) {
         const int i = i_base + s;
-        vin[s] = (i >= 0 && i < len && s < n_in) ? ldg2(pin) : make_float2(0.f, 0.f);
-        if (DOG) pv[s] = (s >= 2 * R && s < n_in) ? ldg2(ppv) : make_float2(0.f, 0.f);
+        vin[s] = (i >= 0 && i < len && s < n_in) ? ldgv<VT>(pin) : zerov<VT>();
+        if (DOG) pv[s] = (s >= 2 * R && s < n_in) ? ldgv<VT>(ppv) : zerov<VT>();
         pin += plane;
         if (DOG) ppv += plane;
     }
-    z2_round<R, DOG, true, false>(acc, vin, pv, 0, n_in, i_base, len, pin, ppv, pout, pdog, plane, taps);
+    z2_round<R, DOG, true, false, VT>(acc, vin, pv, 0, n_in, i_base, len, pin, ppv, pout, pdog, plane, taps);
     for (int ub = T; ub < n_in; ub += T) {
         // interior round: every prefetch [ub+P, ub+P+T) is inside the volume and the segment, every store is valid
         const bool fast = (i_base + ub + P >= 0) && (i_base + ub + P + T <= len) && (ub + P + T <= n_in) && (ub >= 2 * R);
-        if (fast) z2_round<R, DOG, false, true>(acc, vin, pv, ub, n_in, i_base, len, pin, ppv, pout, pdog, plane, taps);
-        else z2_round<R, DOG, false, false>(acc, vin, pv, ub, n_in, i_base, len, pin, ppv, pout, pdog, plane, taps);
+        if (fast) z2_round<R, DOG, false, true, VT>(acc, vin, pv, ub, n_in, i_base, len, pin, ppv, pout, pdog, plane, taps);
+        else z2_round<R, DOG, false, false, VT>(acc, vin, pv, ub, n_in, i_base, len, pin, ppv, pout, pdog, plane, taps);
     }
 }
 
@@ -258,7 +297,7 @@ static inline XY2Tile make_xy2_tile(int TX, int TY, int R)
     t.rows = TY + 2 * R;
     t.rows8 = (t.rows + 7) & ~7;
     t.tile_bytes = (unsigned)((size_t)t.rows * t.W_in * sizeof(float));
-    t.smem = sizeof(float) * ((size_t)t.rows8 * t.W_in + (size_t)t.rows8 * t.W_xb) + 128 + 16;
+    t.smem = sizeof(float) * (2 * (size_t)t.rows8 * t.W_in + (size_t)t.rows8 * t.W_xb) + 128 + 16;   // 2 input stages + x-pass buffer
     return t;
 }
 
@@ -266,17 +305,31 @@ static inline XY2Tile make_xy2_tile(int TX, int TY, int R)
 // TX wide.  Tiles are limited to 2 resident CTAs per SM (<= ~110 KB of shared memory each).
 static inline XY2Tile choose_xy2_tile(int pitch, int Y, int Z, int R, int sm_count)
 {
+    static int max_kb = -1, force_tx = 0, force_ty = 0;   // S3D_XY2_SMEM_KB / S3D_XY2_TX / S3D_XY2_TY (experiments)
+    if (max_kb < 0) {
+        const char *e = getenv("S3D_XY2_SMEM_KB");
+        max_kb = e ? atoi(e) : 75;
+        if (max_kb < 16 || max_kb > 112) max_kb = 75;
+        const char *fx = getenv("S3D_XY2_TX"), *fy = getenv("S3D_XY2_TY");
+        if (fx && fy) { force_tx = atoi(fx); force_ty = atoi(fy); }
+    }
+    if (force_tx >= 32 && force_tx % 32 == 0 && force_ty >= kKY && force_ty % kKY == 0) {
+        XY2Tile t = make_xy2_tile(force_tx, force_ty, R);
+        if (t.smem <= 113 * 1024 && t.W_in <= 256 && t.rows <= 256) return t;
+    }
+    // Cost model: a tile costs (x-pass rounds) + 2 (y-pass rounds) item times -- an x item is 16 outputs on
+    // 8-lane groups (32 groups per round), a y item 32 outputs (256 per round) -- and two persistent CTAs
+    // per SM share the tiles.
     XY2Tile best = make_xy2_tile(32, kKY, R);
     double best_cost = 1e300;
-    static int max_kb = -1;          // S3D_XY2_SMEM_KB: cap on the tile's shared memory (experiments)
-    if (max_kb < 0) { const char *e = getenv("S3D_XY2_SMEM_KB"); max_kb = e ? atoi(e) : 75; if (max_kb < 16 || max_kb > 112) max_kb = 75; }
     for (int TX = 32; TX <= 128; TX += 32)
         for (int TY = kKY; TY <= 128; TY += kKY) {
             XY2Tile t = make_xy2_tile(TX, TY, R);
             if (t.smem > (size_t)max_kb * 1024 || t.W_in > 256 || t.rows > 256) continue;
-            long long ctas = (long long)((pitch + TX - 1) / TX) * ((Y + TY - 1) / TY) * Z;
-            long long rounds = (ctas + sm_count - 1) / sm_count;
-            double work = (double)TX * (t.rows8 + TY) + 600.0;      // + fixed cost per CTA (TMA round trip, barriers)
+            long long tiles = (long long)((pitch + TX - 1) / TX) * ((Y + TY - 1) / TY) * Z;
+            long long rounds = (tiles + 2 * sm_count - 1) / (2 * sm_count);
+            int x_items = (t.rows8 / 8) * (TX / kKX), y_items = (TX / 2) * (TY / kKY);
+            double work = (double)((x_items + 31) / 32) + 2.0 * ((y_items + kXY2Threads - 1) / kXY2Threads) + 0.5;
             double cost = (double)rounds * work;
             if (cost < best_cost) { best_cost = cost; best = t; }
         }
@@ -322,35 +375,48 @@ static bool launch_blur_xy2(cudaStream_t st, const float *in, float *tmp, int X,
 {
     XY2Tile tile = choose_xy2_tile(pitch, Y, Z, R, sm_count);
     CUtensorMap map;
-    if (Z > 65535 || !make_volume_map_box(&map, in, Y, Z, pitch, tile.W_in, tile.rows)) return false;
+    if (!make_volume_map_box(&map, in, Y, Z, pitch, tile.W_in, tile.rows)) return false;
     TapsSmall t;
     memset(&t, 0, sizeof(t));
     for (int j = 0; j < 2 * R + 1; j++) t.w[j] = taps[j];
-    dim3 grid((pitch + tile.TX - 1) / tile.TX, (Y + tile.TY - 1) / tile.TY, Z);
-    blur_xy2_kernel<R><<<grid, kXY2Threads, tile.smem, st>>>(map, tmp, X, Y, pitch, tile, t);
+    const int n_tx = (pitch + tile.TX - 1) / tile.TX, n_ty = (Y + tile.TY - 1) / tile.TY;
+    const long long n_tiles = (long long)n_tx * n_ty * Z;
+    if (n_tiles > 0x7fffffffll) return false;
+    const int grid = (int)(n_tiles < 2ll * sm_count ? n_tiles : 2ll * sm_count);
+    blur_xy2_kernel<R><<<grid, kXY2Threads, tile.smem, st>>>(map, tmp, X, Y, pitch, tile, n_tx, n_ty, (int)n_tiles, t);
     *err = cudaGetLastError();
     return true;
 }
 
 // z (+DoG): tmp -> out.  `target` = threads wanted in flight (segments along z are added to reach it).
+// Radii up to kZ2Vec4MaxR march 4 columns per thread (128-bit accesses: twice the bytes in flight per
+// load instruction), wider ones 2 columns (register budget: V*(2R+1) partial sums per thread).
+constexpr int kZ2Vec4MaxR = 4;
+
 template <int R>
 static cudaError_t launch_blur_z2(cudaStream_t st, const float *tmp, float *out, const float *prev, float *dog,
-                                  int Y, int Z, int pitch, const float *taps, int target)
+                                  int Y, int Z, int pitch, const float *taps, int target, int force_v)
 {
     TapsSmall t;
     memset(&t, 0, sizeof(t));
     for (int j = 0; j < 2 * R + 1; j++) t.w[j] = taps[j];
     long long plane = (long long)pitch * Y;
-    int n_pairs = (int)(plane / 2);
-    int n_seg = (int)((target + n_pairs - 1) / n_pairs);
+    const int V = force_v ? force_v : (R <= kZ2Vec4MaxR ? 4 : 2);
+    int n_vec = (int)(plane / V);
+    int n_seg = (int)((target + n_vec - 1) / n_vec);
     int max_seg = (Z + 31) / 32;            // segments re-read 2R planes of halo: keep them >= 32 planes
     if (n_seg > max_seg) n_seg = max_seg;
     if (n_seg < 1) n_seg = 1;
     int seg_len = (Z + n_seg - 1) / n_seg;
     n_seg = (Z + seg_len - 1) / seg_len;
-    dim3 grid((unsigned)((n_pairs + 127) / 128), (unsigned)n_seg);
-    if (dog) blur_z2_kernel<R, true><<<grid, 128, 0, st>>>(tmp, out, prev, dog, n_pairs, plane, Z, seg_len, t);
-    else blur_z2_kernel<R, false><<<grid, 128, 0, st>>>(tmp, out, tmp, out, n_pairs, plane, Z, seg_len, t);
+    dim3 grid((unsigned)((n_vec + 127) / 128), (unsigned)n_seg);
+    if (V == 4) {
+        if (dog) blur_z2_kernel<R, true, float4><<<grid, 128, 0, st>>>(tmp, out, prev, dog, n_vec, plane, Z, seg_len, t);
+        else blur_z2_kernel<R, false, float4><<<grid, 128, 0, st>>>(tmp, out, tmp, out, n_vec, plane, Z, seg_len, t);
+    } else {
+        if (dog) blur_z2_kernel<R, true, float2><<<grid, 128, 0, st>>>(tmp, out, prev, dog, n_vec, plane, Z, seg_len, t);
+        else blur_z2_kernel<R, false, float2><<<grid, 128, 0, st>>>(tmp, out, tmp, out, n_vec, plane, Z, seg_len, t);
+    }
     return cudaGetLastError();
 }
 

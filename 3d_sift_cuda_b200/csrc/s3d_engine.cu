@@ -18,6 +18,7 @@
 #include "s3d_voxel.cuh"
 #include "s3d_blur_fused.cuh"
 #include "s3d_blur2.cuh"
+#include "s3d_blur3.cuh"
 #include "s3d_keypoint.cuh"
 #include "s3d_small_octaves.cuh"
 
@@ -180,6 +181,12 @@ struct s3d_ctx {
                                  // the per-level launches (each pass is an L2 round trip + a cluster barrier either way), so off.
     bool xy_fused = true;        // x and y passes in one TMA-tiled kernel (S3D_XY=0: separate passes)
     bool blur2 = true;           // second-generation level kernels (s3d_blur2.cuh); S3D_BLUR2=0: first generation
+    int f3_max_r = 0;            // one-kernel level (s3d_blur3.cuh) for radii up to this (S3D_F3_MAXR; 0 = never: measured slower than the two-kernel level at MNI size, see profiles/README.md) ...
+    long long f3_min_voxels = 0; // ... and volumes of at least this many voxels (S3D_F3_MIN_VOXELS)
+    int f3_ctas = 0;             // S3D_F3_CTAS: CTAs the one-kernel level aims for (0 = one per SM)
+    unsigned long long *d_stamps = nullptr;   // S3D_STAMPS=1
+    int z2_vec = 0;              // S3D_Z2_VEC=2|4: columns per thread of the z march (0 = by radius)
+    bool serial = false;         // S3D_SERIAL=1: no branches, every kernel on the main stream (standalone kernel times)
     int fused_ctas = 0;          // S3D_FUSED_CTAS: CTAs the fused blur aims for (0 = 2 per SM)
     bool timing = false;         // S3D_STAGE_TIMING=1: no graph, events at stage boundaries of the main stream
     std::vector<std::pair<std::string, cudaEvent_t>> marks;
@@ -235,7 +242,14 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
     if (borrow) {
         ctx->stream = (cudaStream_t)stream;
     } else {
-        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        const char *sp = getenv("S3D_SIDE_PRIO");
+        if (sp && sp[0] == 'm') {     // main chain above the side branches (experiments)
+            int lo = 0, hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CK(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, hi));
+        } else {
+            CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        }
         ctx->own_stream = true;
     }
     KpTables t;
@@ -251,6 +265,10 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
     // behind them (stream priorities are kept by the captured graph nodes).
     int prio_lo = 0, prio_hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    {   // S3D_SIDE_PRIO=low: side branches below the main chain (experiments)
+        const char *sp = getenv("S3D_SIDE_PRIO");
+        if (sp && (sp[0] == 'l' || sp[0] == 'm')) prio_hi = prio_lo;
+    }
     for (int o = 1; o < kMaxOct; o++) {
         CK(cudaStreamCreateWithPriority(&ctx->side[o], cudaStreamNonBlocking, prio_hi));
         CK(cudaEventCreateWithFlags(&ctx->ev_done[o], cudaEventDisableTiming));
@@ -274,6 +292,19 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
     const char *b2 = getenv("S3D_BLUR2");
     if (b2) ctx->blur2 = (b2[0] != '0');
     CK(init_blur2_attrs());
+    CK(init_blur3_attrs());
+    const char *f3r = getenv("S3D_F3_MAXR");
+    if (f3r) ctx->f3_max_r = atoi(f3r);
+    const char *f3v = getenv("S3D_F3_MIN_VOXELS");
+    if (f3v) ctx->f3_min_voxels = atoll(f3v);
+    const char *stp = getenv("S3D_STAMPS");
+    if (stp && stp[0] == '1') CK(cudaMalloc((void **)&ctx->d_stamps, 4 * sizeof(unsigned long long)));
+    const char *zv = getenv("S3D_Z2_VEC");
+    if (zv) ctx->z2_vec = (atoi(zv) == 2 || atoi(zv) == 4) ? atoi(zv) : 0;
+    const char *ser = getenv("S3D_SERIAL");
+    if (ser) ctx->serial = (ser[0] == '1');
+    const char *f3c = getenv("S3D_F3_CTAS");
+    if (f3c) ctx->f3_ctas = atoi(f3c);
     const char *fc = getenv("S3D_FUSED_CTAS");
     ctx->fused_ctas = fc ? atoi(fc) : 0;
     const char *tm = getenv("S3D_STAGE_TIMING");
@@ -338,6 +369,21 @@ extern "C" int s3d_debug_phase_cycles(unsigned long long *out32)
 }
 #endif
 
+// S3D_STAMPS=1 (profiling): %globaltimer at four points of an extraction -- before / after the input
+// re-pitch (outside the graph), first and last node of the graph -- to see launch gaps without a profiler
+__global__ void stamp_kernel(unsigned long long *slot)
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *slot = t;
+}
+extern "C" int s3d_debug_stamps(s3d_ctx *ctx, unsigned long long *out4)
+{
+    if (!ctx || !ctx->d_stamps) return -1;
+    if (cudaMemcpy(out4, ctx->d_stamps, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // stage launchers
 // ---------------------------------------------------------------------------------------------------
@@ -366,11 +412,19 @@ static void launch_blur_fast(s3d_ctx *ctx, const float *in, float *tmp, float *o
     memset(&t, 0, sizeof(t));
     for (int j = 0; j < 2 * R + 1; j++) t.w[j] = taps[j];
     long long plane = (long long)pitch * Y;
-    if (ctx->blur2 && taps_symmetric(taps, 2 * R + 1) && plane * Z < (1ll << 31)) {
+    const bool sym = taps_symmetric(taps, 2 * R + 1);
+    if (sym && R <= ctx->f3_max_r && plane * Z >= ctx->f3_min_voxels) {
+        cudaError_t e = cudaSuccess;
+        if (launch_blur_f3<R>(ctx->cur, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, ctx->f3_ctas, &e)) {
+            ctx->launches += 1;
+            return;
+        }
+    }
+    if (ctx->blur2 && sym && plane * Z < (1ll << 31)) {
         cudaError_t e = cudaSuccess;
         if (launch_blur_xy2<R>(ctx->cur, in, tmp, X, Y, Z, pitch, taps, ctx->sm_count, &e)) {
             int target2 = ctx->march_target > 0 ? ctx->march_target : ctx->sm_count * 256;
-            launch_blur_z2<R>(ctx->cur, tmp, out, in, dog, Y, Z, pitch, taps, target2);
+            launch_blur_z2<R>(ctx->cur, tmp, out, in, dog, Y, Z, pitch, taps, target2, ctx->z2_vec);
             ctx->launches += 2;
             return;
         }
@@ -794,6 +848,7 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     int *kp_count = p->counts + p->n_lists, *n_features = kp_count + 1, *err = kp_count + 2;
     ctx->cur = st;
     mark(ctx, "start");
+    if (ctx->d_stamps) stamp_kernel<<<1, 1, 0, st>>>(ctx->d_stamps + 2);
     zero_ints_kernel<<<1, 256, 0, st>>>(p->counts, p->n_lists + 8 + kMaxOct * 3);
     ctx->launches++;
 
@@ -831,7 +886,7 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     }
     for (int o = 0; o < o_small; o++) {
         const OctaveDesc &od = p->pyr.oct[o];
-        cudaStream_t so = (o == 0) ? st : ctx->side[o];
+        cudaStream_t so = (o == 0 || ctx->serial) ? st : ctx->side[o];
         ctx->cur = so;
         if (o > 0) CK(cudaStreamWaitEvent(so, ctx->ev_fork[o - 1], 0));
         for (int j = 1; j < 6; j++) {
@@ -868,7 +923,7 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
                 // The branch runs beside the blur of the next level; only the refinement of centre level 3
                 // (after level 5) is exposed.
                 CK(cudaEventRecord(ctx->ev_lvl[o][j - 2], so));
-                cudaStream_t sd = ctx->det[o];
+                cudaStream_t sd = ctx->serial ? st : ctx->det[o];
                 CK(cudaStreamWaitEvent(sd, ctx->ev_lvl[o][j - 2], 0));
                 ctx->cur = sd;
                 int c_det = j - 1, c_ref = j - 2;
@@ -912,6 +967,7 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
                                                               p->kp_ori0, p->kp_rots, p->kp_patch0, prm->descriptor, size_factor, p->octave_base,
                                                               p->row_cap, p->feats, p->dbg_patches, p->dbg_prerank);
     mark(ctx, "row_offsets+describe");
+    if (ctx->d_stamps) stamp_kernel<<<1, 1, 0, st>>>(ctx->d_stamps + 3);
     ctx->launches += 5;
     CK(cudaGetLastError());
     return S3D_OK;
@@ -990,7 +1046,9 @@ static s3d_status stage_input(s3d_ctx *ctx, const float *src, bool from_host)
     // dense -> pitched in one pass straight from the caller's buffer (outside the graph: the source
     // pointer changes from call to call)
     dim3 grid((dst.pitch + 255) / 256, (unsigned)(rows < 8192 ? rows : 8192));
+    if (ctx->d_stamps) stamp_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_stamps + 0);
     pad_rows_kernel<<<grid, 256, 0, ctx->stream>>>(src, p->X, (long long)rows, dst.p, dst.pitch);
+    if (ctx->d_stamps) stamp_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_stamps + 1);
     CK(cudaGetLastError());
     return S3D_OK;
 }
@@ -1083,6 +1141,114 @@ extern "C" s3d_status s3d_extract(s3d_ctx *ctx, const float *h_volume, int X, in
     if (s != S3D_OK) return s;
     return s3d_fetch_features(ctx, out, n_out);
 }
+
+// ---------------------------------------------------------------------------------------------------
+// batch level: n_contexts extraction contexts on one device, fed round-robin
+// ---------------------------------------------------------------------------------------------------
+struct s3d_batch {
+    int device = 0;
+    std::vector<s3d_ctx *> ctx;
+    std::string err;
+    int launches = 0;
+};
+
+extern "C" s3d_status s3d_batch_create(int device, int n_contexts, s3d_batch **out)
+{
+    if (!out || n_contexts < 1 || n_contexts > 64) return S3D_ERR_INVALID;
+    *out = nullptr;
+    s3d_batch *b = new s3d_batch();
+    b->device = device;
+    for (int i = 0; i < n_contexts; i++) {
+        s3d_ctx *c = nullptr;
+        s3d_status st = s3d_ctx_create(device, &c);
+        if (st != S3D_OK) {
+            if (c) s3d_ctx_destroy(c);
+            for (s3d_ctx *q : b->ctx) s3d_ctx_destroy(q);
+            delete b;
+            return st;
+        }
+        b->ctx.push_back(c);
+    }
+    *out = b;
+    return S3D_OK;
+}
+
+extern "C" void s3d_batch_destroy(s3d_batch *b)
+{
+    if (!b) return;
+    for (s3d_ctx *c : b->ctx) s3d_ctx_destroy(c);
+    delete b;
+}
+
+extern "C" const char *s3d_batch_last_error(const s3d_batch *b) { return b ? b->err.c_str() : "null batch"; }
+extern "C" int s3d_batch_launches_per_volume(s3d_batch *b) { return b ? b->launches : 0; }
+
+// volume i runs on context i % n; before a context is reused its previous volume is collected
+static s3d_status batch_run(s3d_batch *b, const float *const *vols, int n, int X, int Y, int Z, const s3d_params *prm,
+                            bool from_host, s3d_feature **rows, int *n_rows, int *n_kps)
+{
+    if (!b || !vols || n < 0 || !prm) return S3D_ERR_INVALID;
+    const int nc = (int)b->ctx.size();
+    std::vector<int> pending(nc, -1);
+    auto collect = [&](int c) -> s3d_status {
+        const int j = pending[c];
+        pending[c] = -1;
+        if (j < 0) return S3D_OK;
+        s3d_status st;
+        if (rows) {
+            int nr = 0;
+            st = s3d_fetch_features(b->ctx[c], &rows[j], &nr);
+            if (n_rows) n_rows[j] = nr;
+            if (n_kps) n_kps[j] = b->ctx[c]->h_counts[0];
+        } else {
+            int nk = 0, nr = 0;
+            st = s3d_fetch_counts(b->ctx[c], &nk, &nr);
+            if (n_rows) n_rows[j] = nr;
+            if (n_kps) n_kps[j] = nk;
+        }
+        if (st != S3D_OK) b->err = b->ctx[c]->err;
+        return st;
+    };
+    s3d_status first_err = S3D_OK;
+    for (int i = 0; i < n && first_err == S3D_OK; i++) {
+        const int c = i % nc;
+        s3d_status st = collect(c);
+        if (st == S3D_OK)
+            st = from_host ? s3d_extract_host_async(b->ctx[c], vols[i], X, Y, Z, prm)
+                           : s3d_extract_device(b->ctx[c], vols[i], X, Y, Z, prm);
+        if (st != S3D_OK) { if (b->err.empty() || st != S3D_OK) b->err = b->ctx[c]->err; first_err = st; break; }
+        pending[c] = i;
+    }
+    for (int k = 0; k < nc; k++) {      // drain in submission order
+        const int c = (n + k) % nc;
+        s3d_status st = collect(c);
+        if (st != S3D_OK && first_err == S3D_OK) first_err = st;
+    }
+    if (nc > 0) b->launches = b->ctx[0]->last_launches;
+    return first_err;
+}
+
+extern "C" s3d_status s3d_batch_extract(s3d_batch *b, const float *const *h_volumes, int n_volumes, int X, int Y, int Z,
+                                        const s3d_params *prm, s3d_feature **rows, int *n_rows)
+{
+    if (!rows || !n_rows) return S3D_ERR_INVALID;
+    for (int i = 0; i < n_volumes; i++) { rows[i] = nullptr; n_rows[i] = 0; }
+    return batch_run(b, h_volumes, n_volumes, X, Y, Z, prm, true, rows, n_rows, nullptr);
+}
+
+extern "C" s3d_status s3d_batch_extract_device(s3d_batch *b, const float *const *d_volumes, int n_volumes, int X, int Y, int Z,
+                                               const s3d_params *prm, int *n_keypoints, int *n_rows)
+{
+    return batch_run(b, d_volumes, n_volumes, X, Y, Z, prm, false, nullptr, n_rows, n_keypoints);
+}
+
+extern "C" void *s3d_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void s3d_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 // ---------------------------------------------------------------------------------------------------
 // introspection

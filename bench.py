@@ -5,15 +5,19 @@ orientation + SIFT-Rank descriptors) on synthetic MNI-sized phantoms.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 One "step" = one 182x218x182 fp32 volume through the whole path on each GPU (BASELINE.json config 2;
-with N > 1 this is config 4's batch sharding: every rank extracts its own volume, no data-path
-collective, weak scaling).  Prints ONE JSON line on rank 0:
+with N > 1 this is config 4's batch sharding: every rank extracts its own volumes, no data-path
+collective, weak scaling).  The K steps of a run go through the batch entry point of the C-ABI
+(s3d_batch_*: --contexts extraction contexts in flight per GPU), timed as ONE region between two CUDA
+events with barrier + synchronize on both sides.  Prints ONE JSON line on rank 0:
 
-  value      volumes/s, whole job, volume already resident in HBM when the timed region starts
-             (CUDA events on the engine's stream, per step, L2 flushed between steps, max over ranks)
-  e2e        same metric through the public C-ABI call with HOST buffers: pinned H2D of the volume and
-             D2H of the feature rows inside the timed region, every step
+  value      volumes/s, whole job, volumes already resident in HBM when the timed region starts
+             (s3d_batch_extract_device; inputs rotate through a pool larger than L2; max over ranks)
+  latency_ms_per_volume   one volume alone on the GPU, one context, L2 flushed between steps
+  e2e        same metric through s3d_batch_extract with HOST buffers: pinned H2D of every volume and
+             D2H of its feature rows inside the timed region
   roofline   the heaviest blur level (17 taps + fused DoG at octave-0 size): algorithmic bytes
-             (read G_{j-1}, write G_j, write DoG = 12 B/voxel) / measured duration vs MEASURED_PEAKS.json
+             (read G_{j-1}, write G_j, write DoG = 12 B/voxel) / measured duration vs MEASURED_PEAKS.json;
+             `levels` lists all six levels of octave 0
   cpu_baseline  the reference's own CPU path (oracle/_ref) on the host cores, bounded sample
 
 --impl reference times the reference's CPU implementation (oracle/_ref, else the oracle port) with
@@ -193,8 +197,11 @@ def run_ours(args):
     eng = pkg.Engine(local)
     st = torch.cuda.ExternalStream(eng.stream, device=dev)
     params = pkg.Params()
-    # a small pool of distinct volumes per rank so no step can reuse a previous step's result
-    npool = 4
+    nctx = max(1, args.contexts)
+    batch = pkg.Batch(local, nctx)
+    # A pool of distinct volumes per rank, larger than L2 (8 x 28.9 MB = 231 MB > 126 MB), rotated so that no
+    # step can reuse a previous step's input or result; every context also owns its own 0.44 GB pyramid.
+    npool = 8
     vols = [pkg.phantom.brain_phantom(SHAPE, 1 + rank * npool + i, NBLOBS) for i in range(npool)]
     X, Y, Z = SHAPE
     d_vols = [torch.from_numpy(v).to(dev) for v in vols]
@@ -202,19 +209,36 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
     torch.cuda.synchronize()
 
-    # ---- device-resident throughput (value) ----
-    for i in range(args.warmup):
-        eng.extract_device(d_vols[i % npool], SHAPE, params)
-    eng.sync()
-    nk, nf = eng.fetch_counts()
-    launches_per_step = eng.launch_count()
+    def timed(fn):
+        """device time of fn() between two events on an otherwise idle GPU, barrier + synchronize on both sides"""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        return dmod.max_over_ranks(e0.elapsed_time(e1), device=dev), out
+
+    # ---- device-resident throughput (value): K volumes through s3d_batch_extract_device -------------
+    batch.extract_device([d_vols[i % npool] for i in range(max(args.warmup, 2 * nctx))], SHAPE, params)
+    launches_per_step = batch.launches_per_volume()
     sampler = ClockSampler(local)
-    barrier()
     if rank == 0:
         sampler.start()
+    seq = [d_vols[i % npool] for i in range(args.steps)]
+    total_ms, (nks, nfs) = timed(lambda: batch.extract_device(seq, SHAPE, params))
+    nk, nf = nks[0], nfs[0]
+    ms_per_step = total_ms / args.steps
+    value = world * 1e3 / ms_per_step
+
+    # ---- latency of one volume alone on the GPU (one context, L2 flushed between steps) ---------------
+    for i in range(3):
+        eng.extract_device(d_vols[i % npool], SHAPE, params)
+    eng.sync()
     evs = []
     with torch.cuda.stream(st):
-        for i in range(args.steps):
+        for i in range(min(args.steps, 50)):
             flush.zero_()                                  # evict L2 (untimed)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(st)
@@ -222,100 +246,94 @@ def run_ours(args):
             e1.record(st)
             evs.append((e0, e1))
     eng.sync()
-    barrier()
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
-    total_ms = dmod.max_over_ranks(total_ms, device=dev)
-    ms_per_step = total_ms / args.steps
-    value = world * 1e3 / ms_per_step
+    lat_ms = dmod.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs) / len(evs), device=dev)
 
-    # ---- end to end through the public call with host buffers (e2e) ----
-    # Every step = s3d_extract_host_async (H2D of the 28.9 MB volume from pinned memory + the whole path)
-    # followed by s3d_fetch_features (D2H of the rows).  Two engine contexts alternate so that the H2D
-    # copy of step i+1 overlaps the kernels of step i (the public API is one context per stream).
-    eng2 = pkg.Engine(local)
-    engines = [eng, eng2]
-    for i in range(max(args.warmup, 4)):
-        engines[i % 2].extract_host_async(h_vols[i % npool], params)
-        engines[i % 2].fetch_features()
+    # ---- end to end through the public batch call with host buffers (e2e) ----------------------------
+    # s3d_batch_extract: every step's 28.9 MB volume is copied from pinned host memory (H2D) and its feature
+    # rows are copied back (D2H) inside the timed region; the contexts overlap the copies with compute.
+    batch.extract([h_vols[i % npool] for i in range(max(4, 2 * nctx))], params)
+    hseq = [h_vols[i % npool] for i in range(args.steps)]
+    e2e_ms, rows = timed(lambda: batch.extract(hseq, params))
+    d2h = sum(r.nbytes + 12 for r in rows)
+    e2e = {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": N0 * 4,
+           "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps,
+           "note": "s3d_batch_extract with %d contexts per GPU: pinned H2D of every volume and D2H of its rows inside the timed region" % nctx}
+    # same thing strictly one step at a time (latency of a single featExtract-style call with host buffers)
     barrier()
     t0 = time.perf_counter()
-    d2h = 0
-    pending = None
-    for i in range(args.steps):
-        e_i = engines[i % 2]
-        e_i.extract_host_async(h_vols[i % npool], params)
-        if pending is not None:
-            f = pending.fetch_features()
-            d2h += f.nbytes + 12
-        pending = e_i
-    f = pending.fetch_features()
-    d2h += f.nbytes + 12
-    torch.cuda.synchronize()
-    e2e_s = dmod.max_over_ranks(time.perf_counter() - t0, device=dev)
-    e2e = {"value": world * args.steps / e2e_s, "unit": "volumes/s", "h2d_bytes_per_step": N0 * 4,
-           "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * e2e_s / args.steps,
-           "note": "2 contexts alternate: H2D of step i+1 overlaps compute of step i; every step's H2D and D2H are inside the timed region"}
-    # same thing strictly one step at a time (latency of a single featExtract call with host buffers)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(min(args.steps, 50)):
         eng.extract_host_async(h_vols[i % npool], params)
         eng.fetch_features()
     torch.cuda.synchronize()
-    e2e["serial_ms_per_step"] = 1e3 * dmod.max_over_ranks(time.perf_counter() - t0, device=dev) / args.steps
+    e2e["serial_ms_per_step"] = 1e3 * dmod.max_over_ranks(time.perf_counter() - t0, device=dev) / min(args.steps, 50)
+    clocks = sampler.stop() if rank == 0 else None   # sampled across all timed regions
 
-    # ---- batch throughput: several volumes in flight on one GPU (BASELINE.json config 4 per GPU) ----
-    batch = None
-    if rank == 0 or world > 1:
-        nctx = 4
-        pool_e = engines + [pkg.Engine(local) for _ in range(nctx - 2)]
-        for i in range(2 * nctx):
-            pool_e[i % nctx].extract_device(d_vols[i % npool], SHAPE, params)
-        for e_ in pool_e:
-            e_.sync()
-        nb = max(args.steps, 2 * nctx)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(nb):
-            pool_e[i % nctx].extract_device(d_vols[i % npool], SHAPE, params)
-        for e_ in pool_e:
-            e_.sync()
-        bs = dmod.max_over_ranks(time.perf_counter() - t0, device=dev)
-        batch = {"value": world * nb / bs, "unit": "volumes/s", "contexts_per_gpu": nctx, "volumes": nb,
-                 "note": "device-resident volumes, %d contexts (streams) per GPU in flight, wall clock" % nctx}
-        for e_ in pool_e[2:]:
-            e_.close()
-    clocks = sampler.stop() if rank == 0 else None   # sampled across all timed regions (value, e2e, batch)
-
-    # ---- roofline of the dominant stage: the 17-tap blur level at octave-0 size with fused DoG ----
+    # ---- roofline of the dominant stage: the blur levels of octave 0 (x+y kernel, z kernel with fused DoG) ----
+    # Algorithmic bytes of a level = read G_{j-1}, write G_j, write DoG = 12 B/voxel (the initial blur writes no
+    # DoG: 8 B/voxel).  Each level is timed alone with CUDA events on the engine's stream, L2 flushed before
+    # every launch (cold) and back to back in a -> b -> a chains (warm, as inside the pipeline).  The headline
+    # entry is the heaviest level (17 taps); `levels` lists all six.  `traffic` = dram bytes read + written per
+    # level from the ncu --set full capture summarised in profiles/r1_blur_level_traffic.json.
     roof = None
     if rank == 0:
         peak, peak_src = measured_peaks()
         pitch = (X + 7) // 8 * 8
         a = torch.zeros((Z, Y, pitch), dtype=torch.float32, device=dev)
         a[:, :, :X] = d_vols[0]
-        tmp, out, dog = torch.empty_like(a), torch.empty_like(a), torch.empty_like(a)
-        taps = pkg.gaussian_taps(3.0900)    # level 4 -> 5 of every octave: 17 taps
+        b2, tmp, dog = torch.zeros_like(a), torch.zeros_like(a), torch.zeros_like(a)
         torch.cuda.synchronize()
-        for _ in range(3):
-            eng.blur3d(a, tmp, out, X, taps, dog)
-        eng.sync()
-        reps, ms = 10, 0.0
-        with torch.cuda.stream(st):
-            for _ in range(reps):
-                flush.zero_()
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_blur_level_traffic.json")))["levels"]
+        except Exception:
+            pass
+        levels = []
+        sched = [("initial", 1.5199, False), ("1", 1.2263, True), ("2", 1.5450, True), ("3", 1.9466, True),
+                 ("4", 2.4525, True), ("5", 3.0900, True)]
+        for name, sigma, with_dog in sched:
+            taps = pkg.gaussian_taps(sigma)
+            dg = dog if with_dog else None
+            for _ in range(3):
+                eng.blur3d(a, tmp, b2, X, taps, dg)
+            eng.sync()
+            reps, lev = 10, []
+            with torch.cuda.stream(st):
+                for _ in range(reps):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(st)
+                    eng.blur3d(a, tmp, b2, X, taps, dg)
+                    e1.record(st)
+                    lev.append((e0, e1))
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(st)
-                eng.blur3d(a, tmp, out, X, taps, dog)
+                for k in range(reps):
+                    if k % 2 == 0:
+                        eng.blur3d(a, tmp, b2, X, taps, dg)
+                    else:
+                        eng.blur3d(b2, tmp, a, X, taps, dg)
                 e1.record(st)
-                evs.append((e0, e1))
-        eng.sync()
-        ms = sum(x.elapsed_time(y) for x, y in evs[-reps:]) / reps
-        alg = 12.0 * N0                   # read G_{j-1}, write G_j, write DoG
-        achieved = alg / (ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "blur level (x + y + z passes, 17 taps, fused DoG) at 182x218x182",
-                "ms_per_launch": ms, "algorithmic_bytes": alg, "peak_source": peak_src,
+            eng.sync()
+            cold = sum(x.elapsed_time(y) for x, y in lev) / reps
+            warm = e0.elapsed_time(e1) / reps
+            alg = (12.0 if with_dog else 8.0) * N0
+            tr = traffic.get(str(len(taps)))
+            levels.append({"level": name, "taps": len(taps), "algorithmic_bytes": alg, "ms_cold": cold, "ms_warm": warm,
+                           "achieved_cold": alg / (cold * 1e-3) / 1e9, "frac_cold": alg / (cold * 1e-3) / 1e9 / peak,
+                           "achieved_warm": alg / (warm * 1e-3) / 1e9, "frac_warm": alg / (warm * 1e-3) / 1e9 / peak,
+                           "traffic": (tr["dram_read"] + tr["dram_write"]) if tr else None})
+            a[:, :, :X] = d_vols[0]
+            torch.cuda.synchronize()
+        top = levels[-1]
+        tot_alg = sum(l["algorithmic_bytes"] for l in levels)
+        tot_ms = sum(l["ms_cold"] for l in levels)
+        roof = {"bound": "hbm", "achieved": top["achieved_cold"], "peak": peak, "unit": "GB/s", "frac": top["frac_cold"],
+                "traffic": top["traffic"],
+                "kernel": "blur level 4->5 (blur_xy2_kernel<8> + blur_z2_kernel<8,DoG>: x, y, z passes, 17 taps, fused DoG) at 182x218x182, L2 flushed before each launch",
+                "ms_per_launch": top["ms_cold"], "algorithmic_bytes": top["algorithmic_bytes"], "peak_source": peak_src,
+                "levels": levels,
+                "octave0_blur_chain": {"algorithmic_bytes": tot_alg, "ms": tot_ms, "achieved": tot_alg / (tot_ms * 1e-3) / 1e9,
+                                       "frac": tot_alg / (tot_ms * 1e-3) / 1e9 / peak},
                 "pipeline": {"algorithmic_bytes": algorithmic_bytes(SHAPE), "ms": ms_per_step,
                              "achieved": algorithmic_bytes(SHAPE) / (ms_per_step * 1e-3) / 1e9,
                              "frac": algorithmic_bytes(SHAPE) / (ms_per_step * 1e-3) / 1e9 / peak,
@@ -328,18 +346,22 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "gvoxels_per_s": value * N0 / 1e9,
             "config": {"workload": WORKLOAD, "shape_xyz": list(SHAPE), "phantom": "brain_phantom(seed=1.., nblobs=400)",
-                       "parallelism": "one volume per GPU per step, no data-path collective" if world > 1 else "single GPU",
-                       "l2": "256 MiB buffer written between timed steps (L2 flush, untimed)",
+                       "parallelism": ("volumes sharded over %d GPUs, no data-path collective; " % world if world > 1 else "single GPU; ")
+                                      + "%d extraction contexts (streams) in flight per GPU (s3d_batch)" % nctx,
+                       "contexts_per_gpu": nctx,
+                       "l2": "inputs larger than L2: a pool of 8 distinct volumes (231 MB) is rotated and every context "
+                             "owns a 0.44 GB pyramid; the one-volume latency below flushes L2 (256 MiB write) between steps",
                        "keypoints_per_volume": nk, "rows_per_volume": nf},
+            "latency_ms_per_volume": lat_ms,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "launches_per_step": launches_per_step, "roofline": roof, "cpu_baseline": cpu, "batch": batch,
+            "launches_per_step": launches_per_step, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     eng.close()
-    eng2.close()
+    batch.close()
     return 0
 
 
@@ -350,6 +372,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--contexts", type=int, default=4, help="extraction contexts in flight per GPU")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -173,6 +173,32 @@ s3d_status s3d_fetch_counts(s3d_ctx *ctx, int *n_keypoints, int *n_features);
 s3d_status s3d_result_device(s3d_ctx *ctx, const s3d_feature **d_features, const int **d_n_features);
 void s3d_free(void *p);
 
+/* ---- batch level: many volumes on one GPU (BASELINE.json config 4, per GPU) -----------------------
+ * The reference's featExtract handles one volume per process run (R/featExtract/featExtract.cpp:206-590);
+ * a study of N volumes is N runs.  s3d_batch keeps `n_contexts` extraction contexts (streams + resident
+ * pyramid plans) on one device and feeds them round-robin, so the PCIe transfer, the bandwidth-bound
+ * pyramid kernels and the latency-bound keypoint kernels of different volumes overlap.  Volumes are
+ * independent: results are identical to s3d_extract on each volume, in input order.  Across GPUs the batch
+ * is sharded by the caller, one process (or thread) per GPU, with no communication.
+ *
+ * s3d_batch_extract        : volumes[i] is a dense HOST array (pinned memory from s3d_host_alloc lets the
+ *                            H2D copy run asynchronously); rows[i] is malloc'ed (s3d_free), n_rows[i] its count.
+ * s3d_batch_extract_device : volumes[i] is a dense DEVICE array; only the counts are brought back
+ *                            (n_keypoints / n_rows may be NULL); this is the form bench.py's `value` times. */
+typedef struct s3d_batch s3d_batch;
+s3d_status s3d_batch_create(int device, int n_contexts, s3d_batch **batch);
+void s3d_batch_destroy(s3d_batch *batch);
+const char *s3d_batch_last_error(const s3d_batch *batch);
+s3d_status s3d_batch_extract(s3d_batch *batch, const float *const *h_volumes, int n_volumes, int X, int Y, int Z,
+                             const s3d_params *params, s3d_feature **rows, int *n_rows);
+s3d_status s3d_batch_extract_device(s3d_batch *batch, const float *const *d_volumes, int n_volumes, int X, int Y, int Z,
+                                    const s3d_params *params, int *n_keypoints, int *n_rows);
+/* kernel launches (graph nodes included) per volume of the last batch call */
+int s3d_batch_launches_per_volume(s3d_batch *batch);
+/* page-locked host memory for volumes (cudaHostAlloc / cudaFreeHost) */
+void *s3d_host_alloc(size_t bytes);
+void s3d_host_free(void *p);
+
 /* ---- introspection for parity tests --------------------------------------------------------------
  * Pyramid of the last extraction: Gaussian level g (0..5) or DoG level (0..4) of an octave, copied
  * densely (X*Y*Z floats) to host memory.  dims receives X, Y, Z of that octave. */

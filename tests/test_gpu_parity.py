@@ -234,3 +234,84 @@ def test_small_octaves_cluster_kernel_bit_exact(pkg, oracle, monkeypatch):
             assert eng.extract(vol).tobytes() == oracle.extract(vol)["features"].tobytes()
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("env", [{"S3D_F3_MAXR": "8"}, {"S3D_F3_MAXR": "0", "S3D_BLUR2": "0"},
+                                 {"S3D_F3_MAXR": "0", "S3D_Z2_VEC": "2", "S3D_XY2_TX": "32", "S3D_XY2_TY": "48"},
+                                 {"S3D_F3_MAXR": "0", "S3D_Z2_VEC": "4", "S3D_MARCH_TARGET": "200000"}])
+def test_every_blur_path_bit_exact(pkg, oracle, monkeypatch, env):
+    """Each selectable blur path -- the one-kernel level (s3d_blur3.cuh), the first-generation kernels, the
+    second-generation x+y / z kernels with 2 and 4 columns per thread and several z segments -- must give
+    the oracle's bits for every radius of the schedule, DoG and zero padding included."""
+    import torch
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    eng = pkg.Engine(0)
+    try:
+        for shape_xyz in [(48, 40, 36), (37, 29, 23), (70, 66, 41), (130, 35, 70)]:
+            vol = pkg.phantom.blob_phantom(shape_xyz, seed=5, nblobs=20)
+            X = shape_xyz[0]
+            for sigma in (0.5, 0.95, 1.2263, 1.5199, 1.9466, 2.4525, 3.09):
+                want = oracle.blur(vol, sigma)
+                d_in = to_dev(vol)
+                d_tmp, d_out, d_dog = torch.zeros_like(d_in), torch.zeros_like(d_in), torch.zeros_like(d_in)
+                ready()
+                eng.blur3d(d_in, d_tmp, d_out, X, pkg.gaussian_taps(sigma), d_dog)
+                eng.sync()
+                assert (bits(from_dev(d_out, X)) == bits(want)).all(), (shape_xyz, sigma)
+                assert (bits(from_dev(d_dog, X)) == bits(oracle.dog(vol, want))).all(), (shape_xyz, sigma)
+                assert float(d_out[:, :, X:].abs().sum()) == 0.0
+        vol = pkg.phantom.blob_phantom((64, 64, 64), 0, 60)
+        assert eng.extract(vol).tobytes() == oracle.extract(vol)["features"].tobytes()
+    finally:
+        eng.close()
+
+
+def test_asymmetric_taps_take_the_general_path(pkg, engine):
+    """Product sharing needs w[j] == w[2R-j]; taps that are not symmetric must fall back and still follow
+    the left-to-right sum (checked against a numpy restatement of filter_1d)."""
+    import torch
+    rng = np.random.default_rng(3)
+    vol = rng.random((20, 24, 40), dtype=np.float32)
+    taps = np.array([0.1, 0.2, 0.3, 0.25, 0.15], np.float32)
+    def blur_axis(a, axis):
+        a = np.moveaxis(a, axis, -1)
+        pad = np.zeros(a.shape[:-1] + (a.shape[-1] + 4,), np.float32)
+        pad[..., 2:-2] = a
+        acc = np.zeros_like(a)
+        for j in range(5):
+            acc = (acc + (taps[j] * pad[..., j:j + a.shape[-1]]).astype(np.float32)).astype(np.float32)
+        return np.moveaxis(acc, -1, axis)
+    want = blur_axis(blur_axis(blur_axis(vol, 2), 1), 0)
+    d_in = to_dev(vol)
+    d_tmp, d_out = torch.zeros_like(d_in), torch.zeros_like(d_in)
+    ready()
+    engine.blur3d(d_in, d_tmp, d_out, 40, taps)
+    engine.sync()
+    assert (bits(from_dev(d_out, 40)) == bits(want)).all()
+
+
+def test_batch_matches_single_volume_extraction(pkg, engine):
+    """s3d_batch (several contexts in flight on one GPU): rows identical to s3d_extract per volume, input order."""
+    import torch
+    vols = [pkg.phantom.blob_phantom((64, 56, 48), seed, 40 + 5 * seed) for seed in range(7)]
+    want = [engine.extract(v) for v in vols]
+    assert sum(len(w) for w in want) > 100
+    b = pkg.Batch(0, 3)
+    try:
+        got = b.extract(vols)
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert g.tobytes() == w.tobytes()
+        pinned = [torch.from_numpy(v).pin_memory() for v in vols]
+        got = b.extract(pinned)
+        for g, w in zip(got, want):
+            assert g.tobytes() == w.tobytes()
+        d = [torch.from_numpy(v).cuda() for v in vols]
+        torch.cuda.synchronize()
+        nk, nr = b.extract_device(d, (64, 56, 48))
+        assert nr == [len(w) for w in want]
+        assert b.launches_per_volume() > 0
+        assert b.extract([]) == []
+    finally:
+        b.close()
