@@ -1045,9 +1045,10 @@ static s3d_status stage_input(s3d_ctx *ctx, const float *src, bool from_host)
     }
     // dense -> pitched in one pass straight from the caller's buffer (outside the graph: the source
     // pointer changes from call to call)
-    dim3 grid((dst.pitch + 255) / 256, (unsigned)(rows < 8192 ? rows : 8192));
+    const size_t row_blocks = (rows + 3) / 4, max_blocks = (size_t)ctx->sm_count * 16;     // grid-stride over rows: blocks live long enough to overlap their loads
+    dim3 block(64, 4), grid((dst.pitch + 255) / 256, (unsigned)(row_blocks < max_blocks ? row_blocks : max_blocks));
     if (ctx->d_stamps) stamp_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_stamps + 0);
-    pad_rows_kernel<<<grid, 256, 0, ctx->stream>>>(src, p->X, (long long)rows, dst.p, dst.pitch);
+    pad_rows_kernel<<<grid, block, 0, ctx->stream>>>(src, p->X, (long long)rows, dst.p, dst.pitch);
     if (ctx->d_stamps) stamp_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_stamps + 1);
     CK(cudaGetLastError());
     return S3D_OK;

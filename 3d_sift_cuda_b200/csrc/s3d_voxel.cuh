@@ -301,13 +301,22 @@ __global__ void double_kernel(const float *__restrict__ in, int X, int Y, int Z,
     out[((long long)z * DY + y) * opitch + x] = r;
 }
 
-// dense (pitch == X) <-> pitched copies with zeroed padding; grid.y = rows
+// dense (pitch == X) <-> pitched copies with zeroed padding.  Block = (64, 4): four rows per block, a thread
+// moves elements x = tx, tx + 64, ... of its row (coalesced 32-bit loads and stores, 32-bit index arithmetic
+// inside the row); rows are walked with a grid-stride loop.
 __global__ void pad_rows_kernel(const float *__restrict__ in, int X, long long rows, float *__restrict__ out, int pitch)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= pitch) return;
-    for (long long row = blockIdx.y; row < rows; row += gridDim.y)
-        out[row * pitch + x] = (x < X) ? __ldg(in + row * X + x) : 0.0f;
+    for (long long row = blockIdx.y * blockDim.y + threadIdx.y; row < rows; row += (long long)gridDim.y * blockDim.y) {
+        const float *src = in + row * X;
+        float *dst = out + row * pitch;
+        for (int x0 = blockIdx.x * 256 + threadIdx.x; x0 < pitch; x0 += gridDim.x * 256) {
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const int x = x0 + 64 * j; v[j] = (x < X) ? __ldg(src + x) : 0.0f; }
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const int x = x0 + 64 * j; if (x < pitch) dst[x] = v[j]; }
+        }
+    }
 }
 
 __global__ void unpad_rows_kernel(const float *__restrict__ in, int pitch, long long rows, float *__restrict__ out, int X)
@@ -346,27 +355,41 @@ __global__ void __launch_bounds__(256) detect_face_kernel(const float *__restric
     const int z0 = blockIdx.z * kDetectZ + 1;
     const bool inside = (x <= X - 2 && y <= Y - 2);
     const long long plane = (long long)pitch * Y;
-    const long long base = (long long)(inside ? y : 1) * pitch + (inside ? x : 1);
-    float col[kDetectZ + 2], xm[kDetectZ], xp[kDetectZ], ym[kDetectZ], yp[kDetectZ];
-#pragma unroll
-    for (int k = 0; k < kDetectZ + 2; k++) {
-        int z = min(z0 - 1 + k, Z - 1);
-        col[k] = __ldg(centre + (long long)z * plane + base);
-    }
-#pragma unroll
-    for (int k = 0; k < kDetectZ; k++) {
-        const float *p = centre + (long long)min(z0 + k, Z - 1) * plane + base;
-        xm[k] = __ldg(p - 1); xp[k] = __ldg(p + 1); ym[k] = __ldg(p - pitch); yp[k] = __ldg(p + pitch);
-    }
-    const int lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
+    const unsigned int base = (unsigned int)((inside ? y : 1) * pitch + (inside ? x : 1));
+    // strict extremum over the 6 face neighbours  <=>  c > max(neighbours)  or  c < min(neighbours):
+    // two 3-input min/max trees per voxel instead of twelve compares (the pass is issue bound, not
+    // memory bound: ncu showed 58 instructions per voxel at 67 % issue utilisation before this form)
+    float up, c, dn;                 // z-1, z, z+1 of the running column
+    const float *p = centre + (long long)(z0 - 1) * plane + base;
+    up = __ldg(p);
+    p += plane;
+    c = __ldg(p);
     unsigned livemask = 0;
+    if (z0 + kDetectZ <= Z - 1) {    // every plane z0-1 .. z0+kDetectZ exists: no clamps (uniform per block)
 #pragma unroll
-    for (int k = 0; k < kDetectZ; k++) {
-        const float c = col[k + 1];
-        bool mx = (col[k] < c) && (col[k + 2] < c) && (xm[k] < c) && (xp[k] < c) && (ym[k] < c) && (yp[k] < c);
-        bool mn = (col[k] > c) && (col[k + 2] > c) && (xm[k] > c) && (xp[k] > c) && (ym[k] > c) && (yp[k] > c);
-        if (inside && (z0 + k <= Z - 2) && (mx || mn)) livemask |= 1u << k;
+        for (int k = 0; k < kDetectZ; k++) {
+            const float xm = __ldg(p - 1), xp = __ldg(p + 1), ym = __ldg(p - pitch), yp = __ldg(p + pitch);
+            dn = __ldg(p + plane);
+            const float hi = fmaxf(fmaxf(fmaxf(xm, xp), fmaxf(ym, yp)), fmaxf(up, dn));
+            const float lo = fminf(fminf(fminf(xm, xp), fminf(ym, yp)), fminf(up, dn));
+            if (c > hi || c < lo) livemask |= 1u << k;
+            up = c; c = dn; p += plane;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kDetectZ; k++) {
+            const bool zin = (z0 + k <= Z - 2);
+            const float *q = zin ? p : centre + base;       // keep the addresses legal past the last interior plane
+            const float xm = __ldg(q - 1), xp = __ldg(q + 1), ym = __ldg(q - pitch), yp = __ldg(q + pitch);
+            dn = __ldg(zin ? q + plane : q);
+            const float hi = fmaxf(fmaxf(fmaxf(xm, xp), fmaxf(ym, yp)), fmaxf(up, dn));
+            const float lo = fminf(fminf(fminf(xm, xp), fminf(ym, yp)), fminf(up, dn));
+            if (zin && (c > hi || c < lo)) livemask |= 1u << k;
+            up = c; c = dn; p += plane;
+        }
     }
+    if (!inside) livemask = 0;
+    const int lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
     // one atomic per warp for all 8 z steps
     int mine = __popc(livemask), incl = mine;
 #pragma unroll
