@@ -186,6 +186,7 @@ struct s3d_ctx {
     int f3_ctas = 0;             // S3D_F3_CTAS: CTAs the one-kernel level aims for (0 = one per SM)
     unsigned long long *d_stamps = nullptr;   // S3D_STAMPS=1
     int z2_vec = 0;              // S3D_Z2_VEC=2|4: columns per thread of the z march (0 = by radius)
+    int tail_a = 3, tail_b = 6, tail_d = 10;   // blocks per SM of orient_a / orient_b / describe (S3D_TAIL_BLOCKS=a,b,d)
     bool serial = false;         // S3D_SERIAL=1: no branches, every kernel on the main stream (standalone kernel times)
     int fused_ctas = 0;          // S3D_FUSED_CTAS: CTAs the fused blur aims for (0 = 2 per SM)
     bool timing = false;         // S3D_STAGE_TIMING=1: no graph, events at stage boundaries of the main stream
@@ -301,6 +302,8 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
     if (stp && stp[0] == '1') CK(cudaMalloc((void **)&ctx->d_stamps, 4 * sizeof(unsigned long long)));
     const char *zv = getenv("S3D_Z2_VEC");
     if (zv) ctx->z2_vec = (atoi(zv) == 2 || atoi(zv) == 4) ? atoi(zv) : 0;
+    const char *tb = getenv("S3D_TAIL_BLOCKS");
+    if (tb) { int a = 0, b = 0, d = 0; if (sscanf(tb, "%d,%d,%d", &a, &b, &d) == 3 && a > 0 && b > 0 && d > 0) { ctx->tail_a = a; ctx->tail_b = b; ctx->tail_d = d; } }
     const char *ser = getenv("S3D_SERIAL");
     if (ser) ctx->serial = (ser[0] == '1');
     const char *f3c = getenv("S3D_F3_CTAS");
@@ -954,15 +957,15 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     // orientation: per keypoint, then per (keypoint, primary direction)
     float eig = prm->eig_thres;
     int *work_b_count = kp_count + 3;
-    orient_a_kernel<<<ctx->sm_count * 3, 256, sizeof(HistSmem), st>>>(p->pyr, p->kps, kp_count, eig, p->kp_nprim, p->kp_eigs,
+    orient_a_kernel<<<ctx->sm_count * ctx->tail_a, 256, sizeof(HistSmem), st>>>(p->pyr, p->kps, kp_count, eig, p->kp_nprim, p->kp_eigs,
                                                                      p->kp_ori0, p->kp_p1, p->kp_patch0, p->work_b, work_b_count);
     mark(ctx, "orient_a");
-    orient_b_kernel<<<ctx->sm_count * 6, 256, sizeof(HistSmem), st>>>(p->work_b, work_b_count, p->kp_p1, p->kp_patch0, p->kp_nsec, p->kp_rots);
+    orient_b_kernel<<<ctx->sm_count * ctx->tail_b, 256, sizeof(HistSmem), st>>>(p->work_b, work_b_count, p->kp_p1, p->kp_patch0, p->kp_nsec, p->kp_rots);
     mark(ctx, "orient_b");
     row_offsets_kernel<<<1, 1024, 0, st>>>(p->kp_nprim, p->kp_nsec, kp_count, p->nrows, p->row_off, p->row_map, n_features, p->row_cap, err);
     float size_factor = 1.0f;
     if (p->double_mode > 0 || p->pre_step_done > 0) size_factor /= 2; else if (p->double_mode < 0 || p->pre_step_done < 0) size_factor *= 2;
-    int grid_d = ctx->sm_count * 10;
+    int grid_d = ctx->sm_count * ctx->tail_d;
     describe_kernel<<<grid_d, 128, sizeof(DescribeSmem), st>>>(p->pyr, p->kps, n_features, p->row_map, p->kp_nsec, p->kp_eigs,
                                                               p->kp_ori0, p->kp_rots, p->kp_patch0, prm->descriptor, size_factor, p->octave_base,
                                                               p->row_cap, p->feats, p->dbg_patches, p->dbg_prerank);

@@ -194,6 +194,26 @@ def run_ours(args):
         cpu = {"value": (n + n2) / (dt + dt2), "unit": "volumes/s", "cores": procs, "kind": cb.kind(),
                "sample": "2 timed rounds x %d volumes (one MNI volume per worker process), 1 warm-up round" % procs}
 
+    # the reference's OWN CUDA path (featExtract -d0, oracle/_ref/featExtract_ref_cuda built from the reference
+    # sources for sm_100a), timed on this GPU before ours: a baseline, not a target and not an oracle
+    ref_cuda = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_cuda_baseline.py"), "--reps", "2", "--timeout", "90"],
+                                 capture_output=True, text=True, timeout=400)
+            r = json.loads(out.stdout.strip().splitlines()[-1])
+            if "d0_best_stage_sum_s" in r:
+                ref_cuda = {"value": 1.0 / r["d0_best_stage_sum_s"], "unit": "volumes/s", "kind": "reference -d0 (CUDA, sm_100a build)",
+                            "stage_sum_s": r["d0_best_stage_sum_s"], "process_wall_s": r["d0_best_wall_s"],
+                            "rows": r["d0_runs"][0].get("rows"), "cpu_rows": (r.get("cpu") or {}).get("rows"),
+                            "single_core_cpu_stage_sum_s": (r.get("cpu") or {}).get("stage_sum_s"),
+                            "sample": "best of 2 CLI runs on one MNI phantom; value = 1 / sum of the reference's own per-stage timers "
+                                      "(pyramid, DoG, detection: excludes its CPU keypoint/descriptor stages, file I/O and CUDA start-up)"}
+            else:
+                ref_cuda = {"unavailable": r.get("unavailable") or str(r.get("d0_runs"))[:200]}
+        except Exception as exc:      # noqa: BLE001
+            ref_cuda = {"unavailable": repr(exc)[:200]}
+
     eng = pkg.Engine(local)
     st = torch.cuda.ExternalStream(eng.stream, device=dev)
     params = pkg.Params()
@@ -354,7 +374,7 @@ def run_ours(args):
                        "keypoints_per_volume": nk, "rows_per_volume": nf},
             "latency_ms_per_volume": lat_ms,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "launches_per_step": launches_per_step, "roofline": roof, "cpu_baseline": cpu,
+            "launches_per_step": launches_per_step, "roofline": roof, "cpu_baseline": cpu, "ref_cuda_baseline": ref_cuda,
         }
         print(json.dumps(line))
     if dist is not None:
