@@ -117,6 +117,7 @@ def _run_slab_octave(engine, api, d_buf, o, z_off, z_global, own0, own1, base_pa
     """One octave of one slab on the engine; returns (features, level, is_max) per row."""
     nz, Y, X = d_buf.shape
     prm = api.Params(descriptor=base_params["descriptor"], eig_thres=base_params["eig_thres"],
+                     max_keypoints=base_params.get("max_keypoints", 0), max_features=base_params.get("max_features", 0),
                      input_is_g0=(o > 0), octave_base=o, max_octaves=1,
                      slab=(z_off, z_global, own0, own1), pre_step_done=base_params["double_mode"])
     engine.extract_device(d_buf, (X, Y, nz), prm)
@@ -171,7 +172,7 @@ def _pre_stepped_dims(shape_zyx, double_mode):
 
 
 def extract_slab(engine, volume, rank=0, world=1, group=None, double_mode=0, descriptor=0, eig_thres=140.0,
-                 halo=SLAB_HALO, emulate_ranks=None):
+                 halo=SLAB_HALO, emulate_ranks=None, max_keypoints=0, max_features=0):
     """featExtract of ONE volume split into z slabs over ``world`` ranks; rank 0 returns the feature rows
     in the reference's order (bit-identical to the whole-volume engine), other ranks return None.
 
@@ -182,7 +183,8 @@ def extract_slab(engine, volume, rank=0, world=1, group=None, double_mode=0, des
     import importlib
     import torch
     api = importlib.import_module("3d_sift_cuda_b200.api")
-    base = {"descriptor": descriptor, "eig_thres": eig_thres, "double_mode": double_mode}
+    base = {"descriptor": descriptor, "eig_thres": eig_thres, "double_mode": double_mode,
+            "max_keypoints": max_keypoints, "max_features": max_features}
     X0, Y0, Z0 = _pre_stepped_dims(volume.shape, double_mode)
     emu = emulate_ranks is not None
     nranks = emulate_ranks if emu else world
@@ -190,7 +192,8 @@ def extract_slab(engine, volume, rank=0, world=1, group=None, double_mode=0, des
     my_ranks = list(range(nranks)) if emu else [rank]
     if nranks == 1 or K == 0:
         if emu or rank == 0:
-            return engine.extract(volume, api.Params(double_mode=double_mode, descriptor=descriptor, eig_thres=eig_thres))
+            return engine.extract(volume, api.Params(double_mode=double_mode, descriptor=descriptor, eig_thres=eig_thres,
+                                                     max_keypoints=max_keypoints, max_features=max_features))
         return None
     if not emu:
         import torch.distributed as dist
@@ -267,7 +270,8 @@ def extract_slab(engine, volume, rank=0, world=1, group=None, double_mode=0, des
         assert tuple(full.shape) == (dims[2], dims[1], dims[0]), (full.shape, dims)
         torch.cuda.synchronize()
         engine.extract_device(full, dims, api.Params(descriptor=descriptor, eig_thres=eig_thres, input_is_g0=True,
-                                                     octave_base=K, pre_step_done=double_mode))
+                                                     octave_base=K, pre_step_done=double_mode,
+                                                     max_keypoints=max_keypoints, max_features=max_features))
         tail = engine.fetch_features()
 
     # ---- rank 0 merges (small: feature rows only)

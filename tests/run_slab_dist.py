@@ -16,19 +16,21 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 shape = tuple(int(v) for v in sys.argv[1:4]) if len(sys.argv) >= 4 else (128, 128, 256)
 dm = int(sys.argv[4]) if len(sys.argv) >= 5 else 0
-vol = pkg.phantom.blob_phantom(shape, 17, 300)
+CAP = 1 << 18      # keypoint capacity: a 512^3 pyramid yields far more than the default 16384
+nblobs = int(os.environ.get("SLAB_BLOBS", "300"))
+vol = pkg.phantom.blob_phantom(shape, 17, nblobs)
 eng = pkg.Engine(local)
 Z0 = shape[2] * (2 if dm == 1 else 1)
 K, bounds = d.slab_plan(Z0, world)
 dist.barrier()
 for it in range(2):
     torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
-    slab = d.extract_slab(eng, vol, rank, world, None, double_mode=dm)
+    slab = d.extract_slab(eng, vol, rank, world, None, double_mode=dm, max_keypoints=CAP, max_features=8 * CAP)
     torch.cuda.synchronize(); dist.barrier(); t_slab = time.perf_counter() - t0
 ok = True
 if rank == 0:
     t0 = time.perf_counter()
-    whole = eng.extract(vol, pkg.Params(double_mode=dm))
+    whole = eng.extract(vol, pkg.Params(double_mode=dm, max_keypoints=CAP, max_features=8 * CAP))
     t_whole = time.perf_counter() - t0
     ok = (len(slab) == len(whole)) and slab.tobytes() == whole.tobytes()
     print("slab mode: world %d, shape %s, double_mode %d, slab octaves K=%d, bounds %s" % (world, shape, dm, K, bounds))
