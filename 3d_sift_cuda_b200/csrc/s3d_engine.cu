@@ -158,6 +158,7 @@ struct Plan {
     cudaGraphExec_t graph = nullptr;
     int graph_descriptor = -1; float graph_eig = 0;
     std::vector<void *> allocs;
+    unsigned long long last_use = 0;
 };
 
 struct s3d_ctx {
@@ -165,7 +166,10 @@ struct s3d_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::string err;
-    Plan *plan = nullptr;
+    Plan *plan = nullptr;               // active plan (one of `plans`)
+    std::vector<Plan *> plans;          // resident plans, least recently used evicted beyond max_plans: a caller that
+    int max_plans = 4;                  // alternates between a few shapes (slab mode: one per octave) keeps its buffers
+    unsigned long long use_clock = 0;   // and instantiated graphs (S3D_PLAN_CACHE)
     int launches = 0;
     int last_launches = 0;
     bool use_graph = true;
@@ -304,6 +308,8 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
     if (zv) ctx->z2_vec = (atoi(zv) == 2 || atoi(zv) == 4) ? atoi(zv) : 0;
     const char *tb = getenv("S3D_TAIL_BLOCKS");
     if (tb) { int a = 0, b = 0, d = 0; if (sscanf(tb, "%d,%d,%d", &a, &b, &d) == 3 && a > 0 && b > 0 && d > 0) { ctx->tail_a = a; ctx->tail_b = b; ctx->tail_d = d; } }
+    const char *pc = getenv("S3D_PLAN_CACHE");
+    if (pc && atoi(pc) >= 1) ctx->max_plans = atoi(pc);
     const char *ser = getenv("S3D_SERIAL");
     if (ser) ctx->serial = (ser[0] == '1');
     const char *f3c = getenv("S3D_F3_CTAS");
@@ -320,15 +326,22 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
 extern "C" s3d_status s3d_ctx_create(int device, s3d_ctx **ctx) { return ctx_create(device, nullptr, false, ctx); }
 extern "C" s3d_status s3d_ctx_create_on_stream(int device, void *stream, s3d_ctx **ctx) { return ctx_create(device, stream, true, ctx); }
 
-static void plan_free(s3d_ctx *ctx)
+static void plan_destroy(s3d_ctx *ctx, Plan *p)
 {
-    Plan *p = ctx->plan;
     if (!p) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (p->graph) cudaGraphExecDestroy(p->graph);
     for (void *a : p->allocs) cudaFree(a);
+    for (size_t i = 0; i < ctx->plans.size(); i++)
+        if (ctx->plans[i] == p) { ctx->plans.erase(ctx->plans.begin() + i); break; }
+    if (ctx->plan == p) { ctx->plan = nullptr; ctx->has_result = false; }
     delete p;
+}
+
+static void plan_free(s3d_ctx *ctx)     // every resident plan
+{
+    while (!ctx->plans.empty()) plan_destroy(ctx, ctx->plans.back());
     ctx->plan = nullptr;
     ctx->has_result = false;
 }
@@ -672,20 +685,53 @@ static cudaError_t plan_alloc(Plan *p, T **ptr, size_t count)
     return cudaSuccess;
 }
 
+static bool plan_matches(const Plan *old, int X, int Y, int Z, const s3d_params *prm, int kp_cap, int row_cap)
+{
+    return old && old->X == X && old->Y == Y && old->Z == Z && old->double_mode == prm->double_mode &&
+           old->kp_cap == kp_cap && old->row_cap == row_cap && old->keep_patches == (prm->keep_patches ? 1 : 0) &&
+           old->input_is_g0 == prm->input_is_g0 && old->octave_base == prm->octave_base && old->max_octaves == prm->max_octaves &&
+           old->slab == prm->slab && old->z_off == prm->z_off && old->z_global == prm->z_global &&
+           old->own_z0 == prm->own_z0 && old->own_z1 == prm->own_z1 && old->pre_step_done == prm->pre_step_done;
+}
+
+static s3d_status plan_fill(s3d_ctx *ctx, Plan *p, int X, int Y, int Z, const s3d_params *prm, int kp_cap, int row_cap);
+
+// Make the plan for (shape, options) the active one: the active plan, a resident one, or a new one (the least
+// recently used resident plan is released first when max_plans are resident).
 static s3d_status plan_build(s3d_ctx *ctx, int X, int Y, int Z, const s3d_params *prm)
 {
     int kp_cap = prm->max_keypoints > 0 ? prm->max_keypoints : 16384;
     int row_cap = prm->max_features > 0 ? prm->max_features : 8 * kp_cap;
-    Plan *old = ctx->plan;
-    if (old && old->X == X && old->Y == Y && old->Z == Z && old->double_mode == prm->double_mode &&
-        old->kp_cap == kp_cap && old->row_cap == row_cap && old->keep_patches == (prm->keep_patches ? 1 : 0) &&
-        old->input_is_g0 == prm->input_is_g0 && old->octave_base == prm->octave_base && old->max_octaves == prm->max_octaves &&
-        old->slab == prm->slab && old->z_off == prm->z_off && old->z_global == prm->z_global &&
-        old->own_z0 == prm->own_z0 && old->own_z1 == prm->own_z1 && old->pre_step_done == prm->pre_step_done)
-        return S3D_OK;
-    plan_free(ctx);
+    ctx->use_clock++;
+    if (plan_matches(ctx->plan, X, Y, Z, prm, kp_cap, row_cap)) { ctx->plan->last_use = ctx->use_clock; return S3D_OK; }
+    for (Plan *q : ctx->plans)
+        if (plan_matches(q, X, Y, Z, prm, kp_cap, row_cap)) {
+            ctx->plan = q;
+            ctx->has_result = false;
+            q->last_use = ctx->use_clock;
+            return S3D_OK;
+        }
+    while ((int)ctx->plans.size() >= (ctx->max_plans > 1 ? ctx->max_plans : 1)) {
+        Plan *lru = ctx->plans[0];
+        for (Plan *q : ctx->plans) if (q->last_use < lru->last_use) lru = q;
+        plan_destroy(ctx, lru);
+    }
     Plan *p = new Plan();
+    p->last_use = ctx->use_clock;
+    ctx->plans.push_back(p);
     ctx->plan = p;
+    ctx->has_result = false;
+    s3d_status st = plan_fill(ctx, p, X, Y, Z, prm, kp_cap, row_cap);
+    if (st != S3D_OK) {       // never leave a half-built plan behind (its key would match the next call)
+        std::string msg = ctx->err;
+        plan_destroy(ctx, p);
+        ctx->err = msg;
+    }
+    return st;
+}
+
+static s3d_status plan_fill(s3d_ctx *ctx, Plan *p, int X, int Y, int Z, const s3d_params *prm, int kp_cap, int row_cap)
+{
     p->X = X; p->Y = Y; p->Z = Z; p->double_mode = prm->double_mode;
     p->kp_cap = kp_cap; p->row_cap = row_cap; p->keep_patches = prm->keep_patches ? 1 : 0;
     p->input_is_g0 = prm->input_is_g0; p->octave_base = prm->octave_base; p->max_octaves = prm->max_octaves;

@@ -315,3 +315,18 @@ def test_batch_matches_single_volume_extraction(pkg, engine):
         assert b.extract([]) == []
     finally:
         b.close()
+
+
+def test_plan_cache_keeps_results_identical(pkg, engine):
+    """A context keeps a few plans resident (S3D_PLAN_CACHE, default 4): alternating between shapes, and
+    evicting beyond the cache size, must give the same rows as the first visit of each shape."""
+    shapes = [(64, 56, 48), (40, 44, 52), (64, 56, 48), (33, 47, 41), (72, 40, 36), (40, 44, 52), (50, 50, 50), (64, 56, 48)]
+    first = {}
+    for k, sh in enumerate(shapes):
+        vol = pkg.phantom.blob_phantom(sh, 11, 40)
+        rows = engine.extract(vol)
+        if sh in first:
+            assert rows.tobytes() == first[sh].tobytes(), (k, sh)
+        else:
+            first[sh] = rows
+            assert len(rows) > 0
