@@ -192,7 +192,12 @@ __device__ __forceinline__ void z2_step(VT (&acc)[2 * R + 1], const int S, const
         }
 }
 
-template <int R> struct Z2Cfg { static constexpr int T = 2 * R + 1; static constexpr int P = (T < 6) ? T - 1 : 6; };   // P: prefetch distance (steps)
+#ifndef S3D_Z2_PREFETCH_WIDE
+#define S3D_Z2_PREFETCH_WIDE 10
+#endif
+// P: prefetch distance in steps (planes in flight per thread and stream); wide radii hold 148+ registers per thread
+// (12 warps per SM), so they need more loads in flight per thread to cover the HBM latency
+template <int R> struct Z2Cfg { static constexpr int T = 2 * R + 1; static constexpr int P = (T < 6) ? T - 1 : (R >= 5 ? S3D_Z2_PREFETCH_WIDE : 6); };
 
 template <int R, bool DOG, bool FIRST, bool FAST, typename VT>
 __device__ __forceinline__ void z2_round(VT (&acc)[2 * R + 1], VT (&vin)[2 * R + 1], VT (&pv)[2 * R + 1],

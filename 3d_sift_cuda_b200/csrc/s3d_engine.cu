@@ -168,7 +168,7 @@ struct s3d_ctx {
     std::string err;
     Plan *plan = nullptr;               // active plan (one of `plans`)
     std::vector<Plan *> plans;          // resident plans, least recently used evicted beyond max_plans: a caller that
-    int max_plans = 4;                  // alternates between a few shapes (slab mode: one per octave) keeps its buffers
+    int max_plans = 6;                  // alternates between a few shapes (slab mode: one per octave) keeps its buffers
     unsigned long long use_clock = 0;   // and instantiated graphs (S3D_PLAN_CACHE)
     int launches = 0;
     int last_launches = 0;
