@@ -36,7 +36,11 @@ EXPORTS = [
     "s3d_copy_level_device", "s3d_get_row_keypoints",
     "s3d_batch_create", "s3d_batch_destroy", "s3d_batch_last_error", "s3d_batch_extract", "s3d_batch_extract_device",
     "s3d_batch_launches_per_volume", "s3d_host_alloc", "s3d_host_free",
+    "s3d_extract_typed", "s3d_extract_typed_async", "s3d_batch_extract_typed",
 ]
+
+# NIfTI datatype codes accepted by the typed entry points (reference featExtract.cpp:18-77)
+DTYPE_CODES = {"uint8": 2, "int16": 4, "int32": 8, "float32": 16, "float64": 64, "int8": 256, "uint16": 512, "uint32": 768}
 
 
 class S3DError(RuntimeError):
@@ -123,6 +127,9 @@ def load_library():
     L.s3d_batch_extract.argtypes = [vp, C.POINTER(vp), i, i, i, i, vp, C.POINTER(vp), C.POINTER(i)]
     L.s3d_batch_extract_device.argtypes = [vp, C.POINTER(vp), i, i, i, i, vp, C.POINTER(i), C.POINTER(i)]
     L.s3d_batch_launches_per_volume.argtypes = [vp]
+    L.s3d_extract_typed.argtypes = [vp, vp, i, i, i, i, vp, C.POINTER(vp), C.POINTER(i)]
+    L.s3d_extract_typed_async.argtypes = [vp, vp, i, i, i, i, vp]
+    L.s3d_batch_extract_typed.argtypes = [vp, C.POINTER(vp), i, i, i, i, i, vp, C.POINTER(vp), C.POINTER(i)]
     L.s3d_host_alloc.argtypes = [C.c_size_t]
     L.s3d_host_alloc.restype = vp
     L.s3d_host_free.argtypes = [vp]
@@ -207,6 +214,18 @@ class Engine:
         out, n = C.c_void_p(), C.c_int()
         self._ck(self.L.s3d_extract(self.ctx, v.ctypes.data_as(C.c_void_p), X, Y, Z, C.byref(params.c),
                                     C.byref(out), C.byref(n)), "s3d_extract")
+        return _copy_out(out, n.value, FEATURE_DTYPE, self.L.s3d_free)
+
+    def extract_typed(self, volume, params=None):
+        """Host volume of any NIfTI scalar dtype (numpy (Z, Y, X)): raw voxels go over PCIe, the cast to float
+        runs on the device (s3d_extract_typed) -- same rows as extract(volume.astype(float32))."""
+        params = params or Params()
+        v = np.ascontiguousarray(volume)
+        code = DTYPE_CODES[v.dtype.name]
+        Z, Y, X = v.shape
+        out, n = C.c_void_p(), C.c_int()
+        self._ck(self.L.s3d_extract_typed(self.ctx, v.ctypes.data_as(C.c_void_p), code, X, Y, Z, C.byref(params.c),
+                                          C.byref(out), C.byref(n)), "s3d_extract_typed")
         return _copy_out(out, n.value, FEATURE_DTYPE, self.L.s3d_free)
 
     def extract_device(self, d_volume, shape_xyz, params=None):
@@ -370,6 +389,22 @@ class Batch:
         cnt = (C.c_int * n)()
         self._ck(self.L.s3d_batch_extract(self.b, self._ptrs(h_volumes), n, X, Y, Z, C.byref(params.c), rows, cnt),
                  "s3d_batch_extract")
+        return [_copy_out(C.c_void_p(rows[k]), cnt[k], FEATURE_DTYPE, self.L.s3d_free) for k in range(n)]
+
+    def extract_typed(self, h_volumes, params=None):
+        """Like extract() for host volumes of one NIfTI scalar dtype (numpy arrays or pinned torch tensors)."""
+        params = params or Params()
+        n = len(h_volumes)
+        if n == 0:
+            return []
+        v0 = h_volumes[0]
+        name = str(v0.dtype).replace("torch.", "")
+        code = DTYPE_CODES[name]
+        Z, Y, X = v0.shape
+        rows = (C.c_void_p * n)()
+        cnt = (C.c_int * n)()
+        self._ck(self.L.s3d_batch_extract_typed(self.b, self._ptrs(h_volumes), code, n, X, Y, Z, C.byref(params.c), rows, cnt),
+                 "s3d_batch_extract_typed")
         return [_copy_out(C.c_void_p(rows[k]), cnt[k], FEATURE_DTYPE, self.L.s3d_free) for k in range(n)]
 
     def extract_device(self, d_volumes, shape_xyz, params=None):

@@ -163,9 +163,18 @@ int main(int argc, char **argv)
         memset(&im.qto_xyz, 0, sizeof(Mat44));
         im.qto_xyz.m[0][0] = im.qto_xyz.m[1][1] = im.qto_xyz.m[2][2] = im.qto_xyz.m[3][3] = 1.0f;
         im.sto_xyz = im.qto_xyz;
-    } else if (niftimin::read(inPath, im) < 0) {
+    } else if (niftimin::read(inPath, im, /*keep_raw=*/true) < 0) {
         printf("Error: could not read input file: %s\n", inPath);
         return -1;
+    }
+    // NIfTI voxels stay in their file datatype when they can go to the device as they are (the cast to float
+    // then runs there, s3d_extract_typed); the host-side isotropic resampling needs floats
+    const bool need_iso = bIso && (im.dx != im.dy || im.dy != im.dz || im.dx != im.dz);
+    const bool typed = !im.raw.empty() && !need_iso && im.datatype != 16;
+    if (!im.raw.empty() && !typed) {
+        im.data.resize((size_t)im.nx * im.ny * im.nz * im.nt);
+        niftimin::cast_to_float(im.raw.data(), im.datatype, im.data.size(), im.data.data());
+        im.raw.clear();
     }
 
     int X = im.nx, Y = im.ny, Z = im.nz;
@@ -189,7 +198,7 @@ int main(int argc, char **argv)
                     vol[((size_t)z * nY + y) * nX + x] = trilinear(im.data.data(), X, Y, Z, (float)(x * rf[0] + 0.5), (float)(y * rf[1] + 0.5), (float)(z * rf[2] + 0.5));
         X = nX; Y = nY; Z = nZ;
         im.dx = im.dy = im.dz = fMin;
-    } else {
+    } else if (!typed) {
         vol.assign(im.data.begin(), im.data.begin() + (size_t)X * Y * Z);
     }
     int eX = X, eY = Y, eZ = Z;   // extraction resolution (after -2+/-2-)
@@ -208,11 +217,15 @@ int main(int argc, char **argv)
     prm.double_mode = bDouble; prm.descriptor = descriptor; prm.eig_thres = fEigThres;
     s3d_feature *feats = nullptr;
     int n = 0;
-    s3d_status st = s3d_extract(ctx, vol.data(), X, Y, Z, &prm, &feats, &n);
+    auto run = [&]() {
+        return typed ? s3d_extract_typed(ctx, im.raw.data(), im.datatype, X, Y, Z, &prm, &feats, &n)
+                     : s3d_extract(ctx, vol.data(), X, Y, Z, &prm, &feats, &n);
+    };
+    s3d_status st = run();
     if (st == S3D_ERR_CAPACITY) {   // retry once with room for a very dense volume
         prm.max_keypoints = 1 << 18;
         prm.max_features = 1 << 21;
-        st = s3d_extract(ctx, vol.data(), X, Y, Z, &prm, &feats, &n);
+        st = run();
     }
     if (st != S3D_OK) {
         printf("Error: could not extract features, %s.\n", st == S3D_ERR_NOMEM ? "insufficient memory" : s3d_last_error(ctx));

@@ -23,7 +23,9 @@ struct Image {
     float dx = 1, dy = 1, dz = 1;
     int qform_code = 0, sform_code = 0;
     Mat44 qto_xyz, sto_xyz;
-    std::vector<float> data;   // x fastest
+    std::vector<float> data;   // x fastest (filled by to_float(); read() fills it unless keep_raw)
+    std::vector<unsigned char> raw;   // voxels in the file's datatype, host byte order (keep_raw only)
+    int datatype = 16;         // NIfTI datatype code of `raw`
 };
 
 static inline void swap_bytes(void *p, size_t size, size_t count)
@@ -81,7 +83,24 @@ static inline bool ends_with(const std::string &s, const char *suf)
 }
 
 // returns 0 on success, <0 on failure (like fioReadNifti's negative codes)
-static inline int read(const std::string &path, Image &img)
+// plain casts, as reg_changeDatatype1 does (reference featExtract.cpp:18-77)
+static inline void cast_to_float(const void *raw, int datatype, size_t nvox, float *o)
+{
+    switch (datatype) {
+    case 2:   for (size_t i = 0; i < nvox; i++) o[i] = (float)((const unsigned char *)raw)[i]; break;
+    case 256: for (size_t i = 0; i < nvox; i++) o[i] = (float)((const signed char *)raw)[i]; break;
+    case 4:   for (size_t i = 0; i < nvox; i++) o[i] = (float)((const short *)raw)[i]; break;
+    case 512: for (size_t i = 0; i < nvox; i++) o[i] = (float)((const unsigned short *)raw)[i]; break;
+    case 8:   for (size_t i = 0; i < nvox; i++) o[i] = (float)((const int *)raw)[i]; break;
+    case 768: for (size_t i = 0; i < nvox; i++) o[i] = (float)((const unsigned int *)raw)[i]; break;
+    case 16:  memcpy(o, raw, nvox * 4); break;
+    case 64:  for (size_t i = 0; i < nvox; i++) o[i] = (float)((const double *)raw)[i]; break;
+    }
+}
+
+// keep_raw: leave the voxels in their file datatype in img.raw (for the typed C-ABI entry point, which casts
+// on the device) instead of converting to float here
+static inline int read(const std::string &path, Image &img, bool keep_raw = false)
 {
     std::string hdr_path = path, img_path = path;
     if (ends_with(path, ".img")) hdr_path = path.substr(0, path.size() - 4) + ".hdr";
@@ -160,18 +179,13 @@ static inline int read(const std::string &path, Image &img)
     gzclose(f);
     if (got != raw.size()) return -2;
     if (swp && bpv > 1) swap_bytes(raw.data(), bpv, nvox);
-    img.data.resize(nvox);
-    float *o = img.data.data();
-    switch (datatype) {   // plain casts, as reg_changeDatatype1 does
-    case 2:   for (size_t i = 0; i < nvox; i++) o[i] = (float)((const unsigned char *)raw.data())[i]; break;
-    case 256: for (size_t i = 0; i < nvox; i++) o[i] = (float)((const char *)raw.data())[i]; break;
-    case 4:   for (size_t i = 0; i < nvox; i++) o[i] = (float)((const short *)raw.data())[i]; break;
-    case 512: for (size_t i = 0; i < nvox; i++) o[i] = (float)((const unsigned short *)raw.data())[i]; break;
-    case 8:   for (size_t i = 0; i < nvox; i++) o[i] = (float)((const int *)raw.data())[i]; break;
-    case 768: for (size_t i = 0; i < nvox; i++) o[i] = (float)((const unsigned int *)raw.data())[i]; break;
-    case 16:  memcpy(o, raw.data(), nvox * 4); break;
-    case 64:  for (size_t i = 0; i < nvox; i++) o[i] = (float)((const double *)raw.data())[i]; break;
+    img.datatype = datatype;
+    if (keep_raw) {
+        img.raw.swap(raw);
+        return 0;
     }
+    img.data.resize(nvox);
+    cast_to_float(raw.data(), datatype, nvox, img.data.data());
     return 0;
 }
 

@@ -134,6 +134,8 @@ struct Plan {
     int kp_cap = 0, row_cap = 0, cand_cap = 0, keep_patches = 0;
     int n_oct = 0;
     Vol stage;                   // dense copy of the input (pitch == X)
+    void *raw_stage = nullptr;   // typed input as it crossed PCIe (allocated on first use, raw_bytes large)
+    size_t raw_bytes = 0;
     Vol img0;                    // pre-stepped, pitched input of the pyramid
     std::vector<Vol> g, d;       // [oct*6 + level], [oct*5 + level]
     float *tmp1 = nullptr;            // scratch of the initial blur (octave-0 size)
@@ -1079,10 +1081,58 @@ static s3d_status run_pipeline(s3d_ctx *ctx, const s3d_params *prm)
 
 // Bring the caller's dense volume into the plan: straight into the pitched pyramid input (or level 0)
 // with a strided copy when no resize pre-step is needed, else into the dense staging buffer.
-static s3d_status stage_input(s3d_ctx *ctx, const float *src, bool from_host)
+static int dtype_bytes(int dtype)
+{
+    switch (dtype) {
+    case S3D_DT_UINT8: case S3D_DT_INT8: return 1;
+    case S3D_DT_INT16: case S3D_DT_UINT16: return 2;
+    case S3D_DT_INT32: case S3D_DT_UINT32: case S3D_DT_FLOAT32: return 4;
+    case S3D_DT_FLOAT64: return 8;
+    default: return 0;
+    }
+}
+
+template <typename T>
+static void launch_convert(s3d_ctx *ctx, const void *src, int X, size_t rows, float *dst, int pitch)
+{
+    const size_t row_blocks = (rows + 3) / 4, max_blocks = (size_t)ctx->sm_count * 16;
+    dim3 block(64, 4), grid((pitch + 255) / 256, (unsigned)(row_blocks < max_blocks ? row_blocks : max_blocks));
+    convert_rows_kernel<T><<<grid, block, 0, ctx->stream>>>((const T *)src, X, (long long)rows, dst, pitch);
+}
+
+static s3d_status stage_input(s3d_ctx *ctx, const void *src_any, bool from_host, int dtype = S3D_DT_FLOAT32)
 {
     Plan *p = ctx->plan;
-    size_t row = sizeof(float) * (size_t)p->X, rows = (size_t)p->Y * p->Z;
+    size_t rows = (size_t)p->Y * p->Z;
+    if (dtype != S3D_DT_FLOAT32) {
+        // typed host input: raw bytes over PCIe, cast + re-pitch on the device (dense when a resize pre-step follows)
+        const int bpv = dtype_bytes(dtype);
+        if (bpv == 0 || !from_host) return fail(ctx, S3D_ERR_INVALID, "unsupported input datatype");
+        const size_t bytes = (size_t)bpv * p->X * rows;
+        if (p->raw_bytes < bytes) {
+            void *q = nullptr;
+            cudaError_t e = cudaMalloc(&q, bytes + 256);
+            if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e); cudaGetLastError(); return S3D_ERR_NOMEM; }
+            p->allocs.push_back(q);
+            p->raw_stage = q;
+            p->raw_bytes = bytes;
+        }
+        CK(cudaMemcpyAsync(p->raw_stage, src_any, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        Vol &dst = (p->double_mode != 0) ? p->stage : (p->input_is_g0 ? (p->n_oct > 0 ? p->g[0] : p->img0) : p->img0);
+        switch (dtype) {
+        case S3D_DT_UINT8: launch_convert<unsigned char>(ctx, p->raw_stage, p->X, rows, dst.p, dst.pitch); break;
+        case S3D_DT_INT8: launch_convert<signed char>(ctx, p->raw_stage, p->X, rows, dst.p, dst.pitch); break;
+        case S3D_DT_INT16: launch_convert<short>(ctx, p->raw_stage, p->X, rows, dst.p, dst.pitch); break;
+        case S3D_DT_UINT16: launch_convert<unsigned short>(ctx, p->raw_stage, p->X, rows, dst.p, dst.pitch); break;
+        case S3D_DT_INT32: launch_convert<int>(ctx, p->raw_stage, p->X, rows, dst.p, dst.pitch); break;
+        case S3D_DT_UINT32: launch_convert<unsigned int>(ctx, p->raw_stage, p->X, rows, dst.p, dst.pitch); break;
+        default: launch_convert<double>(ctx, p->raw_stage, p->X, rows, dst.p, dst.pitch); break;
+        }
+        CK(cudaGetLastError());
+        return S3D_OK;
+    }
+    const float *src = (const float *)src_any;
+    size_t row = sizeof(float) * (size_t)p->X;
     if (p->double_mode != 0) {
         CK(cudaMemcpyAsync(p->stage.p, src, row * rows, from_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
         return S3D_OK;
@@ -1123,6 +1173,20 @@ extern "C" s3d_status s3d_extract_host_async(s3d_ctx *ctx, const float *h_volume
     s = plan_build(ctx, X, Y, Z, prm);
     if (s != S3D_OK) return s;
     s = stage_input(ctx, h_volume, true);
+    if (s != S3D_OK) return s;
+    return run_pipeline(ctx, prm);
+}
+
+extern "C" s3d_status s3d_extract_typed_async(s3d_ctx *ctx, const void *h_volume, int dtype, int X, int Y, int Z, const s3d_params *prm)
+{
+    if (dtype == S3D_DT_FLOAT32) return s3d_extract_host_async(ctx, (const float *)h_volume, X, Y, Z, prm);
+    s3d_status s = check_params(ctx, (const float *)h_volume, X, Y, Z, prm);
+    if (s != S3D_OK) return s;
+    if (dtype_bytes(dtype) == 0) return fail(ctx, S3D_ERR_INVALID, "unsupported input datatype");
+    CK(cudaSetDevice(ctx->device));
+    s = plan_build(ctx, X, Y, Z, prm);
+    if (s != S3D_OK) return s;
+    s = stage_input(ctx, h_volume, true, dtype);
     if (s != S3D_OK) return s;
     return run_pipeline(ctx, prm);
 }
@@ -1192,6 +1256,15 @@ extern "C" s3d_status s3d_extract(s3d_ctx *ctx, const float *h_volume, int X, in
     return s3d_fetch_features(ctx, out, n_out);
 }
 
+extern "C" s3d_status s3d_extract_typed(s3d_ctx *ctx, const void *h_volume, int dtype, int X, int Y, int Z, const s3d_params *prm,
+                                        s3d_feature **out, int *n_out)
+{
+    if (!out || !n_out) return S3D_ERR_INVALID;
+    s3d_status s = s3d_extract_typed_async(ctx, h_volume, dtype, X, Y, Z, prm);
+    if (s != S3D_OK) return s;
+    return s3d_fetch_features(ctx, out, n_out);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // batch level: n_contexts extraction contexts on one device, fed round-robin
 // ---------------------------------------------------------------------------------------------------
@@ -1234,8 +1307,8 @@ extern "C" const char *s3d_batch_last_error(const s3d_batch *b) { return b ? b->
 extern "C" int s3d_batch_launches_per_volume(s3d_batch *b) { return b ? b->launches : 0; }
 
 // volume i runs on context i % n; before a context is reused its previous volume is collected
-static s3d_status batch_run(s3d_batch *b, const float *const *vols, int n, int X, int Y, int Z, const s3d_params *prm,
-                            bool from_host, s3d_feature **rows, int *n_rows, int *n_kps)
+static s3d_status batch_run(s3d_batch *b, const void *const *vols, int n, int X, int Y, int Z, const s3d_params *prm,
+                            bool from_host, int dtype, s3d_feature **rows, int *n_rows, int *n_kps)
 {
     if (!b || !vols || n < 0 || !prm) return S3D_ERR_INVALID;
     const int nc = (int)b->ctx.size();
@@ -1264,8 +1337,8 @@ static s3d_status batch_run(s3d_batch *b, const float *const *vols, int n, int X
         const int c = i % nc;
         s3d_status st = collect(c);
         if (st == S3D_OK)
-            st = from_host ? s3d_extract_host_async(b->ctx[c], vols[i], X, Y, Z, prm)
-                           : s3d_extract_device(b->ctx[c], vols[i], X, Y, Z, prm);
+            st = from_host ? s3d_extract_typed_async(b->ctx[c], vols[i], dtype, X, Y, Z, prm)
+                           : s3d_extract_device(b->ctx[c], (const float *)vols[i], X, Y, Z, prm);
         if (st != S3D_OK) { if (b->err.empty() || st != S3D_OK) b->err = b->ctx[c]->err; first_err = st; break; }
         pending[c] = i;
     }
@@ -1283,13 +1356,21 @@ extern "C" s3d_status s3d_batch_extract(s3d_batch *b, const float *const *h_volu
 {
     if (!rows || !n_rows) return S3D_ERR_INVALID;
     for (int i = 0; i < n_volumes; i++) { rows[i] = nullptr; n_rows[i] = 0; }
-    return batch_run(b, h_volumes, n_volumes, X, Y, Z, prm, true, rows, n_rows, nullptr);
+    return batch_run(b, (const void *const *)h_volumes, n_volumes, X, Y, Z, prm, true, S3D_DT_FLOAT32, rows, n_rows, nullptr);
+}
+
+extern "C" s3d_status s3d_batch_extract_typed(s3d_batch *b, const void *const *h_volumes, int dtype, int n_volumes, int X, int Y, int Z,
+                                              const s3d_params *prm, s3d_feature **rows, int *n_rows)
+{
+    if (!rows || !n_rows) return S3D_ERR_INVALID;
+    for (int i = 0; i < n_volumes; i++) { rows[i] = nullptr; n_rows[i] = 0; }
+    return batch_run(b, h_volumes, n_volumes, X, Y, Z, prm, true, dtype, rows, n_rows, nullptr);
 }
 
 extern "C" s3d_status s3d_batch_extract_device(s3d_batch *b, const float *const *d_volumes, int n_volumes, int X, int Y, int Z,
                                                const s3d_params *prm, int *n_keypoints, int *n_rows)
 {
-    return batch_run(b, d_volumes, n_volumes, X, Y, Z, prm, false, nullptr, n_rows, n_keypoints);
+    return batch_run(b, (const void *const *)d_volumes, n_volumes, X, Y, Z, prm, false, S3D_DT_FLOAT32, nullptr, n_rows, n_keypoints);
 }
 
 extern "C" void *s3d_host_alloc(size_t bytes)

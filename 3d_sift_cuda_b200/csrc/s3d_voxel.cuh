@@ -319,6 +319,26 @@ __global__ void pad_rows_kernel(const float *__restrict__ in, int X, long long r
     }
 }
 
+// Typed input (NIfTI scalar datatypes): the reference converts every voxel to float with a plain C cast on the
+// host before anything else (reg_changeDatatype1, R/featExtract/featExtract.cpp:18-77).  Here the raw voxels
+// cross PCIe in their file datatype and the cast is fused into the re-pitch; int -> float and double -> float
+// casts round to nearest even on both sides, so the result is the same bits.
+template <typename T>
+__global__ void convert_rows_kernel(const T *__restrict__ in, int X, long long rows, float *__restrict__ out, int pitch)
+{
+    for (long long row = blockIdx.y * blockDim.y + threadIdx.y; row < rows; row += (long long)gridDim.y * blockDim.y) {
+        const T *src = in + row * X;
+        float *dst = out + row * pitch;
+        for (int x0 = blockIdx.x * 256 + threadIdx.x; x0 < pitch; x0 += gridDim.x * 256) {
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const int x = x0 + 64 * j; v[j] = (x < X) ? (float)src[x] : 0.0f; }
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const int x = x0 + 64 * j; if (x < pitch) dst[x] = v[j]; }
+        }
+    }
+}
+
 __global__ void unpad_rows_kernel(const float *__restrict__ in, int pitch, long long rows, float *__restrict__ out, int X)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

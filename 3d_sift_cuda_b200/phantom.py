@@ -61,17 +61,23 @@ def brain_phantom(shape_xyz=(182, 218, 182), seed=1, nblobs=400):
     return np.ascontiguousarray(vol.astype(np.float32))
 
 
-def write_nifti(path, vol, pixdim=(1.0, 1.0, 1.0), qoffset=None, quatern=(0.0, 0.0, 0.0)):
-    """Minimal single-file NIfTI-1 (.nii): 348-byte header + 4 pad bytes, float32, vox_offset 352.
-    With ``qoffset`` the qform (code 1) is written from ``quatern`` (b, c, d) and the offsets."""
+_NIFTI_CODES = {"uint8": (2, 8), "int16": (4, 16), "int32": (8, 32), "float32": (16, 32), "float64": (64, 64),
+                "int8": (256, 8), "uint16": (512, 16), "uint32": (768, 32)}
+
+
+def write_nifti(path, vol, pixdim=(1.0, 1.0, 1.0), qoffset=None, quatern=(0.0, 0.0, 0.0), dtype=np.float32):
+    """Minimal single-file NIfTI-1 (.nii): 348-byte header + 4 pad bytes, vox_offset 352, voxels stored as
+    ``dtype`` (float32 unless given).  With ``qoffset`` the qform (code 1) is written from ``quatern``
+    (b, c, d) and the offsets."""
     import struct
-    vol = np.ascontiguousarray(vol, dtype=np.float32)
+    vol = np.ascontiguousarray(vol, dtype=dtype)
+    code, bitpix = _NIFTI_CODES[vol.dtype.name]
     Z, Y, X = vol.shape
     h = bytearray(348)
     struct.pack_into("<i", h, 0, 348)
     struct.pack_into("<8h", h, 40, 3, X, Y, Z, 1, 1, 1, 1)
-    struct.pack_into("<h", h, 70, 16)      # datatype float32
-    struct.pack_into("<h", h, 72, 32)      # bitpix
+    struct.pack_into("<h", h, 70, code)    # datatype
+    struct.pack_into("<h", h, 72, bitpix)  # bitpix
     struct.pack_into("<8f", h, 76, 1.0, pixdim[0], pixdim[1], pixdim[2], 1.0, 1.0, 1.0, 1.0)
     struct.pack_into("<f", h, 108, 352.0)  # vox_offset
     struct.pack_into("<f", h, 112, 1.0)    # scl_slope

@@ -289,6 +289,16 @@ def run_ours(args):
     e2e = {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": N0 * 4,
            "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps,
            "note": "s3d_batch_extract with %d contexts per GPU: pinned H2D of every volume and D2H of its rows inside the timed region" % nctx}
+    # typed input: the same phantoms stored as int16, the commonest NIfTI datatype of MNI-space
+    # images -- raw voxels cross PCIe (14.4 MB per volume), the cast to float runs on the device
+    i16_vols = [torch.from_numpy(np.rint(v).astype(np.int16)).pin_memory() for v in vols]
+    batch.extract_typed([i16_vols[i % npool] for i in range(max(4, 2 * nctx))], params)
+    iseq = [i16_vols[i % npool] for i in range(args.steps)]
+    i16_ms, irows = timed(lambda: batch.extract_typed(iseq, params))
+    e2e_i16 = {"value": world * args.steps / (i16_ms * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": N0 * 2,
+               "d2h_bytes_per_step": sum(r.nbytes + 12 for r in irows) // args.steps, "ms_per_step": i16_ms / args.steps,
+               "note": "s3d_batch_extract_typed, int16 voxels (phantom rounded to integers: a different input than the float32 "
+                       "runs, same shape and content), %d contexts per GPU" % nctx}
     # same thing strictly one step at a time (latency of a single featExtract-style call with host buffers)
     barrier()
     t0 = time.perf_counter()
@@ -384,7 +394,7 @@ def run_ours(args):
                              "owns a 0.44 GB pyramid; the one-volume latency below flushes L2 (256 MiB write) between steps",
                        "keypoints_per_volume": nk, "rows_per_volume": nf},
             "latency_ms_per_volume": lat_ms,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks, "e2e": e2e, "e2e_int16": e2e_i16, "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step, "roofline": roof, "cpu_baseline": cpu, "ref_cuda_baseline": ref_cuda,
         }
         print(json.dumps(line))

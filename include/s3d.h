@@ -165,6 +165,18 @@ s3d_status s3d_extract_device(s3d_ctx *ctx, const float *d_volume, int X, int Y,
  * asynchronously, then run s3d_extract_device on it. */
 s3d_status s3d_extract_host_async(s3d_ctx *ctx, const float *h_volume, int X, int Y, int Z,
                                   const s3d_params *params);
+/* Typed input (sect. 8(f) N1): h_volume holds X*Y*Z voxels of a NIfTI scalar datatype (the codes of nifti1.h).
+ * The reference converts them to float on the host with a plain cast (reg_changeDatatype1,
+ * R/featExtract/featExtract.cpp:18-77) before fioReadNifti returns; here the raw voxels cross PCIe as they are
+ * (1, 2, 4 or 8 bytes per voxel) and the cast is fused into the device-side re-pitch -- same bits, less traffic. */
+typedef enum {
+    S3D_DT_UINT8 = 2, S3D_DT_INT16 = 4, S3D_DT_INT32 = 8, S3D_DT_FLOAT32 = 16, S3D_DT_FLOAT64 = 64,
+    S3D_DT_INT8 = 256, S3D_DT_UINT16 = 512, S3D_DT_UINT32 = 768
+} s3d_dtype;
+s3d_status s3d_extract_typed(s3d_ctx *ctx, const void *h_volume, int dtype, int X, int Y, int Z,
+                             const s3d_params *params, s3d_feature **out, int *n_out);
+s3d_status s3d_extract_typed_async(s3d_ctx *ctx, const void *h_volume, int dtype, int X, int Y, int Z,
+                                   const s3d_params *params);
 /* Synchronise, then copy the last extraction's feature rows to the host (malloc'ed). */
 s3d_status s3d_fetch_features(s3d_ctx *ctx, s3d_feature **out, int *n_out);
 /* Synchronise and return only the counts of the last extraction. */
@@ -191,6 +203,8 @@ void s3d_batch_destroy(s3d_batch *batch);
 const char *s3d_batch_last_error(const s3d_batch *batch);
 s3d_status s3d_batch_extract(s3d_batch *batch, const float *const *h_volumes, int n_volumes, int X, int Y, int Z,
                              const s3d_params *params, s3d_feature **rows, int *n_rows);
+s3d_status s3d_batch_extract_typed(s3d_batch *batch, const void *const *h_volumes, int dtype, int n_volumes, int X, int Y, int Z,
+                                   const s3d_params *params, s3d_feature **rows, int *n_rows);
 s3d_status s3d_batch_extract_device(s3d_batch *batch, const float *const *d_volumes, int n_volumes, int X, int Y, int Z,
                                     const s3d_params *params, int *n_keypoints, int *n_rows);
 /* kernel launches (graph nodes included) per volume of the last batch call */

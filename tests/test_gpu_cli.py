@@ -25,6 +25,10 @@ CASES = [
     ("halve", ["-2-"], dict()),
     ("world_iso", ["-w"], dict(pixdim=(1.5, 1.5, 1.5), qoffset=(-40.0, 12.5, 7.0), quatern=(0.0, 0.0, 0.0))),
     ("world_rot_aniso", ["-w"], dict(pixdim=(1.0, 1.0, 2.0), qoffset=(3.0, -2.0, 1.0), quatern=(0.1, 0.2, 0.3))),
+    # typed NIfTI voxels: our CLI sends them to the device as they are (cast there), the reference casts on the host
+    ("int16", [], dict(dtype=np.int16)),
+    ("uint8_double", ["-2+"], dict(dtype=np.uint8)),
+    ("float64_world_aniso", ["-w"], dict(dtype=np.float64, pixdim=(1.0, 2.0, 1.0), qoffset=(1.0, 2.0, 3.0))),
 ]
 
 
@@ -32,8 +36,12 @@ CASES = [
 def test_cli_matches_reference_cli(pkg, engine, tmp_path, name, flags, hdr):
     if not (os.path.exists(OURS) and os.path.exists(REF)):
         pytest.skip("CLI binaries not built")
-    shape = (72, 64, 80) if name == "halve" else (40, 44, 36) if name == "double" else (56, 60, 52)
+    shape = (72, 64, 80) if name == "halve" else (40, 44, 36) if "double" in name else (56, 60, 52)
     vol = pkg.phantom.blob_phantom(shape, 31, 45)
+    if hdr.get("dtype") is np.int16:
+        vol = vol * 40.0          # use the integer range
+    elif hdr.get("dtype") is np.uint8:
+        vol = np.clip(vol * 2.0, 0, 255)
     nii = str(tmp_path / "in.nii")
     pkg.phantom.write_nifti(nii, vol, **hdr)
     run(REF, flags + [nii, "ref.key"], str(tmp_path))

@@ -330,3 +330,36 @@ def test_plan_cache_keeps_results_identical(pkg, engine):
         else:
             first[sh] = rows
             assert len(rows) > 0
+
+
+@pytest.mark.parametrize("dtype", ["uint8", "int8", "int16", "uint16", "int32", "uint32", "float64", "float32"])
+def test_typed_input_matches_host_cast(pkg, engine, dtype):
+    """Typed input (s3d_extract_typed): the device-side cast gives the rows of the host-side cast the reference
+    does (reg_changeDatatype1, featExtract.cpp:18-77), with and without the -2+ pre-step."""
+    vol = pkg.phantom.blob_phantom((56, 48, 40), 9, 40)
+    if dtype in ("uint8", "int8"):
+        typed = np.clip(vol * (1.0 if dtype == "uint8" else 0.5), 0, 120).astype(dtype)
+    elif dtype == "float64":
+        typed = vol.astype(np.float64) * 1.0000001
+    elif dtype == "float32":
+        typed = vol
+    else:
+        typed = (vol * 37.0).astype(dtype)
+    as_float = typed.astype(np.float32)
+    for dm in (0, 1):
+        prm = pkg.Params(double_mode=dm)
+        want = engine.extract(as_float, prm)
+        got = engine.extract_typed(typed, prm)
+        assert len(want) > 0 and got.tobytes() == want.tobytes(), (dtype, dm)
+
+
+def test_batch_typed_input(pkg, engine):
+    vols = [(pkg.phantom.blob_phantom((64, 56, 48), seed, 50) * 50.0).astype(np.int16) for seed in range(5)]
+    want = [engine.extract(v.astype(np.float32)) for v in vols]
+    b = pkg.Batch(0, 2)
+    try:
+        got = b.extract_typed(vols)
+        for g, w in zip(got, want):
+            assert len(w) > 0 and g.tobytes() == w.tobytes()
+    finally:
+        b.close()
