@@ -363,3 +363,17 @@ def test_batch_typed_input(pkg, engine):
             assert len(w) > 0 and g.tobytes() == w.tobytes()
     finally:
         b.close()
+
+
+@pytest.mark.parametrize("config,descriptor", [("config1_blob128", 0), ("config2_mni", 0), ("config3_mni_brief", 1),
+                                               ("config3_mni_rrief", 2), ("config3_mni_nrrief", 3)])
+def test_baseline_configs_full_size_bit_exact(pkg, oracle, engine, config, descriptor):
+    """BASELINE.json configs 1-3 at their full sizes (128^3 blob phantom; 182x218x182 brain phantom with the
+    SIFT-Rank and the three BRIEF-family descriptors): feature rows identical to the oracle, every descriptor
+    a permutation of the ranks 0..63."""
+    vol = pkg.phantom.blob_phantom() if config == "config1_blob128" else pkg.phantom.brain_phantom()
+    want = oracle.extract(vol, 0, descriptor)["features"]
+    feats = engine.extract(vol, pkg.Params(descriptor=descriptor))
+    assert len(want) > 500
+    assert feats.tobytes() == want.tobytes()
+    assert (np.sort(feats["pc"], axis=1) == np.arange(64, dtype=np.float32)).all()
