@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <string>
 #include <vector>
 
@@ -119,6 +120,38 @@ static void build_tables(KpTables &t)
     }
 }
 
+// One shared-memory carve-out for every kernel of the pipeline.  Kernels that prefer different L1 / shared
+// splits cannot be resident on an SM together: the SM has to drain before it is reconfigured, so the
+// graph's concurrent branches (and the contexts of a batch) serialise behind each other.  With one carve-out
+// the shared-memory-heavy kernels (x+y tiles, orientation histograms) and the cache-reliant ones (detection,
+// z march, refinement) overlap.  S3D_CARVEOUT=<percent of the maximum shared memory> overrides the default.
+template <typename K>
+static void set_carveout(K kernel, int pct) { cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct); }
+template <int R>
+static void set_carveout_blur_r(int pct)
+{
+    set_carveout(blur_xy2_kernel<R>, pct);
+    set_carveout(blur_z2_kernel<R, true, float2>, pct);  set_carveout(blur_z2_kernel<R, false, float2>, pct);
+    set_carveout(blur_z2_kernel<R, true, float4>, pct);  set_carveout(blur_z2_kernel<R, false, float4>, pct);
+    set_carveout(blur_xy_kernel<R>, pct);
+    set_carveout(blur_march_kernel<R, true>, pct);       set_carveout(blur_march_kernel<R, false>, pct);
+}
+static void set_carveout_all(int pct)
+{
+    set_carveout_blur_r<1>(pct); set_carveout_blur_r<2>(pct); set_carveout_blur_r<3>(pct); set_carveout_blur_r<4>(pct);
+    set_carveout_blur_r<5>(pct); set_carveout_blur_r<6>(pct); set_carveout_blur_r<7>(pct); set_carveout_blur_r<8>(pct);
+    set_carveout(detect_face_kernel, pct); set_carveout(detect_full_kernel, pct); set_carveout(detect_kernel, pct);
+    set_carveout(cand_refine_kernel, pct); set_carveout(compact_kernel, pct); set_carveout(row_offsets_kernel, pct);
+    set_carveout(orient_a_kernel, pct); set_carveout(orient_b_kernel, pct); set_carveout(describe_kernel, pct);
+    set_carveout(subsample_kernel, pct); set_carveout(halve_kernel, pct); set_carveout(double_kernel, pct);
+    set_carveout(pad_rows_kernel, pct); set_carveout(zero_ints_kernel, pct); set_carveout(dog_kernel, pct);
+    set_carveout(convert_rows_kernel<unsigned char>, pct); set_carveout(convert_rows_kernel<signed char>, pct);
+    set_carveout(convert_rows_kernel<short>, pct); set_carveout(convert_rows_kernel<unsigned short>, pct);
+    set_carveout(convert_rows_kernel<int>, pct); set_carveout(convert_rows_kernel<unsigned int>, pct);
+    set_carveout(convert_rows_kernel<double>, pct);
+    cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------
@@ -193,6 +226,7 @@ struct s3d_ctx {
     unsigned long long *d_stamps = nullptr;   // S3D_STAMPS=1
     int z2_vec = 0;              // S3D_Z2_VEC=2|4: columns per thread of the z march (0 = by radius)
     int tail_a = 3, tail_b = 6, tail_d = 10;   // blocks per SM of orient_a / orient_b / describe (S3D_TAIL_BLOCKS=a,b,d)
+    int prof_skip = 0;           // S3D_PROF_SKIP (profiling only, results invalid): 1 = no keypoint tail, 2 = no detection/refinement, 3 = both
     bool serial = false;         // S3D_SERIAL=1: no branches, every kernel on the main stream (standalone kernel times)
     int fused_ctas = 0;          // S3D_FUSED_CTAS: CTAs the fused blur aims for (0 = 2 per SM)
     bool timing = false;         // S3D_STAGE_TIMING=1: no graph, events at stage boundaries of the main stream
@@ -312,6 +346,13 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
     if (tb) { int a = 0, b = 0, d = 0; if (sscanf(tb, "%d,%d,%d", &a, &b, &d) == 3 && a > 0 && b > 0 && d > 0) { ctx->tail_a = a; ctx->tail_b = b; ctx->tail_d = d; } }
     const char *pc = getenv("S3D_PLAN_CACHE");
     if (pc && atoi(pc) >= 1) ctx->max_plans = atoi(pc);
+    {
+        const char *co = getenv("S3D_CARVEOUT");
+        int pct = co ? atoi(co) : -1;
+        if (pct >= 0 && pct <= 100) set_carveout_all(pct);
+    }
+    const char *psk = getenv("S3D_PROF_SKIP");
+    if (psk) ctx->prof_skip = atoi(psk);
     const char *ser = getenv("S3D_SERIAL");
     if (ser) ctx->serial = (ser[0] == '1');
     const char *f3c = getenv("S3D_F3_CTAS");
@@ -978,7 +1019,7 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
                 CK(cudaStreamWaitEvent(sd, ctx->ev_lvl[o][j - 2], 0));
                 ctx->cur = sd;
                 int c_det = j - 1, c_ref = j - 2;
-                if (c_det <= 3) {
+                if (c_det <= 3 && !(ctx->prof_skip & 2)) {
                     int l0 = (o * 3 + (c_det - 1)) * 2;
                     s = detect_two_pass(ctx, od.d[c_det - 1], od.d[c_det], od.X, od.Y, od.Z, od.pitch,
                                         p->face[o * 3 + c_det - 1], p->face_counts + o * 3 + c_det - 1, p->face_cap[o * 3 + c_det - 1],
@@ -986,7 +1027,7 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
                                         p->cand_raw + (size_t)(l0 + 1) * p->cand_cap, p->counts + l0 + 1, p->cand_cap, err, od.own0, od.own1);
                     if (s != S3D_OK) { ctx->cur = st; return s; }
                 }
-                if (c_ref >= 1) {
+                if (c_ref >= 1 && !(ctx->prof_skip & 2)) {
                     int l0 = (o * 3 + (c_ref - 1)) * 2;
                     cand_refine_kernel<<<dim3(2, 4), 256, 0, sd>>>(p->pyr, L, l0, p->kp_stage, p->stage_flags, err);
                     ctx->launches++;
@@ -1000,6 +1041,7 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     for (int o = 0; o < o_small; o++) CK(cudaStreamWaitEvent(st, ctx->ev_done[o], 0));
     if (o_small < p->n_oct) CK(cudaStreamWaitEvent(st, ctx->ev_done[o_small], 0));
     mark(ctx, "join (detect+refine tails)");
+    if (ctx->prof_skip & 1) { CK(cudaGetLastError()); return S3D_OK; }
     compact_kernel<<<1, 1024, 0, st>>>(L, p->kp_stage, p->stage_flags, p->kps, kp_count, p->kp_cap, err);
     mark(ctx, "compact");
     // orientation: per keypoint, then per (keypoint, primary direction)
@@ -1008,11 +1050,13 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     orient_a_kernel<<<ctx->sm_count * ctx->tail_a, 256, sizeof(HistSmem), st>>>(p->pyr, p->kps, kp_count, eig, p->kp_nprim, p->kp_eigs,
                                                                      p->kp_ori0, p->kp_p1, p->kp_patch0, p->work_b, work_b_count);
     mark(ctx, "orient_a");
+    if (ctx->prof_skip & 8) { CK(cudaGetLastError()); return S3D_OK; }
     orient_b_kernel<<<ctx->sm_count * ctx->tail_b, 256, sizeof(HistSmem), st>>>(p->work_b, work_b_count, p->kp_p1, p->kp_patch0, p->kp_nsec, p->kp_rots);
     mark(ctx, "orient_b");
     row_offsets_kernel<<<1, 1024, 0, st>>>(p->kp_nprim, p->kp_nsec, kp_count, p->nrows, p->row_off, p->row_map, n_features, p->row_cap, err);
     float size_factor = 1.0f;
     if (p->double_mode > 0 || p->pre_step_done > 0) size_factor /= 2; else if (p->double_mode < 0 || p->pre_step_done < 0) size_factor *= 2;
+    if (ctx->prof_skip & 4) { CK(cudaGetLastError()); return S3D_OK; }
     int grid_d = ctx->sm_count * ctx->tail_d;
     describe_kernel<<<grid_d, 128, sizeof(DescribeSmem), st>>>(p->pyr, p->kps, n_features, p->row_map, p->kp_nsec, p->kp_eigs,
                                                               p->kp_ori0, p->kp_rots, p->kp_patch0, prm->descriptor, size_factor, p->octave_base,
@@ -1333,8 +1377,14 @@ static s3d_status batch_run(s3d_batch *b, const void *const *vols, int n, int X,
         return st;
     };
     s3d_status first_err = S3D_OK;
+    static int stagger_us = -1;
+    if (stagger_us < 0) { const char *e = getenv("S3D_BATCH_STAGGER_US"); stagger_us = e ? atoi(e) : 0; }
     for (int i = 0; i < n && first_err == S3D_OK; i++) {
         const int c = i % nc;
+        if (stagger_us > 0 && i > 0 && i < nc) {      // experiment: de-phase the contexts' first volumes
+            struct timespec ts = { 0, (long)stagger_us * 1000L };
+            nanosleep(&ts, nullptr);
+        }
         s3d_status st = collect(c);
         if (st == S3D_OK)
             st = from_host ? s3d_extract_typed_async(b->ctx[c], vols[i], dtype, X, Y, Z, prm)
