@@ -1003,7 +1003,7 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
                     sa.cand_raw = p->cand_raw; sa.counts = p->counts; sa.cand_cap = p->cand_cap;
                     small_octaves_kernel<<<kSmallClusterCtas, kSmallThreads, 0, ss>>>(p->pyr, sa);
                     int nl = (p->n_oct - o_small) * 6;
-                    cand_refine_kernel<<<dim3(nl, 2), 256, 0, ss>>>(p->pyr, L, o_small * 6, p->kp_stage, p->stage_flags, err);
+                    cand_refine_kernel<<<dim3(nl, 16), 256, 0, ss>>>(p->pyr, L, o_small * 6, p->kp_stage, p->stage_flags, err);
                     ctx->launches += 2;
                     CK(cudaEventRecord(ctx->ev_done[o_small], ss));
                 }
@@ -1029,7 +1029,7 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
                 }
                 if (c_ref >= 1 && !(ctx->prof_skip & 2)) {
                     int l0 = (o * 3 + (c_ref - 1)) * 2;
-                    cand_refine_kernel<<<dim3(2, 4), 256, 0, sd>>>(p->pyr, L, l0, p->kp_stage, p->stage_flags, err);
+                    cand_refine_kernel<<<dim3(2, 32), 256, 0, sd>>>(p->pyr, L, l0, p->kp_stage, p->stage_flags, err);
                     ctx->launches++;
                 }
                 if (j == 5) CK(cudaEventRecord(ctx->ev_done[o], sd));

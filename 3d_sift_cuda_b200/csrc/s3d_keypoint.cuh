@@ -507,6 +507,9 @@ struct ListDesc {            // list = (octave*3 + (c-1))*2 + is_max
     const int *counts;       // [n_lists]
 };
 
+// One WARP per candidate: the lanes split the rank count over the list (coalesced 16-byte loads) and the 27
+// neighbours of the deferred validation; lanes 0..3 then run the four parabola fits (x, y, z, scale) side by
+// side.  (One thread per candidate made this kernel a 15-20 us latency chain: n sequential loads per thread.)
 __global__ void __launch_bounds__(256) cand_refine_kernel(const __grid_constant__ PyramidDesc pyr, ListDesc L, int list_begin,
                                                           s3d_keypoint *__restrict__ stage, unsigned char *__restrict__ flags,
                                                           int *err)
@@ -520,33 +523,41 @@ __global__ void __launch_bounds__(256) cand_refine_kernel(const __grid_constant_
     if (n > L.cap) { if (threadIdx.x == 0 && blockIdx.y == 0) atomicOr(err, ERR_CAND_OVERFLOW); n = L.cap; }
     const s3d_cand *raw = L.raw + (long long)list * L.cap;
     const float *dH = o.d[c - 1], *dC = o.d[c], *dL = o.d[c + 1];
-    for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < n; k += gridDim.y * blockDim.x) {
-        s3d_cand cd = raw[k];
-        long long key = ((long long)cd.z * Y + cd.y) * X + cd.x;
-        int rank = 0;
-        for (int j = 0; j < n; j++) {
-            s3d_cand q = raw[j];
-            rank += (((long long)q.z * Y + q.y) * X + q.x) < key;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int k = blockIdx.y * warps_per_block + (threadIdx.x >> 5); k < n; k += gridDim.y * warps_per_block) {
+        const s3d_cand cd = raw[k];
+        const long long key = ((long long)cd.z * Y + cd.y) * X + cd.x;
+        int cnt = 0;
+        for (int j = lane; j < n; j += 32) {
+            const s3d_cand q = raw[j];
+            cnt += (((long long)q.z * Y + q.y) * X + q.x) < key;
         }
-        long long i = (long long)cd.z * plane + (long long)cd.y * pitch + cd.x;
-        float cv = cd.value;
-        bool ok = true;
-        for (int dz = -1; dz <= 1 && ok; dz++)
-            for (int dy = -1; dy <= 1 && ok; dy++) {
-                const float *row = dL + i + dz * plane + dy * pitch;
-                float a = row[-1], b = row[0], d = row[1];
-                ok = is_max ? ((a < cv) && (b < cv) && (d < cv)) : ((a > cv) && (b > cv) && (d > cv));
-            }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        const int rank = cnt;
+        const long long i = (long long)cd.z * plane + (long long)cd.y * pitch + cd.x;
+        const float cv = cd.value;
+        bool mine = true;
+        if (lane < 27) {
+            const int dz = lane / 9 - 1, dy = (lane / 3) % 3 - 1, dx = lane % 3 - 1;
+            const float a = dL[i + dz * plane + dy * pitch + dx];
+            mine = is_max ? (a < cv) : (a > cv);
+        }
+        const bool ok = __all_sync(0xffffffffu, mine);
         bool valid = false;
         s3d_keypoint kp;
         if (ok) {
             // geometry is computed in GLOBAL plane coordinates (slab mode: local z + z_off), because the
             // parabola arithmetic and later float sums depend on the magnitude of z
             const int gz = cd.z + o.z_off;
-            float fx = (float)interp_quadratic(cd.x - 1, cd.x, cd.x + 1, dC[i - 1], dC[i], dC[i + 1]);
-            float fy = (float)interp_quadratic(cd.y - 1, cd.y, cd.y + 1, dC[i - pitch], dC[i], dC[i + pitch]);
-            float fz = (float)interp_quadratic(gz - 1, gz, gz + 1, dC[i - plane], dC[i], dC[i + plane]);
-            float scale = (float)(2 * interp_quadratic(o.sigma[c - 1], o.sigma[c], o.sigma[c + 1], dH[i], dC[i], dL[i]));
+            float r = 0.0f;
+            if (lane == 0) r = (float)interp_quadratic(cd.x - 1, cd.x, cd.x + 1, dC[i - 1], dC[i], dC[i + 1]);
+            else if (lane == 1) r = (float)interp_quadratic(cd.y - 1, cd.y, cd.y + 1, dC[i - pitch], dC[i], dC[i + pitch]);
+            else if (lane == 2) r = (float)interp_quadratic(gz - 1, gz, gz + 1, dC[i - plane], dC[i], dC[i + plane]);
+            else if (lane == 3) r = (float)(2 * interp_quadratic(o.sigma[c - 1], o.sigma[c], o.sigma[c + 1], dH[i], dC[i], dL[i]));
+            float fx = __shfl_sync(0xffffffffu, r, 0), fy = __shfl_sync(0xffffffffu, r, 1), fz = __shfl_sync(0xffffffffu, r, 2);
+            const float scale = __shfl_sync(0xffffffffu, r, 3);
             fx += 0.5f; fy += 0.5f; fz += 0.5f;
             float fImageRad = 2.0f * scale;
             int iRadMax = (int)(fImageRad + 2);
@@ -559,9 +570,11 @@ __global__ void __launch_bounds__(256) cand_refine_kernel(const __grid_constant_
                 kp.x = fx; kp.y = fy; kp.z = fz; kp.scale = scale;
             }
         }
-        long long slot = (long long)list * L.cap + rank;
-        flags[slot] = valid ? 1 : 0;
-        if (valid) stage[slot] = kp;
+        if (lane == 0) {
+            long long slot = (long long)list * L.cap + rank;
+            flags[slot] = valid ? 1 : 0;
+            if (valid) stage[slot] = kp;
+        }
     }
 }
 

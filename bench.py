@@ -359,7 +359,7 @@ def run_ours(args):
             cold = sum(x.elapsed_time(y) for x, y in lev) / reps
             warm = e0.elapsed_time(e1) / reps
             alg = (12.0 if with_dog else 8.0) * N0
-            tr = traffic.get(str(len(taps)))
+            tr = traffic.get(str(len(taps))) if with_dog else None      # the capture ran every level with the DoG output
             levels.append({"level": name, "taps": len(taps), "algorithmic_bytes": alg, "ms_cold": cold, "ms_warm": warm,
                            "achieved_cold": alg / (cold * 1e-3) / 1e9, "frac_cold": alg / (cold * 1e-3) / 1e9 / peak,
                            "achieved_warm": alg / (warm * 1e-3) / 1e9, "frac_warm": alg / (warm * 1e-3) / 1e9 / peak,
