@@ -226,6 +226,7 @@ struct s3d_ctx {
     unsigned long long *d_stamps = nullptr;   // S3D_STAMPS=1
     int z2_vec = 0;              // S3D_Z2_VEC=2|4: columns per thread of the z march (0 = by radius)
     int tail_a = 3, tail_b = 6, tail_d = 10;   // blocks per SM of orient_a / orient_b / describe (S3D_TAIL_BLOCKS=a,b,d)
+    int desc_threads = 128;      // threads per describe block (S3D_DESC_THREADS: 64 or 128)
     int prof_skip = 0;           // S3D_PROF_SKIP (profiling only, results invalid): 1 = no keypoint tail, 2 = no detection/refinement, 3 = both
     bool serial = false;         // S3D_SERIAL=1: no branches, every kernel on the main stream (standalone kernel times)
     int fused_ctas = 0;          // S3D_FUSED_CTAS: CTAs the fused blur aims for (0 = 2 per SM)
@@ -351,6 +352,8 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
         int pct = co ? atoi(co) : -1;
         if (pct >= 0 && pct <= 100) set_carveout_all(pct);
     }
+    const char *dth = getenv("S3D_DESC_THREADS");
+    if (dth && (atoi(dth) == 64 || atoi(dth) == 128)) ctx->desc_threads = atoi(dth);
     const char *psk = getenv("S3D_PROF_SKIP");
     if (psk) ctx->prof_skip = atoi(psk);
     const char *ser = getenv("S3D_SERIAL");
@@ -1058,7 +1061,7 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     if (p->double_mode > 0 || p->pre_step_done > 0) size_factor /= 2; else if (p->double_mode < 0 || p->pre_step_done < 0) size_factor *= 2;
     if (ctx->prof_skip & 4) { CK(cudaGetLastError()); return S3D_OK; }
     int grid_d = ctx->sm_count * ctx->tail_d;
-    describe_kernel<<<grid_d, 128, sizeof(DescribeSmem), st>>>(p->pyr, p->kps, n_features, p->row_map, p->kp_nsec, p->kp_eigs,
+    describe_kernel<<<grid_d, ctx->desc_threads, sizeof(DescribeSmem), st>>>(p->pyr, p->kps, n_features, p->row_map, p->kp_nsec, p->kp_eigs,
                                                               p->kp_ori0, p->kp_rots, p->kp_patch0, prm->descriptor, size_factor, p->octave_base,
                                                               p->row_cap, p->feats, p->dbg_patches, p->dbg_prerank);
     mark(ctx, "row_offsets+describe");

@@ -171,6 +171,28 @@ def _pre_stepped_dims(shape_zyx, double_mode):
     return X, Y, Z
 
 
+class _Timer:
+    """SLAB_TIMING=1: wall-clock per section of extract_slab (device synchronised at section ends)."""
+
+    def __init__(self, torch):
+        import os
+        import time
+        self.on = os.environ.get("SLAB_TIMING") == "1"
+        self.torch, self.time, self.t, self.acc = torch, time, time.perf_counter(), {}
+
+    def lap(self, name):
+        if not self.on:
+            return
+        self.torch.cuda.synchronize()
+        now = self.time.perf_counter()
+        self.acc[name] = self.acc.get(name, 0.0) + (now - self.t)
+        self.t = now
+
+    def report(self, rank):
+        if self.on:
+            print("slab timing rank %d: " % rank + ", ".join("%s %.1f ms" % (k, 1e3 * v) for k, v in self.acc.items()), flush=True)
+
+
 def extract_slab(engine, volume, rank=0, world=1, group=None, double_mode=0, descriptor=0, eig_thres=140.0,
                  halo=SLAB_HALO, emulate_ranks=None, max_keypoints=0, max_features=0):
     """featExtract of ONE volume split into z slabs over ``world`` ranks; rank 0 returns the feature rows
@@ -198,6 +220,7 @@ def extract_slab(engine, volume, rank=0, world=1, group=None, double_mode=0, des
     if not emu:
         import torch.distributed as dist
 
+    tm = _Timer(torch)
     own_g0 = {}      # rank -> dense device tensor of its own planes of the current octave's level 0
     results = {r: [] for r in my_ranks}
     dims = (X0, Y0, Z0)
@@ -240,13 +263,16 @@ def extract_slab(engine, volume, rank=0, world=1, group=None, double_mode=0, des
                 if hi_t is not None:
                     parts.append(hi_t)
                 bufs[r] = (lo, torch.cat(parts).contiguous())
+        tm.lap("assemble/halo")
         # ---- run the octave, keep the own part of the next octave's level 0
         nxt = {}
         for r in my_ranks:
             z_off, d_buf = bufs[r]
             torch.cuda.synchronize()
             results[r].append(_run_slab_octave(engine, api, d_buf, o, z_off, Zo, own[r][0], own[r][1], base))
+            tm.lap("octave run+fetch")
             nxt[r] = _next_own_level0(engine, torch, z_off, own[r][0], own[r][1], dims)
+            tm.lap("next level0")
         own_g0 = nxt
         dims = (Xo // 2, Yo // 2, Zo // 2)
 
@@ -274,18 +300,57 @@ def extract_slab(engine, volume, rank=0, world=1, group=None, double_mode=0, des
                                                      max_keypoints=max_keypoints, max_features=max_features))
         tail = engine.fetch_features()
 
+    tm.lap("collapse tail")
     # ---- rank 0 merges (small: feature rows only)
     if emu:
         per_rank = [results[r] for r in range(nranks)]
     else:
-        gathered = [None] * nranks if rank == 0 else None
-        dist.gather_object(results[rank], gathered, dst=0, group=group)
+        # Rows travel as raw bytes over NCCL (device tensors), not as pickled objects: per (octave, level,
+        # min/max) only the row COUNTS are needed to rebuild the level / is_max columns, because every rank's
+        # rows are already in (level, minima then maxima, raster) order.
+        mine = results[rank]
+        counts = np.zeros((K, 3, 2), np.int64)
+        for o_, (f_, lv_, mx_) in enumerate(mine):
+            for level in (1, 2, 3):
+                for is_max in (0, 1):
+                    counts[o_, level - 1, is_max] = int(np.count_nonzero((lv_ == level) & (mx_ == is_max)))
+        c_dev = torch.from_numpy(counts.reshape(-1)).cuda()
+        all_counts = [torch.empty_like(c_dev) for _ in range(nranks)]
+        dist.all_gather(all_counts, c_dev, group=group)
+        itemsize = api.FEATURE_DTYPE.itemsize
         if rank != 0:
+            parts = [np.ascontiguousarray(f_).view(np.uint8).reshape(-1) for f_, _, _ in mine if len(f_)]
+            if parts:
+                dist.send(torch.from_numpy(np.concatenate(parts)).cuda(), 0, group)
+            tm.lap("send rows")
+            tm.report(rank)
             return None
-        per_rank = gathered
+        per_rank = [mine]
+        for r in range(1, nranks):
+            cr = all_counts[r].cpu().numpy().reshape(K, 3, 2)
+            total = int(cr.sum())
+            res_r = []
+            if total:
+                buf = torch.empty(total * itemsize, dtype=torch.uint8, device="cuda")
+                dist.recv(buf, r, group)
+                flat = buf.cpu().numpy().view(api.FEATURE_DTYPE)
+            else:
+                flat = np.zeros(0, api.FEATURE_DTYPE)
+            pos = 0
+            for o_ in range(K):
+                n_o = int(cr[o_].sum())
+                lv_ = np.repeat(np.array([1, 1, 2, 2, 3, 3]), cr[o_].reshape(-1))
+                mx_ = np.repeat(np.array([0, 1, 0, 1, 0, 1]), cr[o_].reshape(-1))
+                res_r.append((flat[pos:pos + n_o], lv_, mx_))
+                pos += n_o
+            per_rank.append(res_r)
+        tm.lap("recv rows")
     rows = merge_slab_rows(per_rank, K)
     if tail is not None and len(tail):
         rows.append(tail)
     if not rows:
         return np.zeros(0, api.FEATURE_DTYPE)
-    return np.concatenate(rows)
+    out = np.concatenate(rows)
+    tm.lap("merge")
+    tm.report(rank)
+    return out

@@ -29,9 +29,10 @@ for it in range(2):
     torch.cuda.synchronize(); dist.barrier(); t_slab = time.perf_counter() - t0
 ok = True
 if rank == 0:
-    t0 = time.perf_counter()
-    whole = eng.extract(vol, pkg.Params(double_mode=dm, max_keypoints=CAP, max_features=8 * CAP))
-    t_whole = time.perf_counter() - t0
+    for it in range(2):      # second call: plan and graph already resident
+        t0 = time.perf_counter()
+        whole = eng.extract(vol, pkg.Params(double_mode=dm, max_keypoints=CAP, max_features=8 * CAP))
+        t_whole = time.perf_counter() - t0
     ok = (len(slab) == len(whole)) and slab.tobytes() == whole.tobytes()
     print("slab mode: world %d, shape %s, double_mode %d, slab octaves K=%d, bounds %s" % (world, shape, dm, K, bounds))
     print("rows slab %d whole %d  identical %s  | slab %.1f ms (incl. host slicing + H2D), whole-volume on one GPU %.1f ms"
