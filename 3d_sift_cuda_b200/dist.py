@@ -171,6 +171,54 @@ def _pre_stepped_dims(shape_zyx, double_mode):
     return X, Y, Z
 
 
+def gather_slab_rows(mine, K, rank, nranks, group=None):
+    """Bring every rank's slab results to rank 0 (returns per_rank there, None elsewhere).
+
+    ``mine[o] = (features, level, is_max)`` for the K slab octaves.  Rows travel as raw bytes in tensors (on the
+    device with NCCL, on the host with gloo), not as pickled objects: per (octave, level, min/max) only the row
+    COUNTS are needed to rebuild the level / is_max columns, because every rank's rows are already in
+    (level, minima then maxima, raster) order."""
+    import importlib
+    import torch
+    import torch.distributed as dist
+    api = importlib.import_module("3d_sift_cuda_b200.api")
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    counts = np.zeros((K, 3, 2), np.int64)
+    for o_, (f_, lv_, mx_) in enumerate(mine):
+        for level in (1, 2, 3):
+            for is_max in (0, 1):
+                counts[o_, level - 1, is_max] = int(np.count_nonzero((lv_ == level) & (mx_ == is_max)))
+    c_dev = torch.from_numpy(counts.reshape(-1)).to(dev)
+    all_counts = [torch.empty_like(c_dev) for _ in range(nranks)]
+    dist.all_gather(all_counts, c_dev, group=group)
+    itemsize = api.FEATURE_DTYPE.itemsize
+    if rank != 0:
+        parts = [np.ascontiguousarray(f_).view(np.uint8).reshape(-1) for f_, _, _ in mine if len(f_)]
+        if parts:
+            dist.send(torch.from_numpy(np.concatenate(parts)).to(dev), 0, group)
+        return None
+    per_rank = [mine]
+    for r in range(1, nranks):
+        cr = all_counts[r].cpu().numpy().reshape(K, 3, 2)
+        total = int(cr.sum())
+        res_r = []
+        if total:
+            buf = torch.empty(total * itemsize, dtype=torch.uint8, device=dev)
+            dist.recv(buf, r, group)
+            flat = buf.cpu().numpy().view(api.FEATURE_DTYPE)
+        else:
+            flat = np.zeros(0, api.FEATURE_DTYPE)
+        pos = 0
+        for o_ in range(K):
+            n_o = int(cr[o_].sum())
+            lv_ = np.repeat(np.array([1, 1, 2, 2, 3, 3]), cr[o_].reshape(-1))
+            mx_ = np.repeat(np.array([0, 1, 0, 1, 0, 1]), cr[o_].reshape(-1))
+            res_r.append((flat[pos:pos + n_o], lv_, mx_))
+            pos += n_o
+        per_rank.append(res_r)
+    return per_rank
+
+
 class _Timer:
     """SLAB_TIMING=1: wall-clock per section of extract_slab (device synchronised at section ends)."""
 
@@ -305,45 +353,11 @@ def extract_slab(engine, volume, rank=0, world=1, group=None, double_mode=0, des
     if emu:
         per_rank = [results[r] for r in range(nranks)]
     else:
-        # Rows travel as raw bytes over NCCL (device tensors), not as pickled objects: per (octave, level,
-        # min/max) only the row COUNTS are needed to rebuild the level / is_max columns, because every rank's
-        # rows are already in (level, minima then maxima, raster) order.
-        mine = results[rank]
-        counts = np.zeros((K, 3, 2), np.int64)
-        for o_, (f_, lv_, mx_) in enumerate(mine):
-            for level in (1, 2, 3):
-                for is_max in (0, 1):
-                    counts[o_, level - 1, is_max] = int(np.count_nonzero((lv_ == level) & (mx_ == is_max)))
-        c_dev = torch.from_numpy(counts.reshape(-1)).cuda()
-        all_counts = [torch.empty_like(c_dev) for _ in range(nranks)]
-        dist.all_gather(all_counts, c_dev, group=group)
-        itemsize = api.FEATURE_DTYPE.itemsize
+        per_rank = gather_slab_rows(results[rank], K, rank, nranks, group)
         if rank != 0:
-            parts = [np.ascontiguousarray(f_).view(np.uint8).reshape(-1) for f_, _, _ in mine if len(f_)]
-            if parts:
-                dist.send(torch.from_numpy(np.concatenate(parts)).cuda(), 0, group)
             tm.lap("send rows")
             tm.report(rank)
             return None
-        per_rank = [mine]
-        for r in range(1, nranks):
-            cr = all_counts[r].cpu().numpy().reshape(K, 3, 2)
-            total = int(cr.sum())
-            res_r = []
-            if total:
-                buf = torch.empty(total * itemsize, dtype=torch.uint8, device="cuda")
-                dist.recv(buf, r, group)
-                flat = buf.cpu().numpy().view(api.FEATURE_DTYPE)
-            else:
-                flat = np.zeros(0, api.FEATURE_DTYPE)
-            pos = 0
-            for o_ in range(K):
-                n_o = int(cr[o_].sum())
-                lv_ = np.repeat(np.array([1, 1, 2, 2, 3, 3]), cr[o_].reshape(-1))
-                mx_ = np.repeat(np.array([0, 1, 0, 1, 0, 1]), cr[o_].reshape(-1))
-                res_r.append((flat[pos:pos + n_o], lv_, mx_))
-                pos += n_o
-            per_rank.append(res_r)
         tm.lap("recv rows")
     rows = merge_slab_rows(per_rank, K)
     if tail is not None and len(tail):

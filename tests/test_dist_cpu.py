@@ -79,3 +79,48 @@ def test_slab_plan_and_merge(pkg):
     per_rank = [[mk(1, [1, 1, 2], [0, 1, 0])], [mk(2, [1, 2, 2], [0, 0, 1])]]
     merged = np.concatenate(d.merge_slab_rows(per_rank, 1))["x"].tolist()
     assert merged == [100, 200, 101, 102, 201, 202]
+
+
+def _slab_gather_worker(rank, world, port, q):
+    import torch.distributed as dist
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    pkg = importlib.import_module("3d_sift_cuda_b200")
+    d = importlib.import_module("3d_sift_cuda_b200.dist")
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+
+    def mk(tag, levels, maxs):
+        f = np.zeros(len(levels), pkg.FEATURE_DTYPE)
+        f["x"] = [tag * 100 + i for i in range(len(levels))]
+        f["pc"][:, 0] = tag
+        return f, np.array(levels), np.array(maxs)
+
+    # two slab octaves per rank, rows already in (level, min then max) order; rank 1 has an empty octave
+    mine = [mk(1, [1, 1, 2, 3], [0, 1, 0, 1]), mk(3, [2, 2], [0, 1])] if rank == 0 else [mk(2, [1, 2, 2, 3, 3], [0, 0, 1, 0, 1]), mk(4, [], [])]
+    per_rank = d.gather_slab_rows(mine, 2, rank, world)
+    out = None
+    if rank == 0:
+        merged = np.concatenate(d.merge_slab_rows(per_rank, 2))
+        out = (merged["x"].tolist(), merged["pc"][:, 0].tolist())
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_slab_rows_gathered_as_bytes_gloo_world2():
+    """The slab mode's row transport (counts + raw bytes, NCCL on GPUs) with gloo on the CPU: rank 0 rebuilds
+    every rank's (features, level, is_max) and merges them in the reference's order."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_slab_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    xs, tags = res[0]
+    # octave 0: level1 min (r0, r1), level1 max (r0), level2 min (r0, r1), level2 max (r1), level3 min (r1), level3 max (r0, r1); octave 1: r0 only
+    assert xs == [100, 200, 101, 102, 201, 202, 203, 103, 204, 300, 301]
+    assert tags == [1, 2, 1, 1, 2, 2, 2, 1, 2, 3, 3]
+    assert res[1] is None
