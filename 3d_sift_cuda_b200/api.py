@@ -154,7 +154,8 @@ def _copy_out(ptr, count, dtype, free):
             free(ptr)
         return np.zeros(0, dtype)
     nbytes = count * np.dtype(dtype).itemsize
-    out = np.frombuffer(C.string_at(ptr, nbytes), dtype=dtype).copy()
+    addr = ptr.value if hasattr(ptr, "value") else int(ptr)
+    out = np.frombuffer((C.c_char * nbytes).from_address(addr), dtype=dtype).copy()     # one copy out of the C buffer
     free(ptr)
     return out
 

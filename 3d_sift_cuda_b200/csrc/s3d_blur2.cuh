@@ -376,7 +376,7 @@ static cudaError_t init_blur2_attrs()
 // x+y: in -> tmp.  Returns false (nothing launched) when the tensor map cannot be encoded.
 template <int R>
 static bool launch_blur_xy2(cudaStream_t st, const float *in, float *tmp, int X, int Y, int Z, int pitch, const float *taps,
-                            int sm_count, cudaError_t *err)
+                            int sm_count, int ctas_per_sm, cudaError_t *err)
 {
     XY2Tile tile = choose_xy2_tile(pitch, Y, Z, R, sm_count);
     CUtensorMap map;
@@ -387,7 +387,10 @@ static bool launch_blur_xy2(cudaStream_t st, const float *in, float *tmp, int X,
     const int n_tx = (pitch + tile.TX - 1) / tile.TX, n_ty = (Y + tile.TY - 1) / tile.TY;
     const long long n_tiles = (long long)n_tx * n_ty * Z;
     if (n_tiles > 0x7fffffffll) return false;
-    const int grid = (int)(n_tiles < 2ll * sm_count ? n_tiles : 2ll * sm_count);
+    // persistent CTAs per SM: 2 when a volume has the GPU to itself; 1 inside a batch, where the other half of
+    // every SM is better spent on the memory-bound kernels of the other volumes in flight
+    const long long slots = (long long)(ctas_per_sm < 1 ? 1 : ctas_per_sm) * sm_count;
+    const int grid = (int)(n_tiles < slots ? n_tiles : slots);
     blur_xy2_kernel<R><<<grid, kXY2Threads, tile.smem, st>>>(map, tmp, X, Y, pitch, tile, n_tx, n_ty, (int)n_tiles, t);
     *err = cudaGetLastError();
     return true;

@@ -226,6 +226,8 @@ struct s3d_ctx {
     unsigned long long *d_stamps = nullptr;   // S3D_STAMPS=1
     int z2_vec = 0;              // S3D_Z2_VEC=2|4: columns per thread of the z march (0 = by radius)
     int tail_a = 3, tail_b = 6, tail_d = 10;   // blocks per SM of orient_a / orient_b / describe (S3D_TAIL_BLOCKS=a,b,d)
+    int xy2_ctas = 2;            // persistent x+y CTAs per SM (S3D_XY2_CTAS_PER_SM; contexts of an s3d_batch use 1)
+    bool xy2_ctas_forced = false;
     int desc_threads = 128;      // threads per describe block (S3D_DESC_THREADS: 64 or 128)
     int prof_skip = 0;           // S3D_PROF_SKIP (profiling only, results invalid): 1 = no keypoint tail, 2 = no detection/refinement, 3 = both
     bool serial = false;         // S3D_SERIAL=1: no branches, every kernel on the main stream (standalone kernel times)
@@ -352,6 +354,8 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
         int pct = co ? atoi(co) : -1;
         if (pct >= 0 && pct <= 100) set_carveout_all(pct);
     }
+    const char *xc = getenv("S3D_XY2_CTAS_PER_SM");
+    if (xc && atoi(xc) >= 1 && atoi(xc) <= 4) { ctx->xy2_ctas = atoi(xc); ctx->xy2_ctas_forced = true; }
     const char *dth = getenv("S3D_DESC_THREADS");
     if (dth && (atoi(dth) == 64 || atoi(dth) == 128)) ctx->desc_threads = atoi(dth);
     const char *psk = getenv("S3D_PROF_SKIP");
@@ -484,7 +488,7 @@ static void launch_blur_fast(s3d_ctx *ctx, const float *in, float *tmp, float *o
     }
     if (ctx->blur2 && sym && plane * Z < (1ll << 31)) {
         cudaError_t e = cudaSuccess;
-        if (launch_blur_xy2<R>(ctx->cur, in, tmp, X, Y, Z, pitch, taps, ctx->sm_count, &e)) {
+        if (launch_blur_xy2<R>(ctx->cur, in, tmp, X, Y, Z, pitch, taps, ctx->sm_count, ctx->xy2_ctas, &e)) {
             int target2 = ctx->march_target > 0 ? ctx->march_target : ctx->sm_count * 256;
             launch_blur_z2<R>(ctx->cur, tmp, out, in, dog, Y, Z, pitch, taps, target2, ctx->z2_vec);
             ctx->launches += 2;
@@ -1337,6 +1341,7 @@ extern "C" s3d_status s3d_batch_create(int device, int n_contexts, s3d_batch **o
             delete b;
             return st;
         }
+        if (!c->xy2_ctas_forced && n_contexts > 1) c->xy2_ctas = 1;      // throughput mode, see launch_blur_xy2
         b->ctx.push_back(c);
     }
     *out = b;
