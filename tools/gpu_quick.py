@@ -1,7 +1,7 @@
 """Ad-hoc GPU smoke + timing (not collected by pytest)."""
 import importlib, sys, time, os
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 pkg = importlib.import_module("3d_sift_cuda_b200")

@@ -1,6 +1,6 @@
 """Profiling helper (not a test): compact CSV of the metrics that matter from ncu --set full reports.
 
-    python tests/ncu_summary.py OUT.csv label1=report1.ncu-rep [label2=report2.ncu-rep ...]
+    python tools/ncu_summary.py OUT.csv label1=report1.ncu-rep [label2=report2.ncu-rep ...]
 """
 import csv
 import subprocess

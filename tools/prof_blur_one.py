@@ -1,5 +1,5 @@
 """Profiling driver (not a test): 4 launches of one blur level (x, y, z+DoG passes) at MNI size.
-usage: python tests/prof_blur_one.py [sigma]   (default 3.09 -> 17 taps)"""
+usage: python tools/prof_blur_one.py [sigma]   (default 3.09 -> 17 taps)"""
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -1,5 +1,5 @@
 """Profiling driver (not a test): N device-resident extractions of the MNI phantom.
-usage: python tests/prof_one.py [n_extractions] [blob128|brainB]"""
+usage: python tools/prof_one.py [n_extractions] [blob128|brainB]"""
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

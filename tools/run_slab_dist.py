@@ -1,7 +1,7 @@
 """Multi-GPU check of the z-slab mode (launch with torchrun, one rank per GPU):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tests/run_slab_dist.py [X Y Z] [double_mode]
+        tools/run_slab_dist.py [X Y Z] [double_mode]
 
 Rank 0 compares the slab result (NCCL halo exchange per octave) with the whole-volume engine and prints
 timings; exit code 1 on any difference."""
