@@ -9,6 +9,7 @@ There is no CPU fallback: if the shared library is missing or no CUDA device is 
 raise ``S3DError``.
 """
 import ctypes as C
+import weakref
 import os
 import subprocess
 
@@ -153,11 +154,12 @@ def _copy_out(ptr, count, dtype, free):
         if ptr:
             free(ptr)
         return np.zeros(0, dtype)
+    # zero copy: the array views the malloc'ed C buffer, which is released (s3d_free) when the array is collected
     nbytes = count * np.dtype(dtype).itemsize
     addr = ptr.value if hasattr(ptr, "value") else int(ptr)
-    out = np.frombuffer((C.c_char * nbytes).from_address(addr), dtype=dtype).copy()     # one copy out of the C buffer
-    free(ptr)
-    return out
+    buf = (C.c_char * nbytes).from_address(addr)
+    weakref.finalize(buf, free, C.c_void_p(addr))
+    return np.frombuffer(buf, dtype=dtype)
 
 
 def _dptr(t):
