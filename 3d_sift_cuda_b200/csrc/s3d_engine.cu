@@ -1399,6 +1399,9 @@ extern "C" s3d_status s3d_batch_create(int device, int n_contexts, s3d_batch **o
             return st;
         }
         if (!c->xy2_ctas_forced && n_contexts > 1) c->xy2_ctas = 1;      // throughput mode, see launch_blur_xy2
+        // ... and the z march runs as one segment: the threads it lacks to cover the memory latency alone are
+        // provided by the other volumes in flight, and no halo planes are read twice (S3D_MARCH_TARGET overrides)
+        if (c->march_target == 0 && n_contexts > 1) c->march_target = 1;
         b->ctx.push_back(c);
     }
     *out = b;

@@ -7,7 +7,7 @@ orientation + SIFT-Rank descriptors) on synthetic MNI-sized phantoms.
 One "step" = one 182x218x182 fp32 volume through the whole path on each GPU (BASELINE.json config 2;
 with N > 1 this is config 4's batch sharding: every rank extracts its own volumes, no data-path
 collective, weak scaling).  The K steps of a run go through the batch entry point of the C-ABI
-(s3d_batch_*: --contexts extraction contexts in flight per GPU), timed as ONE region between two CUDA
+(s3d_batch_*: --contexts extraction contexts in flight per GPU, default 6), timed as ONE region between two CUDA
 events with barrier + synchronize on both sides.  Prints ONE JSON line on rank 0:
 
   value      volumes/s, whole job, volumes already resident in HBM when the timed region starts
@@ -414,7 +414,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--contexts", type=int, default=4, help="extraction contexts in flight per GPU")
+    ap.add_argument("--contexts", type=int, default=6, help="extraction contexts in flight per GPU")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
