@@ -210,7 +210,7 @@ def run_ours(args):
     ref_cuda = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_cuda_baseline.py"), "--reps", "2", "--timeout", "90"],
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_cuda_baseline.py"), "--reps", "3", "--timeout", "90"],
                                  capture_output=True, text=True, timeout=400)
             r = json.loads(out.stdout.strip().splitlines()[-1])
             if "d0_best_stage_sum_s" in r:
@@ -218,7 +218,7 @@ def run_ours(args):
                             "stage_sum_s": r["d0_best_stage_sum_s"], "process_wall_s": r["d0_best_wall_s"],
                             "rows": r["d0_runs"][0].get("rows"), "cpu_rows": (r.get("cpu") or {}).get("rows"),
                             "single_core_cpu_stage_sum_s": (r.get("cpu") or {}).get("stage_sum_s"),
-                            "sample": "best of 2 CLI runs on one MNI phantom; value = 1 / sum of the reference's own per-stage timers "
+                            "sample": "best of 3 CLI runs on one MNI phantom (its run-to-run spread is large: 0.17-2.1 s); value = 1 / sum of the reference's own per-stage timers "
                                       "(pyramid, DoG, detection: excludes its CPU keypoint/descriptor stages, file I/O and CUDA start-up)"}
             else:
                 ref_cuda = {"unavailable": r.get("unavailable") or str(r.get("d0_runs"))[:200]}
