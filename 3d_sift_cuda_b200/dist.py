@@ -101,15 +101,23 @@ def merge_slab_rows(per_rank, n_slab_octaves):
     per_rank[r][o] = (features, level, is_max) with one level / is_max entry per feature row, rows in the
     engine's order (level up, minima then maxima, raster).  Order of the merged list: octave, level,
     minima then maxima, then ranks in z order (= raster order, slabs are z-contiguous)."""
+    # every (rank, octave) result is already grouped by (level, minima then maxima): slice it by the group
+    # counts (views, no boolean masks -- at 1024^3 the rows are 216 MB) and let the caller concatenate once
     out = []
     for o in range(n_slab_octaves):
-        for level in (1, 2, 3):
-            for is_max in (0, 1):
-                for r in range(len(per_rank)):
-                    feats, lv, mx = per_rank[r][o]
-                    sel = (lv == level) & (mx == is_max)
-                    if sel.any():
-                        out.append(feats[sel])
+        groups = []
+        for r in range(len(per_rank)):
+            feats, lv, mx = per_rank[r][o]
+            key = (np.asarray(lv, np.int64) - 1) * 2 + np.asarray(mx, np.int64)
+            if len(key) > 1 and np.any(key[1:] < key[:-1]):
+                raise ValueError("slab rows are not in (level, min/max) order")
+            cnt = np.bincount(key, minlength=6)[:6] if len(key) else np.zeros(6, np.int64)
+            off = np.concatenate([[0], np.cumsum(cnt)])
+            groups.append((feats, off))
+        for g in range(6):
+            for feats, off in groups:
+                if off[g + 1] > off[g]:
+                    out.append(feats[off[g]:off[g + 1]])
     return out
 
 
