@@ -29,13 +29,18 @@ __device__ __forceinline__ float4 addv(float4 a, float4 b) { return make_float4(
 __device__ __forceinline__ float2 subv(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float4 subv(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 template <typename VT> __device__ __forceinline__ VT zerov();
+template <> __device__ __forceinline__ float zerov<float>() { return 0.0f; }
 template <> __device__ __forceinline__ float2 zerov<float2>() { return make_float2(0.f, 0.f); }
 template <> __device__ __forceinline__ float4 zerov<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 template <typename VT> __device__ __forceinline__ VT ldgv(const float *p) { return __ldg(reinterpret_cast<const VT *>(p)); }
 
 // K outputs from a window of K+2R inputs (win[c + j] is tap j of output c).  Inputs are visited in
 // increasing order, so every output accumulates its taps j = 0..2R in order.
-template <int R, int K, typename F>
+// ZERO_START: the sum starts as 0.0f + (first product), like the reference's `fSum = 0; fSum += ...`
+// (GaussBlur3D.cpp:54-58).  It only matters for -0.0: a window of -0.0 voxels (masked images: negative value
+// x 0) sums to +0.0 in the reference.  The x pass -- the only pass that can see -0.0 inputs, a float sum is
+// never -0.0 afterwards -- pays one extra FADD per output for it; the y and z passes start from the product.
+template <int R, int K, typename F, bool ZERO_START = false>
 __device__ __forceinline__ void conv_segment(const F *win, F *acc, const TapsSmall &taps)
 {
 #pragma unroll
@@ -46,7 +51,7 @@ __device__ __forceinline__ void conv_segment(const F *win, F *acc, const TapsSma
 #pragma unroll
         for (int c = 0; c < K; c++) {
             const int j = m - c;
-            if (j == 0) acc[c] = p[0];
+            if (j == 0) acc[c] = ZERO_START ? addv(zerov<F>(), p[0]) : p[0];
             else if (j > 0 && j <= 2 * R) acc[c] = addv(acc[c], p[j <= R ? j : 2 * R - j]);
         }
     }
@@ -120,7 +125,7 @@ blur_xy2_kernel(const __grid_constant__ CUtensorMap in_map, float *__restrict__ 
                     win[4 * q] = u.x; win[4 * q + 1] = u.y; win[4 * q + 2] = u.z; win[4 * q + 3] = u.w;
                 }
                 float acc[kKX];
-                conv_segment<R, kKX, float>(win + (RP - R), acc, taps);
+                conv_segment<R, kKX, float, true>(win + (RP - R), acc, taps);
                 const int xg = x0 + xs * kKX;
                 if (xg + kKX > X) {       // padding columns (x >= X) stay zero in every pass
 #pragma unroll

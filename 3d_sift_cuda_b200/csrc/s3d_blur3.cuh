@@ -97,7 +97,7 @@ __device__ __forceinline__ void f3_x_pass(const float *in_t, float *xb, int t, i
             win[4 * q] = w4.x; win[4 * q + 1] = w4.y; win[4 * q + 2] = w4.z; win[4 * q + 3] = w4.w;
         }
         float o[kF3KX];
-        conv_segment<R, kF3KX, float>(win + (RP - R), o, taps);
+        conv_segment<R, kF3KX, float, true>(win + (RP - R), o, taps);
         const int xg = x0 + xs * kF3KX;
         if (xg + kF3KX > X) {       // padding columns (x >= X) stay zero in every pass
 #pragma unroll

@@ -170,7 +170,7 @@ blur_fused_kernel(const __grid_constant__ CUtensorMap in_map, const float *__res
 #pragma unroll
                 for (int q = 0; q < 2 * R + 2; q++) win[q] = src[q];
             }
-            float o0 = taps.w[0] * win[0], o1 = taps.w[0] * win[1];
+            float o0 = 0.0f + taps.w[0] * win[0], o1 = 0.0f + taps.w[0] * win[1];      // reference: fSum = 0; fSum += ...
 #pragma unroll
             for (int j = 1; j <= 2 * R; j++) { o0 = o0 + taps.w[j] * win[j]; o1 = o1 + taps.w[j] * win[j + 1]; }
             // padding columns (x >= X) must stay zero in every pass
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) blur_xy_kernel(const __grid_constant__ CU
         float o[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            float a = taps.w[0] * win[k + RP - R];
+            float a = 0.0f + taps.w[0] * win[k + RP - R];      // reference: fSum = 0; fSum += ...
 #pragma unroll
             for (int j = 1; j <= 2 * R; j++) a = a + taps.w[j] * win[k + j + RP - R];
             o[k] = (x0 + i4 + k < X) ? a : 0.0f;       // padding columns stay zero

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) blur_x_kernel(const float *__restrict__ i
     float o[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        float acc = taps.w[0] * win[k + RP - R];
+        float acc = 0.0f + taps.w[0] * win[k + RP - R];      // fSum = 0; fSum += ... : a window of -0.0 voxels sums to +0.0
 #pragma unroll
         for (int j = 1; j <= 2 * R; j++) acc = acc + taps.w[j] * win[k + j + RP - R];
         o[k] = (x0 + k < X) ? acc : 0.0f;

@@ -377,3 +377,31 @@ def test_baseline_configs_full_size_bit_exact(pkg, oracle, engine, config, descr
     assert len(want) > 500
     assert feats.tobytes() == want.tobytes()
     assert (np.sort(feats["pc"], axis=1) == np.arange(64, dtype=np.float32)).all()
+
+
+@pytest.mark.parametrize("env", [{}, {"S3D_F3_MAXR": "8"}, {"S3D_F3_MAXR": "0", "S3D_BLUR2": "0"}])
+def test_negative_zero_voxels_bit_exact(pkg, oracle, monkeypatch, env):
+    """Masked images carry -0.0 voxels (negative value x 0).  The reference starts every tap sum from +0.0
+    (GaussBlur3D.cpp:54-58), so a window of -0.0 voxels blurs to +0.0: the levels must match bit for bit."""
+    import torch
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    eng = pkg.Engine(0)
+    try:
+        vol = pkg.phantom.blob_phantom((56, 48, 40), 12, 30) - 50.0       # blobs on a zero background
+        vol[np.abs(vol) < 1.0] = 0.0
+        vol[:, :24, :] *= -1.0                                            # half of the zeros become -0.0
+        vol[20:30, 30:40, 10:30] = -0.0
+        assert np.signbit(vol[vol == 0]).any() and (~np.signbit(vol[vol == 0])).any()
+        for sigma in (1.2263, 1.5199, 3.09):
+            want = oracle.blur(vol, sigma)
+            d_in = to_dev(vol)
+            d_tmp, d_out, d_dog = torch.zeros_like(d_in), torch.zeros_like(d_in), torch.zeros_like(d_in)
+            ready()
+            eng.blur3d(d_in, d_tmp, d_out, 56, pkg.gaussian_taps(sigma), d_dog)
+            eng.sync()
+            assert (bits(from_dev(d_out, 56)) == bits(want)).all(), sigma
+            assert (bits(from_dev(d_dog, 56)) == bits(oracle.dog(vol, want))).all(), sigma
+        assert eng.extract(vol).tobytes() == oracle.extract(vol)["features"].tobytes()
+    finally:
+        eng.close()
