@@ -38,6 +38,7 @@ EXPORTS = [
     "s3d_batch_create", "s3d_batch_destroy", "s3d_batch_last_error", "s3d_batch_extract", "s3d_batch_extract_device",
     "s3d_batch_launches_per_volume", "s3d_host_alloc", "s3d_host_free",
     "s3d_extract_typed", "s3d_extract_typed_async", "s3d_batch_extract_typed",
+    "s3d_write_features_bin", "s3d_read_features_text",
 ]
 
 # NIfTI datatype codes accepted by the typed entry points (reference featExtract.cpp:18-77)
@@ -120,6 +121,8 @@ def load_library():
     L.s3d_copy_level_device.argtypes = [vp, i, i, i, i, i, vp]
     L.s3d_get_row_keypoints.argtypes = [vp, C.POINTER(vp), C.POINTER(i)]
     L.s3d_write_features_text.argtypes = [C.c_char_p, vp, i, f, i, C.POINTER(C.c_char_p)]
+    L.s3d_write_features_bin.argtypes = [C.c_char_p, vp, i, f]
+    L.s3d_read_features_text.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(i)]
     L.s3d_batch_create.argtypes = [i, i, C.POINTER(vp)]
     L.s3d_batch_destroy.argtypes = [vp]
     L.s3d_batch_destroy.restype = None
@@ -423,6 +426,25 @@ class Batch:
 
     def launches_per_volume(self):
         return self.L.s3d_batch_launches_per_volume(self.b)
+
+
+def write_features_bin(path, feats, eig_thres=-1.0):
+    """msFeature3DVectorOutputBin (MultiScale.h:228-303)."""
+    L = load_library()
+    f = np.ascontiguousarray(feats, dtype=FEATURE_DTYPE)
+    st = L.s3d_write_features_bin(path.encode(), f.ctypes.data_as(C.c_void_p), len(f), eig_thres)
+    if st != 0:
+        raise S3DError("s3d_write_features_bin: %s" % _STATUS.get(st, st))
+
+
+def read_features_text(path):
+    """msFeature3DVectorInputText (MultiScale.h:305-384): feature rows of a text .key file."""
+    L = load_library()
+    out, n = C.c_void_p(), C.c_int()
+    st = L.s3d_read_features_text(path.encode(), C.byref(out), C.byref(n))
+    if st != 0:
+        raise S3DError("s3d_read_features_text(%s): %s" % (path, _STATUS.get(st, st)))
+    return _copy_out(out, n.value, FEATURE_DTYPE, L.s3d_free)
 
 
 def write_features_text(path, feats, shape_xyz, eig_thres=140.0, comments=None):

@@ -1621,3 +1621,69 @@ extern "C" s3d_status s3d_write_features_text(const char *path, const s3d_featur
     fclose(f);
     return S3D_OK;
 }
+
+// msFeature3DVectorOutputBin, reference MultiScale.h:228-303
+extern "C" s3d_status s3d_write_features_bin(const char *path, const s3d_feature *feats, int n, float fEigThres)
+{
+    if (!path || (n > 0 && !feats)) return S3D_ERR_INVALID;
+    FILE *f = fopen(path, "wb");
+    if (!f) return S3D_ERR_INVALID;
+    auto keep = [&](const s3d_feature &ft) {
+        float fEigSum = ft.eigs[0] + ft.eigs[1] + ft.eigs[2];
+        float fEigPrd = ft.eigs[0] * ft.eigs[1] * ft.eigs[2];
+        float fEigSumProd = fEigSum * fEigSum * fEigSum;
+        return (fEigSumProd < fEigThres * fEigPrd || fEigThres < 0);
+    };
+    int cnt = 0;
+    for (int i = 0; i < n; i++) if (keep(feats[i])) cnt++;
+    fprintf(f, "# featExtract %s\n", "1.1");
+    fprintf(f, "Features: %d\n", cnt);
+    for (int i = 0; i < n; i++) {
+        const s3d_feature &ft = feats[i];
+        if (!keep(ft)) continue;
+        fwrite(&ft.x, sizeof(float), 1, f);
+        fwrite(&ft.y, sizeof(float), 1, f);
+        fwrite(&ft.z, sizeof(float), 1, f);
+        fwrite(&ft.scale, sizeof(float), 1, f);
+        fwrite(ft.ori, sizeof(float), 9, f);
+        fwrite(ft.eigs, sizeof(float), 3, f);
+        fwrite(&ft.flag, sizeof(unsigned int), 1, f);
+        unsigned char pc[64];
+        for (int j = 0; j < 64; j++) pc[j] = (unsigned char)(ft.pc[j]);
+        fwrite(pc, sizeof(unsigned char), 64, f);
+    }
+    fclose(f);
+    return S3D_OK;
+}
+
+// msFeature3DVectorInputText, reference MultiScale.h:305-384
+extern "C" s3d_status s3d_read_features_text(const char *path, s3d_feature **out, int *n_out)
+{
+    if (!path || !out || !n_out) return S3D_ERR_INVALID;
+    *out = nullptr; *n_out = 0;
+    FILE *f = fopen(path, "rt");
+    if (!f) return S3D_ERR_INVALID;
+    char buff[400];
+    buff[0] = '#';
+    while (buff[0] == '#')       // read past comments
+        if (!fgets(buff, sizeof(buff), f)) { fclose(f); return S3D_ERR_INVALID; }
+    int n = 0;
+    if (sscanf(buff, "Features: %d\n", &n) <= 0 || n <= 0) { fclose(f); return S3D_ERR_INVALID; }
+    if (!fgets(buff, sizeof(buff), f) || !strstr(buff, "Scale-space location[x y z scale]")) { fclose(f); return S3D_ERR_INVALID; }
+    s3d_feature *h = (s3d_feature *)malloc(sizeof(s3d_feature) * (size_t)n);
+    if (!h) { fclose(f); return S3D_ERR_NOMEM; }
+    for (int i = 0; i < n; i++) {
+        s3d_feature &ft = h[i];
+        bool ok = fscanf(f, "%f\t%f\t%f\t%f\t", &ft.x, &ft.y, &ft.z, &ft.scale) == 4;
+        for (int j = 0; j < 9 && ok; j++) ok = fscanf(f, "%f\t", &ft.ori[j]) == 1;
+        for (int j = 0; j < 3 && ok; j++) ok = fscanf(f, "%f\t", &ft.eigs[j]) == 1;
+        int flag = 0;
+        if (ok) ok = fscanf(f, "%d\t", &flag) == 1;
+        ft.flag = (unsigned int)flag;
+        for (int j = 0; j < 64 && ok; j++) ok = fscanf(f, "%f\t", &ft.pc[j]) == 1;
+        if (!ok) { free(h); fclose(f); return S3D_ERR_INVALID; }     // the reference asserts here
+    }
+    fclose(f);
+    *out = h; *n_out = n;
+    return S3D_OK;
+}

@@ -238,6 +238,14 @@ int s3d_last_launch_count(s3d_ctx *ctx);
 s3d_status s3d_write_features_text(const char *path, const s3d_feature *feats, int n, float eig_thres,
                                    int n_comments, const char *const *comments);
 
+/* Binary feature file: msFeature3DVectorOutputBin (R/src_common/MultiScale.h:228-303) -- two text
+ * header lines, then per kept feature x, y, z, scale, ori[9], eigs[3] (float32), the info flag (uint32) and the
+ * 64 descriptor values as unsigned char.  eig_thres < 0 keeps every row, like the reference's default. */
+s3d_status s3d_write_features_bin(const char *path, const s3d_feature *feats, int n, float eig_thres);
+/* Text feature file reader: msFeature3DVectorInputText (R/src_common/MultiScale.h:305-384), the reader
+ * featMatchMultiple uses (R/featMatchMultiple/featMatchMultiple.cpp:596).  *out is malloc'ed (s3d_free). */
+s3d_status s3d_read_features_text(const char *path, s3d_feature **out, int *n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -292,6 +292,38 @@ int ref_write_text(const ref_feature *feats, int n, const char *path, int x, int
     return msFeature3DVectorOutputText(vec, (char *)path, 140.0f, 3, cc);
 }
 
+/* msFeature3DVectorOutputBin (MultiScale.h:228-303) on records produced by anyone. */
+int ref_write_bin(const ref_feature *feats, int n, const char *path, float eig_thres)
+{
+    std::vector<Feature3D> vec(n);
+    for (int i = 0; i < n; i++) {
+        vec[i].m_uiInfo = feats[i].flag;
+        vec[i].x = feats[i].x; vec[i].y = feats[i].y; vec[i].z = feats[i].z; vec[i].scale = feats[i].scale;
+        memcpy(&vec[i].ori[0][0], feats[i].ori, sizeof(feats[i].ori));
+        memcpy(vec[i].eigs, feats[i].eigs, sizeof(feats[i].eigs));
+        memcpy(vec[i].m_pfPC, feats[i].pc, sizeof(feats[i].pc));
+    }
+    return msFeature3DVectorOutputBin(vec, (char *)path, eig_thres);
+}
+
+/* msFeature3DVectorInputText (MultiScale.h:305-384): the reader featMatchMultiple uses. */
+int ref_read_text(const char *path, ref_feature **feats)
+{
+    std::vector<Feature3D> vec;
+    if (msFeature3DVectorInputText(vec, (char *)path, 140.0f) < 0) return -1;
+    int n = (int)vec.size();
+    *feats = (ref_feature *)malloc(sizeof(ref_feature) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) {
+        ref_feature &o = (*feats)[i];
+        o.flag = vec[i].m_uiInfo;
+        o.x = vec[i].x; o.y = vec[i].y; o.z = vec[i].z; o.scale = vec[i].scale;
+        memcpy(o.ori, &vec[i].ori[0][0], sizeof(o.ori));
+        memcpy(o.eigs, vec[i].eigs, sizeof(o.eigs));
+        memcpy(o.pc, vec[i].m_pfPC, sizeof(o.pc));
+    }
+    return n;
+}
+
 void ref_free(void *p) { free(p); }
 
 } // extern "C"

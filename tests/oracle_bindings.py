@@ -183,6 +183,9 @@ class Reference:
         L.ref_extract.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_write_text.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int]
+        if hasattr(L, "ref_write_bin"):
+            L.ref_write_bin.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_float]
+            L.ref_read_text.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         L.ref_free.argtypes = [C.c_void_p]
 
     def taps(self, sigma):
@@ -257,3 +260,13 @@ class Reference:
     def write_text(self, feats, path, shape_xyz):
         f = np.ascontiguousarray(feats, dtype=FEATURE_DTYPE)
         return self.lib.ref_write_text(f.ctypes.data_as(C.c_void_p), len(f), path.encode(), *shape_xyz)
+
+    def write_bin(self, feats, path, eig_thres=-1.0):
+        f = np.ascontiguousarray(feats, dtype=FEATURE_DTYPE)
+        return self.lib.ref_write_bin(f.ctypes.data_as(C.c_void_p), len(f), path.encode(), eig_thres)
+
+    def read_text(self, path):
+        out = C.c_void_p()
+        n = self.lib.ref_read_text(path.encode(), C.byref(out))
+        assert n >= 0
+        return _take(out, n, FEATURE_DTYPE, self.lib.ref_free)

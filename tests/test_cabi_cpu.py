@@ -62,3 +62,43 @@ def test_text_writer_matches_reference_writer(pkg, tmp_path):
     out = str(tmp_path / "f.key")
     pkg.api.write_features_text(out, feats, (64, 64, 64))
     assert open(out, "rb").read() == open(os.path.join(HERE, "golden", "blob64_ref.key"), "rb").read()
+
+
+def test_binary_writer_matches_reference_writer(pkg, tmp_path):
+    """msFeature3DVectorOutputBin (MultiScale.h:228-303): byte-identical files, with and without the eigenvalue filter."""
+    gold = np.load(os.path.join(HERE, "golden", "ref_golden.npz"))
+    feats = gold["blob64_features"]
+    for name, thres in (("blob64_ref.bin", -1.0), ("blob64_ref_eig140.bin", 140.0)):
+        out = str(tmp_path / name)
+        pkg.api.write_features_bin(out, feats, thres)
+        assert open(out, "rb").read() == open(os.path.join(HERE, "golden", name), "rb").read(), name
+
+
+def test_text_reader_matches_reference_reader(pkg, tmp_path):
+    """msFeature3DVectorInputText (MultiScale.h:305-384) on the reference's own .key file, and a write -> read round trip."""
+    want = np.load(os.path.join(HERE, "golden", "blob64_key_readback.npy"))
+    got = pkg.api.read_features_text(os.path.join(HERE, "golden", "blob64_ref.key"))
+    assert len(got) == len(want) > 0 and got.tobytes() == want.tobytes()
+    out = str(tmp_path / "rt.key")
+    pkg.api.write_features_text(out, got, (64, 64, 64))
+    again = pkg.api.read_features_text(out)
+    assert again.tobytes() == got.tobytes()
+    with pytest.raises(pkg.S3DError):
+        pkg.api.read_features_text(str(tmp_path / "missing.key"))
+    bad = tmp_path / "bad.key"
+    bad.write_text("# comment\nFeatures: 0\n")
+    with pytest.raises(pkg.S3DError):
+        pkg.api.read_features_text(str(bad))
+
+
+def test_feature_io_against_live_reference(pkg, reference, tmp_path):
+    """Same two functions against the reference build itself (oracle/_ref) on other rows."""
+    gold = np.load(os.path.join(HERE, "golden", "ref_golden.npz"))
+    feats = gold["brain_small_features"]
+    a, b = str(tmp_path / "a.bin"), str(tmp_path / "b.bin")
+    pkg.api.write_features_bin(a, feats, 140.0)
+    assert reference.write_bin(feats, b, 140.0) == 0
+    assert open(a, "rb").read() == open(b, "rb").read()
+    key = str(tmp_path / "f.key")
+    pkg.api.write_features_text(key, feats, (91, 109, 91))
+    assert pkg.api.read_features_text(key).tobytes() == reference.read_text(key).tobytes()
