@@ -777,16 +777,22 @@ static s3d_status plan_build(s3d_ctx *ctx, int X, int Y, int Z, const s3d_params
         for (Plan *q : ctx->plans) if (q->last_use < lru->last_use) lru = q;
         plan_destroy(ctx, lru);
     }
-    Plan *p = new Plan();
-    p->last_use = ctx->use_clock;
-    ctx->plans.push_back(p);
-    ctx->plan = p;
-    ctx->has_result = false;
-    s3d_status st = plan_fill(ctx, p, X, Y, Z, prm, kp_cap, row_cap);
-    if (st != S3D_OK) {       // never leave a half-built plan behind (its key would match the next call)
+    s3d_status st = S3D_OK;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        Plan *p = new Plan();
+        p->last_use = ctx->use_clock;
+        ctx->plans.push_back(p);
+        ctx->plan = p;
+        ctx->has_result = false;
+        st = plan_fill(ctx, p, X, Y, Z, prm, kp_cap, row_cap);
+        if (st == S3D_OK) break;
+        // never leave a half-built plan behind (its key would match the next call)
         std::string msg = ctx->err;
         plan_destroy(ctx, p);
         ctx->err = msg;
+        // out of device memory with other plans resident: release them all and try once more
+        if (st != S3D_ERR_NOMEM || ctx->plans.empty() || attempt == 1) break;
+        while (!ctx->plans.empty()) plan_destroy(ctx, ctx->plans.back());
     }
     return st;
 }
