@@ -1138,14 +1138,19 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ P
             }
             __syncthreads();
             PHASE(19);
-            if (threadIdx.x < 64) {
-                // thread owns PC[((sz*2+sy)*2+sx)*8 + k]; walks the voxels that can reach it in raster order
-                const int k = threadIdx.x & 7, sx = (threadIdx.x >> 3) & 1, sy = (threadIdx.x >> 4) & 1, sz = (threadIdx.x >> 5) & 1;
+            if (threadIdx.x < 32) {
+                // thread owns the two bins PC[s*8 + k0], PC[s*8 + k0 + 1] of spatial cell s = (sz*2+sy)*2+sx and walks
+                // the 6^3 voxels that can reach the cell in raster order, so each bin still receives its terms in
+                // the reference's order; the weight product is formed once per voxel and goes to whichever of the
+                // two bins the voxel's orientation selects.  (One warp, two accumulators per lane: 64 threads with
+                // one bin each executed 2.2x the instructions -- describe is issue bound, profiles/README.md.)
+                const int s = threadIdx.x >> 2, k0 = (threadIdx.x & 3) * 2, k1 = k0 + 1;
+                const int sx = s & 1, sy = (s >> 1) & 1, sz = (s >> 2) & 1;
                 const int x0 = sx ? 5 : 0, y0 = sy ? 5 : 0, z0 = sz ? 5 : 0;
                 float wxs[6];
 #pragma unroll
                 for (int q = 0; q < 6; q++) wxs[q] = sx ? (1.0f - S.wlo[x0 + q]) : S.wlo[x0 + q];
-                float acc = 0.0f;
+                float acc0 = 0.0f, acc1 = 0.0f;
                 for (int z = z0; z <= z0 + 5; z++) {
                     float wz = sz ? (1.0f - S.wlo[z]) : S.wlo[z];
                     for (int y = y0; y <= y0 + 5; y++) {
@@ -1156,11 +1161,15 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ P
 #pragma unroll
                         for (int q = 0; q < 6; q++) { b[q] = __float_as_int(S.dy[i0 + q]); mg[q] = S.dx[i0 + q]; }
 #pragma unroll
-                        for (int q = 0; q < 6; q++)
-                            if (b[q] == k) acc = acc + mg[q] * wxs[q] * wy * wz;
+                        for (int q = 0; q < 6; q++) {
+                            const float v = mg[q] * wxs[q] * wy * wz;
+                            if (b[q] == k0) acc0 = acc0 + v;
+                            else if (b[q] == k1) acc1 = acc1 + v;
+                        }
                     }
                 }
-                S.pc[threadIdx.x] = acc;
+                S.pc[s * 8 + k0] = acc0;
+                S.pc[s * 8 + k1] = acc1;
             }
             __syncthreads();
             PHASE(20);
