@@ -60,10 +60,11 @@ __device__ __forceinline__ void conv_segment(const F *win, F *acc, const TapsSma
 // ---------------------------------------------------------------------------------------------------
 // x + y passes on one tile.  Tile size (TX x TY) is chosen by the host per volume shape.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kKX = 16, kKY = 16, kXY2Threads = 256;
+constexpr int kKX = 16, kXY2Threads = 256;      // y segments are 8 or 16 outputs long (template parameter KY)
 
 struct XY2Tile {
-    int TX, TY;          // outputs per tile: TX % 32 == 0, TY % kKY == 0
+    int TX, TY;          // outputs per tile: TX % 32 == 0, TY % KY == 0
+    int KY;              // y-segment length of the kernel instance that runs this tile (host side only)
     int W_in, W_xb;      // shared-memory row pitches (floats), pitch/4 odd
     int rows, rows8;     // TY + 2R, rounded up to 8
     unsigned tile_bytes; // bytes one TMA box brings in
@@ -74,7 +75,7 @@ struct XY2Tile {
 // staged input is double buffered, so the TMA load of the CTA's next tile is in flight while it computes
 // the current one (with one tile per CTA the TMA round trip was exposed: ncu showed the warps parked on
 // the mbarrier 3.4 cycles per issued instruction).
-template <int R>
+template <int R, int KY>
 __global__ void __launch_bounds__(kXY2Threads, 2)
 blur_xy2_kernel(const __grid_constant__ CUtensorMap in_map, float *__restrict__ out, int X, int Y, int pitch,
                 const __grid_constant__ XY2Tile tile, int n_tx, int n_ty, int n_tiles, const __grid_constant__ TapsSmall taps)
@@ -147,27 +148,27 @@ blur_xy2_kernel(const __grid_constant__ CUtensorMap in_map, float *__restrict__ 
             }
         }
 
-        // ---- y pass: item = (column pair, segment of kKY outputs); consecutive lanes = consecutive pairs
+        // ---- y pass: item = (column pair, segment of KY outputs); consecutive lanes = consecutive pairs
         {
             const int n_pairs = tile.TX >> 1;
-            const int n_items = n_pairs * (tile.TY / kKY);
+            const int n_items = n_pairs * (tile.TY / KY);
             for (int it = t; it < n_items; it += kXY2Threads) {
                 const int ys = it / n_pairs, cp = it - ys * n_pairs;
-                const float *col = XB + (ys * kKY) * tile.W_xb + 2 * cp;
-                float2 win[kKY + 2 * R];
+                const float *col = XB + (ys * KY) * tile.W_xb + 2 * cp;
+                float2 win[KY + 2 * R];
 #pragma unroll
-                for (int m = 0; m < kKY + 2 * R; m++) win[m] = *reinterpret_cast<const float2 *>(col + m * tile.W_xb);
-                float2 acc[kKY];
-                conv_segment<R, kKY, float2>(win, acc, taps);
-                const int gx = x0 + 2 * cp, gy = y0 + ys * kKY;
+                for (int m = 0; m < KY + 2 * R; m++) win[m] = *reinterpret_cast<const float2 *>(col + m * tile.W_xb);
+                float2 acc[KY];
+                conv_segment<R, KY, float2>(win, acc, taps);
+                const int gx = x0 + 2 * cp, gy = y0 + ys * KY;
                 if (gx < pitch) {
                     float *dst = out + ((long long)z * Y + gy) * pitch + gx;
-                    if (gy + kKY <= Y) {
+                    if (gy + KY <= Y) {
 #pragma unroll
-                        for (int q = 0; q < kKY; q++) *reinterpret_cast<float2 *>(dst + (long long)q * pitch) = acc[q];
+                        for (int q = 0; q < KY; q++) *reinterpret_cast<float2 *>(dst + (long long)q * pitch) = acc[q];
                     } else {
 #pragma unroll
-                        for (int q = 0; q < kKY; q++) if (gy + q < Y) *reinterpret_cast<float2 *>(dst + (long long)q * pitch) = acc[q];
+                        for (int q = 0; q < KY; q++) if (gy + q < Y) *reinterpret_cast<float2 *>(dst + (long long)q * pitch) = acc[q];
                     }
                 }
             }
@@ -297,11 +298,11 @@ static inline bool taps_symmetric(const float *taps, int n)
 // shared-memory pitch >= w with pitch % 4 == 0 and (pitch / 4) odd
 static inline int odd_pitch(int w) { int p = (w + 3) & ~3; if (((p >> 2) & 1) == 0) p += 4; return p; }
 
-static inline XY2Tile make_xy2_tile(int TX, int TY, int R)
+static inline XY2Tile make_xy2_tile(int TX, int TY, int R, int KY = 16)
 {
     XY2Tile t;
     int RP = (R + 3) & ~3;
-    t.TX = TX; t.TY = TY;
+    t.TX = TX; t.TY = TY; t.KY = KY;
     t.W_in = odd_pitch(TX + 2 * RP);
     t.W_xb = odd_pitch(TX);
     t.rows = TY + 2 * R;
@@ -323,26 +324,41 @@ static inline XY2Tile choose_xy2_tile(int pitch, int Y, int Z, int R, int sm_cou
         const char *fx = getenv("S3D_XY2_TX"), *fy = getenv("S3D_XY2_TY");
         if (fx && fy) { force_tx = atoi(fx); force_ty = atoi(fy); }
     }
-    if (force_tx >= 32 && force_tx % 32 == 0 && force_ty >= kKY && force_ty % kKY == 0) {
-        XY2Tile t = make_xy2_tile(force_tx, force_ty, R);
-        if (t.smem <= 113 * 1024 && t.W_in <= 256 && t.rows <= 256) return t;
-    }
-    // Cost model: a tile costs (x-pass rounds) + 2 (y-pass rounds) item times -- an x item is 16 outputs on
-    // 8-lane groups (32 groups per round), a y item 32 outputs (256 per round) -- and two persistent CTAs
-    // per SM share the tiles.
-    XY2Tile best = make_xy2_tile(32, kKY, R);
-    double best_cost = 1e300;
-    for (int TX = 32; TX <= 128; TX += 32)
-        for (int TY = kKY; TY <= 128; TY += kKY) {
-            XY2Tile t = make_xy2_tile(TX, TY, R);
-            if (t.smem > (size_t)max_kb * 1024 || t.W_in > 256 || t.rows > 256) continue;
-            long long tiles = (long long)((pitch + TX - 1) / TX) * ((Y + TY - 1) / TY) * Z;
-            long long rounds = (tiles + 2 * sm_count - 1) / (2 * sm_count);
-            int x_items = (t.rows8 / 8) * (TX / kKX), y_items = (TX / 2) * (TY / kKY);
-            double work = (double)((x_items + 31) / 32) + 2.0 * ((y_items + kXY2Threads - 1) / kXY2Threads) + 0.5;
-            double cost = (double)rounds * work;
-            if (cost < best_cost) { best_cost = cost; best = t; }
+    static int force_ky = 0;
+    if (force_ky == 0) { const char *e = getenv("S3D_XY2_KY"); force_ky = (e && (atoi(e) == 8 || atoi(e) == 16)) ? atoi(e) : -1; }
+    if (force_tx >= 32 && force_tx % 32 == 0 && force_ty >= 8 && force_ty % 8 == 0) {
+        int ky = force_ky > 0 ? force_ky : (force_ty % 16 == 0 ? 16 : 8);
+        if (force_ty % ky == 0) {
+            XY2Tile t = make_xy2_tile(force_tx, force_ty, R, ky);
+            if (t.smem <= 113 * 1024 && t.W_in <= 256 && t.rows <= 256) return t;
         }
+    }
+    // Cost model in FP32 instructions per thread: the x pass runs ceil(items / 32) rounds of 16-output items on
+    // 8-lane groups, the y pass ceil(items / 256) rounds of 2 x KY-output items; a round costs one item whether
+    // or not every thread has one (the phases end at a block barrier), so shorter y segments (KY = 8: more,
+    // smaller items) win whenever 16-output segments leave most of the threads without an item.  Two persistent
+    // CTAs per SM share the tiles.
+    XY2Tile best = make_xy2_tile(32, 16, R);
+    double best_cost = 1e300;
+    const double cx = (double)(kKX + R) * (R + 1) + 2.0 * R * kKX + 24.0;
+    for (int KY = 8; KY <= 16; KY += 8) {
+        // measured (profiles/README.md): 8-output y segments fill more threads but are never faster than 16-output
+        // ones at MNI size (19.9 / 24.2 / 31.1 us against 18.5 / 23.2 / 30.1 us at 7 / 11 / 17 taps), so KY = 8 is
+        // only used on request (S3D_XY2_KY=8)
+        if (KY != (force_ky > 0 ? force_ky : 16)) continue;
+        const double cy = 2.0 * ((double)(KY + R) * (R + 1) + 2.0 * R * KY) + 2.0 * KY + 2.0 * R + 16.0;
+        for (int TX = 32; TX <= 128; TX += 32)
+            for (int TY = KY; TY <= 128; TY += KY) {
+                XY2Tile t = make_xy2_tile(TX, TY, R, KY);
+                if (t.smem > (size_t)max_kb * 1024 || t.W_in > 256 || t.rows > 256) continue;
+                long long tiles = (long long)((pitch + TX - 1) / TX) * ((Y + TY - 1) / TY) * Z;
+                long long rounds = (tiles + 2 * sm_count - 1) / (2 * sm_count);
+                int x_items = (t.rows8 / 8) * (TX / kKX), y_items = (TX / 2) * (TY / KY);
+                double work = cx * ((x_items + 31) / 32) + cy * ((y_items + kXY2Threads - 1) / kXY2Threads) + 150.0;
+                double cost = (double)rounds * work;
+                if (cost < best_cost) { best_cost = cost; best = t; }
+            }
+    }
     return best;
 }
 
@@ -362,7 +378,9 @@ static bool make_volume_map_box(CUtensorMap *map, const float *vol, int Y, int Z
 template <int R>
 static cudaError_t set_xy2_attr_r()
 {
-    return cudaFuncSetAttribute(blur_xy2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(blur_xy2_kernel<R, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(blur_xy2_kernel<R, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
 }
 // opt-in to > 48 KB of dynamic shared memory for every radius (once per device, from s3d_ctx_create)
 static cudaError_t init_blur2_attrs()
@@ -396,7 +414,8 @@ static bool launch_blur_xy2(cudaStream_t st, const float *in, float *tmp, int X,
     // every SM is better spent on the memory-bound kernels of the other volumes in flight
     const long long slots = (long long)(ctas_per_sm < 1 ? 1 : ctas_per_sm) * sm_count;
     const int grid = (int)(n_tiles < slots ? n_tiles : slots);
-    blur_xy2_kernel<R><<<grid, kXY2Threads, tile.smem, st>>>(map, tmp, X, Y, pitch, tile, n_tx, n_ty, (int)n_tiles, t);
+    if (tile.KY == 8) blur_xy2_kernel<R, 8><<<grid, kXY2Threads, tile.smem, st>>>(map, tmp, X, Y, pitch, tile, n_tx, n_ty, (int)n_tiles, t);
+    else blur_xy2_kernel<R, 16><<<grid, kXY2Threads, tile.smem, st>>>(map, tmp, X, Y, pitch, tile, n_tx, n_ty, (int)n_tiles, t);
     *err = cudaGetLastError();
     return true;
 }

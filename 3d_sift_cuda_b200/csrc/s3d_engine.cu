@@ -130,7 +130,7 @@ static void set_carveout(K kernel, int pct) { cudaFuncSetAttribute(kernel, cudaF
 template <int R>
 static void set_carveout_blur_r(int pct)
 {
-    set_carveout(blur_xy2_kernel<R>, pct);
+    set_carveout(blur_xy2_kernel<R, 8>, pct); set_carveout(blur_xy2_kernel<R, 16>, pct);
     set_carveout(blur_z2_kernel<R, true, float2>, pct);  set_carveout(blur_z2_kernel<R, false, float2>, pct);
     set_carveout(blur_z2_kernel<R, true, float4>, pct);  set_carveout(blur_z2_kernel<R, false, float4>, pct);
     set_carveout(blur_xy_kernel<R>, pct);
