@@ -383,6 +383,23 @@ class Batch:
             arr[k] = v.data_ptr() if hasattr(v, "data_ptr") else v.ctypes.data
         return arr
 
+    @staticmethod
+    def _checked(vols, dtype=None):
+        """Same shape everywhere, C-contiguous; numpy inputs are converted if needed (the returned list keeps
+        the converted arrays alive for the duration of the call)."""
+        out = []
+        shape = tuple(vols[0].shape)
+        for v in vols:
+            if tuple(v.shape) != shape or len(shape) != 3:
+                raise S3DError("batch volumes must all have the same (Z, Y, X) shape")
+            if hasattr(v, "data_ptr"):
+                if not v.is_contiguous() or (dtype is not None and str(v.dtype).replace("torch.", "") != dtype):
+                    raise S3DError("torch volumes must be contiguous%s" % (" " + dtype if dtype else ""))
+                out.append(v)
+            else:
+                out.append(np.ascontiguousarray(v, dtype=dtype) if dtype else np.ascontiguousarray(v))
+        return out
+
     def extract(self, h_volumes, params=None):
         """List of host volumes ((Z, Y, X) float32 numpy arrays or pinned torch tensors of one shape) ->
         list of feature-row arrays, in input order."""
@@ -390,6 +407,7 @@ class Batch:
         n = len(h_volumes)
         if n == 0:
             return []
+        h_volumes = self._checked(h_volumes, "float32")
         Z, Y, X = h_volumes[0].shape
         rows = (C.c_void_p * n)()
         cnt = (C.c_int * n)()
@@ -405,6 +423,9 @@ class Batch:
             return []
         v0 = h_volumes[0]
         name = str(v0.dtype).replace("torch.", "")
+        if name not in DTYPE_CODES:
+            raise S3DError("unsupported voxel datatype %s" % name)
+        h_volumes = self._checked(h_volumes, name)
         code = DTYPE_CODES[name]
         Z, Y, X = v0.shape
         rows = (C.c_void_p * n)()
