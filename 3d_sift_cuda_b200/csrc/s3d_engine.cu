@@ -238,6 +238,8 @@ struct s3d_ctx {
     int tail_a = 3, tail_b = 6, tail_d = 10;   // blocks per SM of orient_a / orient_b / describe (S3D_TAIL_BLOCKS=a,b,d)
     int xy2_ctas = 2;            // persistent x+y CTAs per SM (S3D_XY2_CTAS_PER_SM; contexts of an s3d_batch use 1)
     bool xy2_ctas_forced = false;
+    int detect_ctas = 0;         // resident detect_face blocks per SM (0 = whole grid; S3D_DETECT_CTAS; contexts of an s3d_batch: 4)
+    bool detect_ctas_forced = false;
     int desc_threads = 128;      // threads per describe block (S3D_DESC_THREADS: 64 or 128)
     int prof_skip = 0;           // S3D_PROF_SKIP (profiling only, results invalid): 1 = no keypoint tail, 2 = no detection/refinement, 3 = both
     bool serial = false;         // S3D_SERIAL=1: no branches, every kernel on the main stream (standalone kernel times)
@@ -366,6 +368,8 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
     }
     const char *xc = getenv("S3D_XY2_CTAS_PER_SM");
     if (xc && atoi(xc) >= 1 && atoi(xc) <= 4) { ctx->xy2_ctas = atoi(xc); ctx->xy2_ctas_forced = true; }
+    const char *dct = getenv("S3D_DETECT_CTAS");
+    if (dct && atoi(dct) >= 0) { ctx->detect_ctas = atoi(dct); ctx->detect_ctas_forced = true; }
     const char *dth = getenv("S3D_DESC_THREADS");
     if (dth && (atoi(dth) == 64 || atoi(dth) == 128)) ctx->desc_threads = atoi(dth);
     const char *psk = getenv("S3D_PROF_SKIP");
@@ -687,8 +691,15 @@ static s3d_status detect_two_pass(s3d_ctx *ctx, const float *finer, const float 
     if (X < 3 || Y < 3 || Z < 3) return S3D_OK;
     if ((long long)pitch * Y * Z >= (1ll << 32))      // 32-bit voxel offsets
         return detect_raw_launch(ctx, finer, centre, X, Y, Z, pitch, raw_min, n_min, raw_max, n_max, cap, own0, own1);
-    dim3 block(32, 8), grid((X - 2 + 31) / 32, (Y - 2 + 7) / 8, (Z - 2 + kDetectZ - 1) / kDetectZ);
-    detect_face_kernel<<<grid, block, 0, ctx->cur>>>(finer, centre, X, Y, Z, pitch, face, face_count, face_cap);
+    const int n_zblocks = (Z - 2 + kDetectZ - 1) / kDetectZ;
+    dim3 block(32, 8), grid((X - 2 + 31) / 32, (Y - 2 + 7) / 8, n_zblocks);
+    if (ctx->detect_ctas > 0) {        // batch contexts: cap the resident blocks (see detect_face_kernel)
+        long long per_layer = (long long)grid.x * grid.y;
+        long long gz = ((long long)ctx->detect_ctas * ctx->sm_count + per_layer - 1) / per_layer;
+        if (gz < 1) gz = 1;
+        if (gz < n_zblocks) grid.z = (unsigned)gz;
+    }
+    detect_face_kernel<<<grid, block, 0, ctx->cur>>>(finer, centre, X, Y, Z, pitch, n_zblocks, face, face_count, face_cap);
     CandList lmin{ raw_min, n_min }, lmax{ raw_max, n_max };
     int blocks = (int)(((long long)X * Y * Z / 64 + 255) / 256);
     if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
@@ -1408,6 +1419,7 @@ extern "C" s3d_status s3d_batch_create(int device, int n_contexts, s3d_batch **o
         // ... and the z march runs as one segment: the threads it lacks to cover the memory latency alone are
         // provided by the other volumes in flight, and no halo planes are read twice (S3D_MARCH_TARGET overrides)
         if (c->march_target == 0 && n_contexts > 1) c->march_target = 1;
+        if (!c->detect_ctas_forced && n_contexts > 1) c->detect_ctas = 4;
         b->ctx.push_back(c);
     }
     *out = b;

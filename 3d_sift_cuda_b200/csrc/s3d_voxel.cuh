@@ -367,65 +367,69 @@ constexpr int kDetectZ = 8;   // centre voxels per thread along z
 // speed; the few survivors (strict extrema along x, y and z) are appended to a list of linear voxel
 // offsets with one aggregated atomic per warp.
 __global__ void __launch_bounds__(256) detect_face_kernel(const float *__restrict__ finer, const float *__restrict__ centre,
-                                                          int X, int Y, int Z, int pitch,
+                                                          int X, int Y, int Z, int pitch, int n_zblocks,
                                                           unsigned int *__restrict__ face, int *face_count, int face_cap)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int y = blockIdx.y * blockDim.y + threadIdx.y + 1;
-    const int z0 = blockIdx.z * kDetectZ + 1;
     const bool inside = (x <= X - 2 && y <= Y - 2);
     const long long plane = (long long)pitch * Y;
     const unsigned int base = (unsigned int)((inside ? y : 1) * pitch + (inside ? x : 1));
-    // strict extremum over the 6 face neighbours  <=>  c > max(neighbours)  or  c < min(neighbours):
-    // two 3-input min/max trees per voxel instead of twelve compares (the pass is issue bound, not
-    // memory bound: ncu showed 58 instructions per voxel at 67 % issue utilisation before this form)
-    float up, c, dn;                 // z-1, z, z+1 of the running column
-    const float *p = centre + (long long)(z0 - 1) * plane + base;
-    up = __ldg(p);
-    p += plane;
-    c = __ldg(p);
-    unsigned livemask = 0;
-    if (z0 + kDetectZ <= Z - 1) {    // every plane z0-1 .. z0+kDetectZ exists: no clamps (uniform per block)
-#pragma unroll
-        for (int k = 0; k < kDetectZ; k++) {
-            const float xm = __ldg(p - 1), xp = __ldg(p + 1), ym = __ldg(p - pitch), yp = __ldg(p + pitch);
-            dn = __ldg(p + plane);
-            const float hi = fmaxf(fmaxf(fmaxf(xm, xp), fmaxf(ym, yp)), fmaxf(up, dn));
-            const float lo = fminf(fminf(fminf(xm, xp), fminf(ym, yp)), fminf(up, dn));
-            if (c > hi || c < lo) livemask |= 1u << k;
-            up = c; c = dn; p += plane;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < kDetectZ; k++) {
-            const bool zin = (z0 + k <= Z - 2);
-            const float *q = zin ? p : centre + base;       // keep the addresses legal past the last interior plane
-            const float xm = __ldg(q - 1), xp = __ldg(q + 1), ym = __ldg(q - pitch), yp = __ldg(q + pitch);
-            dn = __ldg(zin ? q + plane : q);
-            const float hi = fmaxf(fmaxf(fmaxf(xm, xp), fmaxf(ym, yp)), fmaxf(up, dn));
-            const float lo = fminf(fminf(fminf(xm, xp), fminf(ym, yp)), fminf(up, dn));
-            if (zin && (c > hi || c < lo)) livemask |= 1u << k;
-            up = c; c = dn; p += plane;
-        }
-    }
-    if (!inside) livemask = 0;
     const int lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
-    // one atomic per warp for all 8 z steps
-    int mine = __popc(livemask), incl = mine;
+    // gridDim.z may be smaller than the number of z blocks (contexts of a batch cap this kernel's footprint so that
+    // other volumes' kernels stay resident next to it): a block then walks several z blocks
+    for (int zb = blockIdx.z; zb < n_zblocks; zb += gridDim.z) {
+        const int z0 = zb * kDetectZ + 1;
+        // strict extremum over the 6 face neighbours  <=>  c > max(neighbours)  or  c < min(neighbours):
+        // two 3-input min/max trees per voxel instead of twelve compares (the pass is issue bound, not
+        // memory bound: ncu showed 58 instructions per voxel at 67 % issue utilisation before this form)
+        float up, c, dn;                 // z-1, z, z+1 of the running column
+        const float *p = centre + (long long)(z0 - 1) * plane + base;
+        up = __ldg(p);
+        p += plane;
+        c = __ldg(p);
+        unsigned livemask = 0;
+        if (z0 + kDetectZ <= Z - 1) {    // every plane z0-1 .. z0+kDetectZ exists: no clamps (uniform per block)
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-    int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0) return;
-    int start = 0;
-    if (lane == 31) start = atomicAdd(face_count, total);
-    start = __shfl_sync(0xffffffffu, start, 31);
-    int pos = start + incl - mine;
+            for (int k = 0; k < kDetectZ; k++) {
+                const float xm = __ldg(p - 1), xp = __ldg(p + 1), ym = __ldg(p - pitch), yp = __ldg(p + pitch);
+                dn = __ldg(p + plane);
+                const float hi = fmaxf(fmaxf(fmaxf(xm, xp), fmaxf(ym, yp)), fmaxf(up, dn));
+                const float lo = fminf(fminf(fminf(xm, xp), fminf(ym, yp)), fminf(up, dn));
+                if (c > hi || c < lo) livemask |= 1u << k;
+                up = c; c = dn; p += plane;
+            }
+        } else {
 #pragma unroll
-    for (int k = 0; k < kDetectZ; k++)
-        if (livemask & (1u << k)) {
-            if (pos < face_cap) face[pos] = (unsigned int)((long long)(z0 + k) * plane + base);
-            pos++;
+            for (int k = 0; k < kDetectZ; k++) {
+                const bool zin = (z0 + k <= Z - 2);
+                const float *q = zin ? p : centre + base;       // keep the addresses legal past the last interior plane
+                const float xm = __ldg(q - 1), xp = __ldg(q + 1), ym = __ldg(q - pitch), yp = __ldg(q + pitch);
+                dn = __ldg(zin ? q + plane : q);
+                const float hi = fmaxf(fmaxf(fmaxf(xm, xp), fmaxf(ym, yp)), fmaxf(up, dn));
+                const float lo = fminf(fminf(fminf(xm, xp), fminf(ym, yp)), fminf(up, dn));
+                if (zin && (c > hi || c < lo)) livemask |= 1u << k;
+                up = c; c = dn; p += plane;
+            }
         }
+        if (!inside) livemask = 0;
+        // one atomic per warp for all 8 z steps
+        int mine = __popc(livemask), incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        int start = 0;
+        if (lane == 31) start = atomicAdd(face_count, total);
+        start = __shfl_sync(0xffffffffu, start, 31);
+        int pos = start + incl - mine;
+#pragma unroll
+        for (int k = 0; k < kDetectZ; k++)
+            if (livemask & (1u << k)) {
+                if (pos < face_cap) face[pos] = (unsigned int)((long long)(z0 + k) * plane + base);
+                pos++;
+            }
+    }
 }
 
 // Pass 2: the full 26 + 27 neighbour test (reference MultiScale.cpp:2260-2524) on the survivors only.
