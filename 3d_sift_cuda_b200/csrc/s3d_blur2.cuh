@@ -287,6 +287,121 @@ __global__ void __launch_bounds__(128) blur_z2_kernel(const float *__restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// z pass, variant with a shared-memory ring (opt-in: S3D_Z3=1).  The register march above can only keep
+// P planes x 2 streams of loads in flight per thread, and its accumulators leave room for 12 warps per SM at
+// 17 taps, so it is bound by memory latency (ncu: long scoreboard 2.3-5.2 stalls per issue, 28-47 % issue
+// utilisation).  Here a block of 128 threads owns 512 contiguous floats of every plane; one thread streams the
+// planes of the input (and of the DoG minuend) into a ring of kZ3Depth slots with 1-D bulk copies
+// (cp.async.bulk + mbarrier), ten planes ahead of the march, without spending a register on prefetch.
+// Planes outside the volume are not copied (their slot is completed by a plain arrive and read as zero).
+// Same arithmetic as blur_z2_kernel (z2_step).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kZ3Depth = 10;
+
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int R, bool DOG>
+__global__ void __launch_bounds__(128) blur_z3_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                      const float *__restrict__ prev, float *__restrict__ dog,
+                                                      int n_vec, long long plane, int len, int seg_len,
+                                                      const __grid_constant__ TapsSmall taps)
+{
+    constexpr int T = 2 * R + 1, D = kZ3Depth;
+    __shared__ __align__(128) float ring_in[D][512];
+    __shared__ __align__(128) float ring_pv[DOG ? D : 1][512];
+    __shared__ uint64_t full[D];
+    const int t = threadIdx.x;
+    const int q0 = blockIdx.x * 128;                      // first float4 column of this block
+    const int nq = min(128, n_vec - q0);
+    const unsigned bytes = (unsigned)nq * 16u;
+    const bool active = t < nq;
+    const int a0 = blockIdx.y * seg_len;
+    const int a1 = min(len, a0 + seg_len);
+    const int n_in = (a1 - a0) + 2 * R;                   // steps u = 0 .. n_in-1 <-> input plane a0 - R + u
+    const int i_base = a0 - R;
+    const float *gin = in + 4ll * q0;
+    const float *gpv = prev + 4ll * q0;
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < D; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int u) {         // thread 0: fill the slot of step u
+        const int s = u % D;
+        const int i = i_base + u;
+        const bool iv = (i >= 0 && i < len);
+        const bool pvv = DOG && (u >= 2 * R);
+        const unsigned tx = (iv ? bytes : 0u) + (pvv ? bytes : 0u);
+        if (tx == 0) { mbar_arrive(&full[s]); return; }
+        mbar_expect_tx(&full[s], tx);
+        if (iv) bulk_copy_g2s(&ring_in[s][0], gin + (long long)i * plane, bytes, &full[s]);
+        if (pvv) bulk_copy_g2s(&ring_pv[DOG ? s : 0][0], gpv + (long long)(a0 + u - 2 * R) * plane, bytes, &full[s]);
+    };
+    if (t == 0)
+        for (int u = 0; u < D && u < n_in; u++) issue(u);
+
+    float4 acc[T];
+#pragma unroll
+    for (int s = 0; s < T; s++) acc[s] = zerov<float4>();
+    float *pout = out + 4ll * (q0 + t) + (long long)(a0 - 2 * R) * plane;
+    float *pdog = dog + 4ll * (q0 + t) + (long long)(a0 - 2 * R) * plane;
+    int slot = 0, phase = 0;
+    for (int ub = 0; ub < n_in; ub += T) {
+#pragma unroll
+        for (int S = 0; S < T; S++) {
+            const int u = ub + S;
+            if (u >= n_in) break;                          // uniform over the block
+            mbar_wait(&full[slot], phase);
+            const int i = i_base + u;
+            float4 v = zerov<float4>(), pvv = zerov<float4>();
+            if (active && i >= 0 && i < len) v = *reinterpret_cast<const float4 *>(&ring_in[slot][4 * t]);
+            if (DOG && active && u >= 2 * R) pvv = *reinterpret_cast<const float4 *>(&ring_pv[DOG ? slot : 0][4 * t]);
+            __syncthreads();                               // every thread has read the slot: refill it
+            if (t == 0 && u + D < n_in) issue(u + D);
+            z2_step<R, false, float4>(acc, S, v, taps);
+            if (active && u >= 2 * R) {
+                const float4 g = acc[(S + 1) % T];
+                *reinterpret_cast<float4 *>(pout) = g;
+                if (DOG) *reinterpret_cast<float4 *>(pdog) = subv(pvv, g);     // prev + (-1)*g, fioMultSum
+            }
+            pout += plane;
+            if (DOG) pdog += plane;
+            if (++slot == D) { slot = 0; phase ^= 1; }
+        }
+    }
+}
+
+template <int R>
+static cudaError_t launch_blur_z3(cudaStream_t st, const float *tmp, float *out, const float *prev, float *dog,
+                                  int Y, int Z, int pitch, const float *taps, int target)
+{
+    TapsSmall t;
+    memset(&t, 0, sizeof(t));
+    for (int j = 0; j < 2 * R + 1; j++) t.w[j] = taps[j];
+    long long plane = (long long)pitch * Y;
+    int n_vec = (int)(plane / 4);
+    int n_seg = (int)((target + n_vec - 1) / n_vec);
+    int max_seg = (Z + 31) / 32;
+    if (n_seg > max_seg) n_seg = max_seg;
+    if (n_seg < 1) n_seg = 1;
+    int seg_len = (Z + n_seg - 1) / n_seg;
+    n_seg = (Z + seg_len - 1) / seg_len;
+    dim3 grid((unsigned)((n_vec + 127) / 128), (unsigned)n_seg);
+    if (dog) blur_z3_kernel<R, true><<<grid, 128, 0, st>>>(tmp, out, prev, dog, n_vec, plane, Z, seg_len, t);
+    else blur_z3_kernel<R, false><<<grid, 128, 0, st>>>(tmp, out, tmp, out, n_vec, plane, Z, seg_len, t);
+    return cudaGetLastError();
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 static inline bool taps_symmetric(const float *taps, int n)
 {

@@ -234,6 +234,7 @@ struct s3d_ctx {
     long long f3_min_voxels = 0; // ... and volumes of at least this many voxels (S3D_F3_MIN_VOXELS)
     int f3_ctas = 0;             // S3D_F3_CTAS: CTAs the one-kernel level aims for (0 = one per SM)
     unsigned long long *d_stamps = nullptr;   // S3D_STAMPS=1
+    bool z3 = false;             // S3D_Z3=1: z pass with the shared-memory ring (blur_z3_kernel) instead of the register march
     int z2_vec = 0;              // S3D_Z2_VEC=2|4: columns per thread of the z march (0 = by radius)
     int tail_a = 3, tail_b = 6, tail_d = 10;   // blocks per SM of orient_a / orient_b / describe (S3D_TAIL_BLOCKS=a,b,d)
     int xy2_ctas = 2;            // persistent x+y CTAs per SM (S3D_XY2_CTAS_PER_SM; contexts of an s3d_batch use 1)
@@ -355,6 +356,8 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
     if (f3v) ctx->f3_min_voxels = atoll(f3v);
     const char *stp = getenv("S3D_STAMPS");
     if (stp && stp[0] == '1') CK(cudaMalloc((void **)&ctx->d_stamps, 4 * sizeof(unsigned long long)));
+    const char *z3e = getenv("S3D_Z3");
+    if (z3e) ctx->z3 = (z3e[0] == '1');
     const char *zv = getenv("S3D_Z2_VEC");
     if (zv) ctx->z2_vec = (atoi(zv) == 2 || atoi(zv) == 4) ? atoi(zv) : 0;
     const char *tb = getenv("S3D_TAIL_BLOCKS");
@@ -505,7 +508,8 @@ static void launch_blur_fast(s3d_ctx *ctx, const float *in, float *tmp, float *o
         cudaError_t e = cudaSuccess;
         if (launch_blur_xy2<R>(ctx->cur, in, tmp, X, Y, Z, pitch, taps, ctx->sm_count, ctx->xy2_ctas, &e)) {
             int target2 = ctx->march_target > 0 ? ctx->march_target : ctx->sm_count * 256;
-            launch_blur_z2<R>(ctx->cur, tmp, out, in, dog, Y, Z, pitch, taps, target2, ctx->z2_vec);
+            if (ctx->z3) launch_blur_z3<R>(ctx->cur, tmp, out, in, dog, Y, Z, pitch, taps, target2);
+            else launch_blur_z2<R>(ctx->cur, tmp, out, in, dog, Y, Z, pitch, taps, target2, ctx->z2_vec);
             ctx->launches += 2;
             return;
         }

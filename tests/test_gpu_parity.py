@@ -238,7 +238,9 @@ def test_small_octaves_cluster_kernel_bit_exact(pkg, oracle, monkeypatch):
 
 @pytest.mark.parametrize("env", [{"S3D_F3_MAXR": "8"}, {"S3D_F3_MAXR": "0", "S3D_BLUR2": "0"},
                                  {"S3D_F3_MAXR": "0", "S3D_Z2_VEC": "2", "S3D_XY2_TX": "32", "S3D_XY2_TY": "48"},
-                                 {"S3D_F3_MAXR": "0", "S3D_Z2_VEC": "4", "S3D_MARCH_TARGET": "200000"}])
+                                 {"S3D_F3_MAXR": "0", "S3D_Z2_VEC": "4", "S3D_MARCH_TARGET": "200000"},
+                                 {"S3D_F3_MAXR": "0", "S3D_Z3": "1", "S3D_MARCH_TARGET": "100000"},
+                                 {"S3D_F3_MAXR": "0", "S3D_XY2_KY": "8"}])
 def test_every_blur_path_bit_exact(pkg, oracle, monkeypatch, env):
     """Each selectable blur path -- the one-kernel level (s3d_blur3.cuh), the first-generation kernels, the
     second-generation x+y / z kernels with 2 and 4 columns per thread and several z segments -- must give
