@@ -115,7 +115,7 @@ blur_xy2_kernel(const __grid_constant__ CUtensorMap in_map, float *__restrict__ 
         {
             const int n_xseg = tile.TX / kKX;
             const int n_items = (tile.rows8 >> 3) * n_xseg;
-            for (int it = t >> 3; it < n_items; it += kXY2Threads / 8) {
+            for (int it = t >> 3; it < n_items; it += (int)blockDim.x / 8) {
                 const int rg = it / n_xseg, xs = it - rg * n_xseg;
                 const int row = rg * 8 + (t & 7);
                 const float *src = in_t + row * tile.W_in + xs * kKX;
@@ -152,7 +152,7 @@ blur_xy2_kernel(const __grid_constant__ CUtensorMap in_map, float *__restrict__ 
         {
             const int n_pairs = tile.TX >> 1;
             const int n_items = n_pairs * (tile.TY / KY);
-            for (int it = t; it < n_items; it += kXY2Threads) {
+            for (int it = t; it < n_items; it += (int)blockDim.x) {
                 const int ys = it / n_pairs, cp = it - ys * n_pairs;
                 const float *col = XB + (ys * KY) * tile.W_xb + 2 * cp;
                 float2 win[KY + 2 * R];
@@ -529,8 +529,10 @@ static bool launch_blur_xy2(cudaStream_t st, const float *in, float *tmp, int X,
     // every SM is better spent on the memory-bound kernels of the other volumes in flight
     const long long slots = (long long)(ctas_per_sm < 1 ? 1 : ctas_per_sm) * sm_count;
     const int grid = (int)(n_tiles < slots ? n_tiles : slots);
-    if (tile.KY == 8) blur_xy2_kernel<R, 8><<<grid, kXY2Threads, tile.smem, st>>>(map, tmp, X, Y, pitch, tile, n_tx, n_ty, (int)n_tiles, t);
-    else blur_xy2_kernel<R, 16><<<grid, kXY2Threads, tile.smem, st>>>(map, tmp, X, Y, pitch, tile, n_tx, n_ty, (int)n_tiles, t);
+    static int threads = 0;            // S3D_XY2_THREADS=128|256 (experiments; the kernel's loops follow blockDim.x)
+    if (threads == 0) { const char *e = getenv("S3D_XY2_THREADS"); threads = (e && atoi(e) == 128) ? 128 : kXY2Threads; }
+    if (tile.KY == 8) blur_xy2_kernel<R, 8><<<grid, threads, tile.smem, st>>>(map, tmp, X, Y, pitch, tile, n_tx, n_ty, (int)n_tiles, t);
+    else blur_xy2_kernel<R, 16><<<grid, threads, tile.smem, st>>>(map, tmp, X, Y, pitch, tile, n_tx, n_ty, (int)n_tiles, t);
     *err = cudaGetLastError();
     return true;
 }
