@@ -16,18 +16,45 @@
 // Shared-memory rows are padded so that 8 lanes reading 16 bytes from 8 consecutive rows hit 8 different
 // bank groups (row pitch / 4 odd).
 #pragma once
-#include "s3d_blur_fused.cuh"
+#include "s3d_voxel.cuh"
+#include "s3d_tma.cuh"
 
 namespace s3d {
 
-__device__ __forceinline__ float mulw(float w, float v) { return w * v; }
-__device__ __forceinline__ float2 mulw(float w, float2 v) { return make_float2(w * v.x, w * v.y); }
-__device__ __forceinline__ float4 mulw(float w, float4 v) { return make_float4(w * v.x, w * v.y, w * v.z, w * v.w); }
+// Packed fp32x2 primitives (sm_100a FFMA2 / FADD2): two separately rounded products / sums per issue slot.
+__device__ __forceinline__ float2 pk_mul(float2 v, float w, float z0) { return __ffma2_rn(v, make_float2(w, w), make_float2(z0, z0)); }
+__device__ __forceinline__ float2 pk_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 pk_sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+
+__device__ __forceinline__ float mulw(const TapsSmall &tp, int k, float v) { return tp.w[k] * v; }
+__device__ __forceinline__ float2 mulw(const TapsSmall &tp, int k, float2 v) { return pk_mul(v, tp.w[k], tp.z0); }
+__device__ __forceinline__ float4 mulw(const TapsSmall &tp, int k, float4 v)
+{
+    const float2 a = pk_mul(make_float2(v.x, v.y), tp.w[k], tp.z0), b = pk_mul(make_float2(v.z, v.w), tp.w[k], tp.z0);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
 __device__ __forceinline__ float addv(float a, float b) { return a + b; }
-__device__ __forceinline__ float2 addv(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float4 addv(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-__device__ __forceinline__ float2 subv(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float4 subv(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float2 addv(float2 a, float2 b) { return pk_add(a, b); }
+__device__ __forceinline__ float4 addv(float4 a, float4 b)
+{
+    const float2 lo = pk_add(make_float2(a.x, a.y), make_float2(b.x, b.y)), hi = pk_add(make_float2(a.z, a.w), make_float2(b.z, b.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float2 subv(float2 a, float2 b) { return pk_sub(a, b); }
+__device__ __forceinline__ float4 subv(float4 a, float4 b)
+{
+    const float2 lo = pk_sub(make_float2(a.x, a.y), make_float2(b.x, b.y)), hi = pk_sub(make_float2(a.z, a.w), make_float2(b.z, b.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+// unpacked variants (one FMUL / FADD per lane) for the z march of wide radii: there the packed forms need aligned
+// register pairs for 2R+1 partial sums, 46 more registers per thread at 17 taps, and the march is bound by the
+// number of warps that cover its memory latency, not by issue slots
+__device__ __forceinline__ float2 mulw_s(const TapsSmall &tp, int k, float2 v) { return make_float2(tp.w[k] * v.x, tp.w[k] * v.y); }
+__device__ __forceinline__ float4 mulw_s(const TapsSmall &tp, int k, float4 v) { return make_float4(tp.w[k] * v.x, tp.w[k] * v.y, tp.w[k] * v.z, tp.w[k] * v.w); }
+__device__ __forceinline__ float2 addv_s(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float4 addv_s(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float2 subv_s(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float4 subv_s(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 template <typename VT> __device__ __forceinline__ VT zerov();
 template <> __device__ __forceinline__ float zerov<float>() { return 0.0f; }
 template <> __device__ __forceinline__ float2 zerov<float2>() { return make_float2(0.f, 0.f); }
@@ -36,23 +63,44 @@ template <typename VT> __device__ __forceinline__ VT ldgv(const float *p) { retu
 
 // K outputs from a window of K+2R inputs (win[c + j] is tap j of output c).  Inputs are visited in
 // increasing order, so every output accumulates its taps j = 0..2R in order.
-// ZERO_START: the sum starts as 0.0f + (first product), like the reference's `fSum = 0; fSum += ...`
-// (GaussBlur3D.cpp:54-58).  It only matters for -0.0: a window of -0.0 voxels (masked images: negative value
-// x 0) sums to +0.0 in the reference.  The x pass -- the only pass that can see -0.0 inputs, a float sum is
-// never -0.0 afterwards -- pays one extra FADD per output for it; the y and z passes start from the product.
-template <int R, int K, typename F, bool ZERO_START = false>
+// Every sum starts as 0.0f + (first product), like the reference's `fSum = 0; fSum += ...` (GaussBlur3D.cpp:54-58).
+// It only matters for zeros: a window whose products are all -0.0 (masked images: negative value x 0; products of
+// denormals that underflow) sums to +0.0 in the reference.  One extra FADD2 per output pair and pass.
+template <int R, int K, typename F>
 __device__ __forceinline__ void conv_segment(const F *win, F *acc, const TapsSmall &taps)
 {
 #pragma unroll
     for (int m = 0; m < K + 2 * R; m++) {
         F p[R + 1];
 #pragma unroll
-        for (int k = 0; k <= R; k++) p[k] = mulw(taps.w[k], win[m]);     // unused products are dead code
+        for (int k = 0; k <= R; k++) p[k] = mulw(taps, k, win[m]);     // unused products are dead code
 #pragma unroll
         for (int c = 0; c < K; c++) {
             const int j = m - c;
-            if (j == 0) acc[c] = ZERO_START ? addv(zerov<F>(), p[0]) : p[0];
+            if (j == 0) acc[c] = addv(zerov<F>(), p[0]);
             else if (j > 0 && j <= 2 * R) acc[c] = addv(acc[c], p[j <= R ? j : 2 * R - j]);
+        }
+    }
+}
+
+// x axis, packed: K outputs (K even) as K/2 pairs from a scalar register window; tap j of output c is
+// win[OFF + c + j].  Output pairs start at even c, so a pair position q = c + j serves taps of one parity only:
+// about (R+1)/2 products per position, (K+R)(R+1)/2 FFMA2 + K*R FADD2 per segment.  Positions are visited in
+// increasing order: every output still accumulates its taps j = 0..2R left to right, starting from 0.0f.
+template <int R, int K, int OFF>
+__device__ __forceinline__ void seg_x_pk(const float *win, float2 *acc, const TapsSmall &tp)
+{
+#pragma unroll
+    for (int q = 0; q <= K - 2 + 2 * R; q++) {
+        const float2 v = make_float2(win[OFF + q], win[OFF + q + 1]);
+        float2 p[R + 1];
+#pragma unroll
+        for (int k = 0; k <= R; k++) p[k] = pk_mul(v, tp.w[k], tp.z0);     // unused products are dead code
+#pragma unroll
+        for (int c2 = 0; c2 < K / 2; c2++) {
+            const int j = q - 2 * c2;
+            if (j == 0) acc[c2] = pk_add(make_float2(0.0f, 0.0f), p[0]);
+            else if (j > 0 && j <= 2 * R) acc[c2] = pk_add(acc[c2], p[j <= R ? j : 2 * R - j]);
         }
     }
 }
@@ -125,17 +173,20 @@ blur_xy2_kernel(const __grid_constant__ CUtensorMap in_map, float *__restrict__ 
                     float4 u = *reinterpret_cast<const float4 *>(src + 4 * q);
                     win[4 * q] = u.x; win[4 * q + 1] = u.y; win[4 * q + 2] = u.z; win[4 * q + 3] = u.w;
                 }
-                float acc[kKX];
-                conv_segment<R, kKX, float, true>(win + (RP - R), acc, taps);
+                float2 acc[kKX / 2];
+                seg_x_pk<R, kKX, RP - R>(win, acc, taps);
                 const int xg = x0 + xs * kKX;
                 if (xg + kKX > X) {       // padding columns (x >= X) stay zero in every pass
 #pragma unroll
-                    for (int q = 0; q < kKX; q++) if (xg + q >= X) acc[q] = 0.0f;
+                    for (int q = 0; q < kKX / 2; q++) {
+                        if (xg + 2 * q >= X) acc[q].x = 0.0f;
+                        if (xg + 2 * q + 1 >= X) acc[q].y = 0.0f;
+                    }
                 }
                 float *dst = XB + row * tile.W_xb + xs * kKX;
 #pragma unroll
                 for (int q = 0; q < kKX / 4; q++)
-                    *reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+                    *reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
             }
         }
         __syncthreads();      // XB complete, stage s free: refill it with the tile after next
@@ -182,19 +233,19 @@ blur_xy2_kernel(const __grid_constant__ CUtensorMap in_map, float *__restrict__ 
 // ---------------------------------------------------------------------------------------------------
 // S (slot of the output started by this step) is a literal after the caller's loop is unrolled, so
 // every accumulator index below is static and acc[] stays in registers.
-template <int R, bool FIRST, typename VT>
+template <int R, bool FIRST, typename VT, bool PK = true>
 __device__ __forceinline__ void z2_step(VT (&acc)[2 * R + 1], const int S, const VT v, const TapsSmall &taps)
 {
     constexpr int T = 2 * R + 1;
     VT p[R + 1];
 #pragma unroll
-    for (int k = 0; k <= R; k++) p[k] = mulw(taps.w[k], v);
-    acc[S] = p[0];
+    for (int k = 0; k <= R; k++) p[k] = PK ? mulw(taps, k, v) : mulw_s(taps, k, v);
+    acc[S] = PK ? addv(zerov<VT>(), p[0]) : addv_s(zerov<VT>(), p[0]);
 #pragma unroll
     for (int j = 1; j <= 2 * R; j++)
         if (!FIRST || j <= S) {      // warm-up round: output S - j of the segment does not exist for j > S
             const int sl = (S - j + 2 * T) % T;
-            acc[sl] = addv(acc[sl], p[j <= R ? j : 2 * R - j]);
+            acc[sl] = PK ? addv(acc[sl], p[j <= R ? j : 2 * R - j]) : addv_s(acc[sl], p[j <= R ? j : 2 * R - j]);
         }
 }
 
@@ -233,12 +284,12 @@ __device__ __forceinline__ void z2_round(VT (&acc)[2 * R + 1], VT (&vin)[2 * R +
             pin += plane;
             if (DOG) ppv += plane;
         }
-        z2_step<R, FIRST, VT>(acc, S, v, taps);
+        z2_step<R, FIRST, VT, false>(acc, S, v, taps);
         if (!FIRST || S == 2 * R) {             // step u completes output u - 2R
             if (FAST || u >= 2 * R) {
                 const VT g = acc[(S + 1) % T];
                 *reinterpret_cast<VT *>(pout) = g;
-                if (DOG) *reinterpret_cast<VT *>(pdog) = subv(pvv, g);   // prev + (-1)*g, fioMultSum
+                if (DOG) *reinterpret_cast<VT *>(pdog) = subv_s(pvv, g);   // prev + (-1)*g, fioMultSum
             }
         }
         pout += plane;
@@ -287,121 +338,6 @@ __global__ void __launch_bounds__(128) blur_z2_kernel(const float *__restrict__ 
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// z pass, variant with a shared-memory ring (opt-in: S3D_Z3=1).  The register march above can only keep
-// P planes x 2 streams of loads in flight per thread, and its accumulators leave room for 12 warps per SM at
-// 17 taps, so it is bound by memory latency (ncu: long scoreboard 2.3-5.2 stalls per issue, 28-47 % issue
-// utilisation).  Here a block of 128 threads owns 512 contiguous floats of every plane; one thread streams the
-// planes of the input (and of the DoG minuend) into a ring of kZ3Depth slots with 1-D bulk copies
-// (cp.async.bulk + mbarrier), ten planes ahead of the march, without spending a register on prefetch.
-// Planes outside the volume are not copied (their slot is completed by a plain arrive and read as zero).
-// Same arithmetic as blur_z2_kernel (z2_step).
-// ---------------------------------------------------------------------------------------------------
-constexpr int kZ3Depth = 10;
-
-__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-template <int R, bool DOG>
-__global__ void __launch_bounds__(128) blur_z3_kernel(const float *__restrict__ in, float *__restrict__ out,
-                                                      const float *__restrict__ prev, float *__restrict__ dog,
-                                                      int n_vec, long long plane, int len, int seg_len,
-                                                      const __grid_constant__ TapsSmall taps)
-{
-    constexpr int T = 2 * R + 1, D = kZ3Depth;
-    __shared__ __align__(128) float ring_in[D][512];
-    __shared__ __align__(128) float ring_pv[DOG ? D : 1][512];
-    __shared__ uint64_t full[D];
-    const int t = threadIdx.x;
-    const int q0 = blockIdx.x * 128;                      // first float4 column of this block
-    const int nq = min(128, n_vec - q0);
-    const unsigned bytes = (unsigned)nq * 16u;
-    const bool active = t < nq;
-    const int a0 = blockIdx.y * seg_len;
-    const int a1 = min(len, a0 + seg_len);
-    const int n_in = (a1 - a0) + 2 * R;                   // steps u = 0 .. n_in-1 <-> input plane a0 - R + u
-    const int i_base = a0 - R;
-    const float *gin = in + 4ll * q0;
-    const float *gpv = prev + 4ll * q0;
-    if (t == 0) {
-#pragma unroll
-        for (int s = 0; s < D; s++) mbar_init(&full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    auto issue = [&](int u) {         // thread 0: fill the slot of step u
-        const int s = u % D;
-        const int i = i_base + u;
-        const bool iv = (i >= 0 && i < len);
-        const bool pvv = DOG && (u >= 2 * R);
-        const unsigned tx = (iv ? bytes : 0u) + (pvv ? bytes : 0u);
-        if (tx == 0) { mbar_arrive(&full[s]); return; }
-        mbar_expect_tx(&full[s], tx);
-        if (iv) bulk_copy_g2s(&ring_in[s][0], gin + (long long)i * plane, bytes, &full[s]);
-        if (pvv) bulk_copy_g2s(&ring_pv[DOG ? s : 0][0], gpv + (long long)(a0 + u - 2 * R) * plane, bytes, &full[s]);
-    };
-    if (t == 0)
-        for (int u = 0; u < D && u < n_in; u++) issue(u);
-
-    float4 acc[T];
-#pragma unroll
-    for (int s = 0; s < T; s++) acc[s] = zerov<float4>();
-    float *pout = out + 4ll * (q0 + t) + (long long)(a0 - 2 * R) * plane;
-    float *pdog = dog + 4ll * (q0 + t) + (long long)(a0 - 2 * R) * plane;
-    int slot = 0, phase = 0;
-    for (int ub = 0; ub < n_in; ub += T) {
-#pragma unroll
-        for (int S = 0; S < T; S++) {
-            const int u = ub + S;
-            if (u >= n_in) break;                          // uniform over the block
-            mbar_wait(&full[slot], phase);
-            const int i = i_base + u;
-            float4 v = zerov<float4>(), pvv = zerov<float4>();
-            if (active && i >= 0 && i < len) v = *reinterpret_cast<const float4 *>(&ring_in[slot][4 * t]);
-            if (DOG && active && u >= 2 * R) pvv = *reinterpret_cast<const float4 *>(&ring_pv[DOG ? slot : 0][4 * t]);
-            __syncthreads();                               // every thread has read the slot: refill it
-            if (t == 0 && u + D < n_in) issue(u + D);
-            z2_step<R, false, float4>(acc, S, v, taps);
-            if (active && u >= 2 * R) {
-                const float4 g = acc[(S + 1) % T];
-                *reinterpret_cast<float4 *>(pout) = g;
-                if (DOG) *reinterpret_cast<float4 *>(pdog) = subv(pvv, g);     // prev + (-1)*g, fioMultSum
-            }
-            pout += plane;
-            if (DOG) pdog += plane;
-            if (++slot == D) { slot = 0; phase ^= 1; }
-        }
-    }
-}
-
-template <int R>
-static cudaError_t launch_blur_z3(cudaStream_t st, const float *tmp, float *out, const float *prev, float *dog,
-                                  int Y, int Z, int pitch, const float *taps, int target)
-{
-    TapsSmall t;
-    memset(&t, 0, sizeof(t));
-    for (int j = 0; j < 2 * R + 1; j++) t.w[j] = taps[j];
-    long long plane = (long long)pitch * Y;
-    int n_vec = (int)(plane / 4);
-    int n_seg = (int)((target + n_vec - 1) / n_vec);
-    int max_seg = (Z + 31) / 32;
-    if (n_seg > max_seg) n_seg = max_seg;
-    if (n_seg < 1) n_seg = 1;
-    int seg_len = (Z + n_seg - 1) / n_seg;
-    n_seg = (Z + seg_len - 1) / seg_len;
-    dim3 grid((unsigned)((n_vec + 127) / 128), (unsigned)n_seg);
-    if (dog) blur_z3_kernel<R, true><<<grid, 128, 0, st>>>(tmp, out, prev, dog, n_vec, plane, Z, seg_len, t);
-    else blur_z3_kernel<R, false><<<grid, 128, 0, st>>>(tmp, out, tmp, out, n_vec, plane, Z, seg_len, t);
-    return cudaGetLastError();
-}
-
 // ---- host side -----------------------------------------------------------------------------------
 static inline bool taps_symmetric(const float *taps, int n)
 {
@@ -427,26 +363,23 @@ static inline XY2Tile make_xy2_tile(int TX, int TY, int R, int KY = 16)
     return t;
 }
 
+// experiment knobs of the x+y kernel (filled from the environment by the engine, see Tuning in s3d_engine.cu)
+struct XY2Tune {
+    int max_kb = 75;                 // shared memory per CTA the tile may use
+    int force_tx = 0, force_ty = 0;  // forced tile (both or none)
+    int ky = 16;                     // y-segment length (8 or 16)
+    int threads = kXY2Threads;       // threads per CTA (128 or 256)
+};
+
 // Tile choice: minimise (rounds of CTAs per SM) x (work per CTA); work = x-pass rows + y-pass rows, both
 // TX wide.  Tiles are limited to 2 resident CTAs per SM (<= ~110 KB of shared memory each).
-static inline XY2Tile choose_xy2_tile(int pitch, int Y, int Z, int R, int sm_count)
+static inline XY2Tile choose_xy2_tile(int pitch, int Y, int Z, int R, int sm_count, const XY2Tune &tn)
 {
-    static int max_kb = -1, force_tx = 0, force_ty = 0;   // S3D_XY2_SMEM_KB / S3D_XY2_TX / S3D_XY2_TY (experiments)
-    if (max_kb < 0) {
-        const char *e = getenv("S3D_XY2_SMEM_KB");
-        max_kb = e ? atoi(e) : 75;
-        if (max_kb < 16 || max_kb > 112) max_kb = 75;
-        const char *fx = getenv("S3D_XY2_TX"), *fy = getenv("S3D_XY2_TY");
-        if (fx && fy) { force_tx = atoi(fx); force_ty = atoi(fy); }
-    }
-    static int force_ky = 0;
-    if (force_ky == 0) { const char *e = getenv("S3D_XY2_KY"); force_ky = (e && (atoi(e) == 8 || atoi(e) == 16)) ? atoi(e) : -1; }
+    const int max_kb = tn.max_kb, force_tx = tn.force_tx, force_ty = tn.force_ty, force_ky = tn.ky;
     if (force_tx >= 32 && force_tx % 32 == 0 && force_ty >= 8 && force_ty % 8 == 0) {
-        int ky = force_ky > 0 ? force_ky : (force_ty % 16 == 0 ? 16 : 8);
-        if (force_ty % ky == 0) {
-            XY2Tile t = make_xy2_tile(force_tx, force_ty, R, ky);
-            if (t.smem <= 113 * 1024 && t.W_in <= 256 && t.rows <= 256) return t;
-        }
+        int ky = (force_ty % force_ky == 0) ? force_ky : 8;
+        XY2Tile t = make_xy2_tile(force_tx, force_ty, R, ky);
+        if (t.smem <= 113 * 1024 && t.W_in <= 256 && t.rows <= 256) return t;
     }
     // Cost model in FP32 instructions per thread: the x pass runs ceil(items / 32) rounds of 16-output items on
     // 8-lane groups, the y pass ceil(items / 256) rounds of 2 x KY-output items; a round costs one item whether
@@ -460,7 +393,7 @@ static inline XY2Tile choose_xy2_tile(int pitch, int Y, int Z, int R, int sm_cou
         // measured (profiles/README.md): 8-output y segments fill more threads but are never faster than 16-output
         // ones at MNI size (19.9 / 24.2 / 31.1 us against 18.5 / 23.2 / 30.1 us at 7 / 11 / 17 taps), so KY = 8 is
         // only used on request (S3D_XY2_KY=8)
-        if (KY != (force_ky > 0 ? force_ky : 16)) continue;
+        if (KY != force_ky) continue;
         const double cy = 2.0 * ((double)(KY + R) * (R + 1) + 2.0 * R * KY) + 2.0 * KY + 2.0 * R + 16.0;
         for (int TX = 32; TX <= 128; TX += 32)
             for (int TY = KY; TY <= 128; TY += KY) {
@@ -475,19 +408,6 @@ static inline XY2Tile choose_xy2_tile(int pitch, int Y, int Z, int R, int sm_cou
             }
     }
     return best;
-}
-
-static bool make_volume_map_box(CUtensorMap *map, const float *vol, int Y, int Z, int pitch, int box_w, int box_h)
-{
-    PFN_encodeTiled enc = get_encode_tiled();
-    if (!enc) return false;
-    cuuint64_t gdim[3] = { (cuuint64_t)pitch, (cuuint64_t)Y, (cuuint64_t)Z };
-    cuuint64_t gstr[2] = { (cuuint64_t)pitch * 4, (cuuint64_t)pitch * Y * 4 };
-    cuuint32_t box[3] = { (cuuint32_t)box_w, (cuuint32_t)box_h, 1 };
-    cuuint32_t estr[3] = { 1, 1, 1 };
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)vol, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS;
 }
 
 template <int R>
@@ -514,14 +434,12 @@ static cudaError_t init_blur2_attrs()
 // x+y: in -> tmp.  Returns false (nothing launched) when the tensor map cannot be encoded.
 template <int R>
 static bool launch_blur_xy2(cudaStream_t st, const float *in, float *tmp, int X, int Y, int Z, int pitch, const float *taps,
-                            int sm_count, int ctas_per_sm, cudaError_t *err)
+                            int sm_count, int ctas_per_sm, const XY2Tune &tn, cudaError_t *err)
 {
-    XY2Tile tile = choose_xy2_tile(pitch, Y, Z, R, sm_count);
+    XY2Tile tile = choose_xy2_tile(pitch, Y, Z, R, sm_count, tn);
     CUtensorMap map;
     if (!make_volume_map_box(&map, in, Y, Z, pitch, tile.W_in, tile.rows)) return false;
-    TapsSmall t;
-    memset(&t, 0, sizeof(t));
-    for (int j = 0; j < 2 * R + 1; j++) t.w[j] = taps[j];
+    TapsSmall t = make_taps_small(taps, 2 * R + 1);
     const int n_tx = (pitch + tile.TX - 1) / tile.TX, n_ty = (Y + tile.TY - 1) / tile.TY;
     const long long n_tiles = (long long)n_tx * n_ty * Z;
     if (n_tiles > 0x7fffffffll) return false;
@@ -529,8 +447,7 @@ static bool launch_blur_xy2(cudaStream_t st, const float *in, float *tmp, int X,
     // every SM is better spent on the memory-bound kernels of the other volumes in flight
     const long long slots = (long long)(ctas_per_sm < 1 ? 1 : ctas_per_sm) * sm_count;
     const int grid = (int)(n_tiles < slots ? n_tiles : slots);
-    static int threads = 0;            // S3D_XY2_THREADS=128|256 (experiments; the kernel's loops follow blockDim.x)
-    if (threads == 0) { const char *e = getenv("S3D_XY2_THREADS"); threads = (e && atoi(e) == 128) ? 128 : kXY2Threads; }
+    const int threads = tn.threads;
     if (tile.KY == 8) blur_xy2_kernel<R, 8><<<grid, threads, tile.smem, st>>>(map, tmp, X, Y, pitch, tile, n_tx, n_ty, (int)n_tiles, t);
     else blur_xy2_kernel<R, 16><<<grid, threads, tile.smem, st>>>(map, tmp, X, Y, pitch, tile, n_tx, n_ty, (int)n_tiles, t);
     *err = cudaGetLastError();
@@ -546,9 +463,7 @@ template <int R>
 static cudaError_t launch_blur_z2(cudaStream_t st, const float *tmp, float *out, const float *prev, float *dog,
                                   int Y, int Z, int pitch, const float *taps, int target, int force_v)
 {
-    TapsSmall t;
-    memset(&t, 0, sizeof(t));
-    for (int j = 0; j < 2 * R + 1; j++) t.w[j] = taps[j];
+    TapsSmall t = make_taps_small(taps, 2 * R + 1);
     long long plane = (long long)pitch * Y;
     const int V = force_v ? force_v : (R <= kZ2Vec4MaxR ? 4 : 2);
     int n_vec = (int)(plane / V);

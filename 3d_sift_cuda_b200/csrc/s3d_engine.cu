@@ -17,11 +17,9 @@
 
 #include "../../include/s3d.h"
 #include "s3d_voxel.cuh"
-#include "s3d_blur_fused.cuh"
 #include "s3d_blur2.cuh"
-#include "s3d_blur3.cuh"
+#include "s3d_blur4.cuh"
 #include "s3d_keypoint.cuh"
-#include "s3d_small_octaves.cuh"
 
 using namespace s3d;
 
@@ -125,33 +123,6 @@ static void build_tables(KpTables &t)
 // graph's concurrent branches (and the contexts of a batch) serialise behind each other.  With one carve-out
 // the shared-memory-heavy kernels (x+y tiles, orientation histograms) and the cache-reliant ones (detection,
 // z march, refinement) overlap.  S3D_CARVEOUT=<percent of the maximum shared memory> overrides the default.
-template <typename K>
-static void set_carveout(K kernel, int pct) { cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct); }
-template <int R>
-static void set_carveout_blur_r(int pct)
-{
-    set_carveout(blur_xy2_kernel<R, 8>, pct); set_carveout(blur_xy2_kernel<R, 16>, pct);
-    set_carveout(blur_z2_kernel<R, true, float2>, pct);  set_carveout(blur_z2_kernel<R, false, float2>, pct);
-    set_carveout(blur_z2_kernel<R, true, float4>, pct);  set_carveout(blur_z2_kernel<R, false, float4>, pct);
-    set_carveout(blur_xy_kernel<R>, pct);
-    set_carveout(blur_march_kernel<R, true>, pct);       set_carveout(blur_march_kernel<R, false>, pct);
-}
-static void set_carveout_all(int pct)
-{
-    set_carveout_blur_r<1>(pct); set_carveout_blur_r<2>(pct); set_carveout_blur_r<3>(pct); set_carveout_blur_r<4>(pct);
-    set_carveout_blur_r<5>(pct); set_carveout_blur_r<6>(pct); set_carveout_blur_r<7>(pct); set_carveout_blur_r<8>(pct);
-    set_carveout(detect_face_kernel, pct); set_carveout(detect_full_kernel, pct); set_carveout(detect_kernel, pct);
-    set_carveout(cand_refine_kernel, pct); set_carveout(compact_kernel, pct); set_carveout(row_offsets_kernel, pct);
-    set_carveout(orient_a_kernel, pct); set_carveout(orient_b_kernel, pct); set_carveout(describe_kernel, pct);
-    set_carveout(subsample_kernel, pct); set_carveout(halve_kernel, pct); set_carveout(double_kernel, pct);
-    set_carveout(pad_rows_kernel, pct); set_carveout(zero_ints_kernel, pct); set_carveout(dog_kernel, pct);
-    set_carveout(convert_rows_kernel<unsigned char>, pct); set_carveout(convert_rows_kernel<signed char>, pct);
-    set_carveout(convert_rows_kernel<short>, pct); set_carveout(convert_rows_kernel<unsigned short>, pct);
-    set_carveout(convert_rows_kernel<int>, pct); set_carveout(convert_rows_kernel<unsigned int>, pct);
-    set_carveout(convert_rows_kernel<double>, pct);
-    cudaGetLastError();
-}
-
 // ---------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------
@@ -196,20 +167,85 @@ struct Plan {
     unsigned long long last_use = 0;
 };
 
+// Experiment / profiling knobs.  Every S3D_* environment variable the library looks at is listed here and is read
+// exactly once per context (tuning_from_env, called by ctx_create); the defaults are what the tests and bench.py run.
+struct Tuning {
+    bool use_graph = true;       // S3D_NO_GRAPH=1: direct launches instead of one CUDA graph per (shape, options)
+    bool serial = false;         // S3D_SERIAL=1: no octave / detection branches, every kernel on the main stream
+    bool timing = false;         // S3D_STAGE_TIMING=1: no graph, events at stage boundaries of the main stream
+    bool stamps = false;         // S3D_STAMPS=1: %globaltimer stamps around the graph (s3d_debug_stamps)
+    int prof_skip = 0;           // S3D_PROF_SKIP (profiling only, results invalid): 1 no keypoint tail, 2 no detection/refinement, 4 no describe, 8 no orient_b
+    int f4_max_r = 6;            // S3D_F4_MAXR: one-kernel level (s3d_blur4.cuh) for radii up to this; wider levels use x+y / z kernels (s3d_blur2.cuh)
+    int f4_ty = 16;              // S3D_F4_TY=16|32: tile rows of the one-kernel level (two / one resident CTAs per SM)
+    int f4_ctas = 0;             // S3D_F4_CTAS: CTAs the one-kernel level aims for (0 = resident CTAs per SM x SMs)
+    int xy2_ctas = 2;            // S3D_XY2_CTAS_PER_SM: persistent x+y CTAs per SM (contexts of an s3d_batch use 1)
+    bool xy2_ctas_forced = false;
+    XY2Tune xy2;                 // S3D_XY2_SMEM_KB, S3D_XY2_TX / S3D_XY2_TY, S3D_XY2_KY, S3D_XY2_THREADS: tile choice of the x+y kernel
+    int z2_vec = 0;              // S3D_Z2_VEC=2|4: columns per thread of the z march (0 = by radius)
+    int march_target = 0;        // S3D_MARCH_TARGET: threads wanted in flight in the z march (0 = 256 per SM)
+    int detect_ctas = 0;         // S3D_DETECT_CTAS: resident detect_face blocks per SM (0 = whole grid; contexts of an s3d_batch: 4)
+    bool detect_ctas_forced = false;
+    int tail_a = 3, tail_b = 6, tail_d = 10;   // S3D_TAIL_BLOCKS=a,b,d: blocks per SM of orient_a / orient_b / describe
+    int desc_threads = 128;      // S3D_DESC_THREADS=64|128: threads per describe block
+    int max_plans = 6;           // S3D_PLAN_CACHE: resident plans (shapes) per context
+};
+
+static int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
+}
+
+static Tuning tuning_from_env()
+{
+    Tuning t;
+    t.use_graph = env_int("S3D_NO_GRAPH", 0) != 1;
+    t.serial = env_int("S3D_SERIAL", 0) == 1;
+    t.timing = env_int("S3D_STAGE_TIMING", 0) == 1;
+    if (t.timing) t.use_graph = false;        // event nodes inside graphs carry no timestamps
+    t.stamps = env_int("S3D_STAMPS", 0) == 1;
+    t.prof_skip = env_int("S3D_PROF_SKIP", 0);
+    int v = env_int("S3D_F4_MAXR", t.f4_max_r);
+    if (v >= 0) t.f4_max_r = v < kF4MaxR ? v : kF4MaxR;
+    if (env_int("S3D_F4_TY", 16) == 32) t.f4_ty = 32;
+    t.f4_ctas = env_int("S3D_F4_CTAS", 0);
+    v = env_int("S3D_XY2_CTAS_PER_SM", 0);
+    if (v >= 1 && v <= 4) { t.xy2_ctas = v; t.xy2_ctas_forced = true; }
+    v = env_int("S3D_XY2_SMEM_KB", t.xy2.max_kb);
+    if (v >= 16 && v <= 112) t.xy2.max_kb = v;
+    t.xy2.force_tx = env_int("S3D_XY2_TX", 0);
+    t.xy2.force_ty = env_int("S3D_XY2_TY", 0);
+    v = env_int("S3D_XY2_KY", 0);
+    if (v == 8 || v == 16) t.xy2.ky = v;
+    if (env_int("S3D_XY2_THREADS", 0) == 128) t.xy2.threads = 128;
+    v = env_int("S3D_Z2_VEC", 0);
+    if (v == 2 || v == 4) t.z2_vec = v;
+    t.march_target = env_int("S3D_MARCH_TARGET", 0);
+    v = env_int("S3D_DETECT_CTAS", -1);
+    if (v >= 0) { t.detect_ctas = v; t.detect_ctas_forced = true; }
+    {
+        const char *tb = getenv("S3D_TAIL_BLOCKS");
+        int a = 0, b = 0, d = 0;
+        if (tb && sscanf(tb, "%d,%d,%d", &a, &b, &d) == 3 && a > 0 && b > 0 && d > 0) { t.tail_a = a; t.tail_b = b; t.tail_d = d; }
+    }
+    v = env_int("S3D_DESC_THREADS", 0);
+    if (v == 64 || v == 128) t.desc_threads = v;
+    v = env_int("S3D_PLAN_CACHE", 0);
+    if (v >= 1) t.max_plans = v;
+    return t;
+}
+
 struct s3d_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::string err;
     Plan *plan = nullptr;               // active plan (one of `plans`)
-    std::vector<Plan *> plans;          // resident plans, least recently used evicted beyond max_plans: a caller that
-    int max_plans = 6;                  // alternates between a few shapes (slab mode: one per octave) keeps its buffers
-    unsigned long long use_clock = 0;   // and instantiated graphs (S3D_PLAN_CACHE)
+    std::vector<Plan *> plans;          // resident plans, least recently used evicted beyond tune.max_plans: a caller that
+    unsigned long long use_clock = 0;   // alternates between a few shapes (slab mode: one per octave) keeps its buffers and graphs
     int launches = 0;
     int last_launches = 0;
-    bool use_graph = true;
     int sm_count = 148;
-    int march_target = 0;
     bool has_result = false;
     int *h_counts = nullptr;     // pinned: kp_count, n_features, err
     // Speculative result copy: when rows will be fetched by the host (s3d_extract, s3d_batch_extract*), the counts
@@ -223,29 +259,8 @@ struct s3d_ctx {
     int spec_guess = 2048;           // rows to copy next time (tracks 1.25 x the last count)
     bool spec_valid = false;         // h_counts / h_rows belong to the current result
     cudaStream_t cur = nullptr;  // stream the stage launchers enqueue on (main stream or an octave branch)
-    bool fused = false;          // S3D_FUSED=1: one-kernel TMA blur level (12 B/voxel but ~2x the instructions of the
-                                 // three-pass path at MNI size, where the volume sits in L2; see profiles/README.md)
-    long long fused_small_voxels = 0;   // S3D_FUSED_SMALL: volumes up to this many voxels use the one-kernel level
-    bool small_kernel = false;   // S3D_SMALL=1: octaves of a few thousand voxels in one cluster kernel.  Measured no faster than
-                                 // the per-level launches (each pass is an L2 round trip + a cluster barrier either way), so off.
-    bool xy_fused = true;        // x and y passes in one TMA-tiled kernel (S3D_XY=0: separate passes)
-    bool blur2 = true;           // second-generation level kernels (s3d_blur2.cuh); S3D_BLUR2=0: first generation
-    int f3_max_r = 0;            // one-kernel level (s3d_blur3.cuh) for radii up to this (S3D_F3_MAXR; 0 = never: measured slower than the two-kernel level at MNI size, see profiles/README.md) ...
-    long long f3_min_voxels = 0; // ... and volumes of at least this many voxels (S3D_F3_MIN_VOXELS)
-    int f3_ctas = 0;             // S3D_F3_CTAS: CTAs the one-kernel level aims for (0 = one per SM)
+    Tuning tune;                 // S3D_* environment knobs, read once in ctx_create
     unsigned long long *d_stamps = nullptr;   // S3D_STAMPS=1
-    bool z3 = false;             // S3D_Z3=1: z pass with the shared-memory ring (blur_z3_kernel) instead of the register march
-    int z2_vec = 0;              // S3D_Z2_VEC=2|4: columns per thread of the z march (0 = by radius)
-    int tail_a = 3, tail_b = 6, tail_d = 10;   // blocks per SM of orient_a / orient_b / describe (S3D_TAIL_BLOCKS=a,b,d)
-    int xy2_ctas = 2;            // persistent x+y CTAs per SM (S3D_XY2_CTAS_PER_SM; contexts of an s3d_batch use 1)
-    bool xy2_ctas_forced = false;
-    int detect_ctas = 0;         // resident detect_face blocks per SM (0 = whole grid; S3D_DETECT_CTAS; contexts of an s3d_batch: 4)
-    bool detect_ctas_forced = false;
-    int desc_threads = 128;      // threads per describe block (S3D_DESC_THREADS: 64 or 128)
-    int prof_skip = 0;           // S3D_PROF_SKIP (profiling only, results invalid): 1 = no keypoint tail, 2 = no detection/refinement, 3 = both
-    bool serial = false;         // S3D_SERIAL=1: no branches, every kernel on the main stream (standalone kernel times)
-    int fused_ctas = 0;          // S3D_FUSED_CTAS: CTAs the fused blur aims for (0 = 2 per SM)
-    bool timing = false;         // S3D_STAGE_TIMING=1: no graph, events at stage boundaries of the main stream
     std::vector<std::pair<std::string, cudaEvent_t>> marks;
     cudaStream_t side[kMaxOct] = {}, det[kMaxOct] = {};     // octave branch, detection/refinement branch
     cudaEvent_t ev_fork[kMaxOct] = {}, ev_done[kMaxOct] = {}, ev_lvl[kMaxOct][4] = {};
@@ -299,14 +314,7 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
     if (borrow) {
         ctx->stream = (cudaStream_t)stream;
     } else {
-        const char *sp = getenv("S3D_SIDE_PRIO");
-        if (sp && sp[0] == 'm') {     // main chain above the side branches (experiments)
-            int lo = 0, hi = 0;
-            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            CK(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, hi));
-        } else {
-            CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        }
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         ctx->own_stream = true;
     }
     KpTables t;
@@ -322,10 +330,6 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
     // behind them (stream priorities are kept by the captured graph nodes).
     int prio_lo = 0, prio_hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    {   // S3D_SIDE_PRIO=low: side branches below the main chain (experiments)
-        const char *sp = getenv("S3D_SIDE_PRIO");
-        if (sp && (sp[0] == 'l' || sp[0] == 'm')) prio_hi = prio_lo;
-    }
     for (int o = 1; o < kMaxOct; o++) {
         CK(cudaStreamCreateWithPriority(&ctx->side[o], cudaStreamNonBlocking, prio_hi));
         CK(cudaEventCreateWithFlags(&ctx->ev_done[o], cudaEventDisableTiming));
@@ -336,57 +340,10 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
         if (!ctx->ev_done[o]) CK(cudaEventCreateWithFlags(&ctx->ev_done[o], cudaEventDisableTiming));
         for (int k = 0; k < 4; k++) CK(cudaEventCreateWithFlags(&ctx->ev_lvl[o][k], cudaEventDisableTiming));
     }
-    const char *g = getenv("S3D_NO_GRAPH");
-    if (g && g[0] == '1') ctx->use_graph = false;
-    const char *fu = getenv("S3D_FUSED");
-    if (fu) ctx->fused = (fu[0] == '1');
-    const char *fs = getenv("S3D_FUSED_SMALL");
-    if (fs) ctx->fused_small_voxels = atoll(fs);
-    const char *sk = getenv("S3D_SMALL");
-    if (sk) ctx->small_kernel = (sk[0] != '0');
-    const char *xy = getenv("S3D_XY");
-    if (xy) ctx->xy_fused = (xy[0] != '0');
-    const char *b2 = getenv("S3D_BLUR2");
-    if (b2) ctx->blur2 = (b2[0] != '0');
+    ctx->tune = tuning_from_env();
     CK(init_blur2_attrs());
-    CK(init_blur3_attrs());
-    const char *f3r = getenv("S3D_F3_MAXR");
-    if (f3r) ctx->f3_max_r = atoi(f3r);
-    const char *f3v = getenv("S3D_F3_MIN_VOXELS");
-    if (f3v) ctx->f3_min_voxels = atoll(f3v);
-    const char *stp = getenv("S3D_STAMPS");
-    if (stp && stp[0] == '1') CK(cudaMalloc((void **)&ctx->d_stamps, 4 * sizeof(unsigned long long)));
-    const char *z3e = getenv("S3D_Z3");
-    if (z3e) ctx->z3 = (z3e[0] == '1');
-    const char *zv = getenv("S3D_Z2_VEC");
-    if (zv) ctx->z2_vec = (atoi(zv) == 2 || atoi(zv) == 4) ? atoi(zv) : 0;
-    const char *tb = getenv("S3D_TAIL_BLOCKS");
-    if (tb) { int a = 0, b = 0, d = 0; if (sscanf(tb, "%d,%d,%d", &a, &b, &d) == 3 && a > 0 && b > 0 && d > 0) { ctx->tail_a = a; ctx->tail_b = b; ctx->tail_d = d; } }
-    const char *pc = getenv("S3D_PLAN_CACHE");
-    if (pc && atoi(pc) >= 1) ctx->max_plans = atoi(pc);
-    {
-        const char *co = getenv("S3D_CARVEOUT");
-        int pct = co ? atoi(co) : -1;
-        if (pct >= 0 && pct <= 100) set_carveout_all(pct);
-    }
-    const char *xc = getenv("S3D_XY2_CTAS_PER_SM");
-    if (xc && atoi(xc) >= 1 && atoi(xc) <= 4) { ctx->xy2_ctas = atoi(xc); ctx->xy2_ctas_forced = true; }
-    const char *dct = getenv("S3D_DETECT_CTAS");
-    if (dct && atoi(dct) >= 0) { ctx->detect_ctas = atoi(dct); ctx->detect_ctas_forced = true; }
-    const char *dth = getenv("S3D_DESC_THREADS");
-    if (dth && (atoi(dth) == 64 || atoi(dth) == 128)) ctx->desc_threads = atoi(dth);
-    const char *psk = getenv("S3D_PROF_SKIP");
-    if (psk) ctx->prof_skip = atoi(psk);
-    const char *ser = getenv("S3D_SERIAL");
-    if (ser) ctx->serial = (ser[0] == '1');
-    const char *f3c = getenv("S3D_F3_CTAS");
-    if (f3c) ctx->f3_ctas = atoi(f3c);
-    const char *fc = getenv("S3D_FUSED_CTAS");
-    ctx->fused_ctas = fc ? atoi(fc) : 0;
-    const char *tm = getenv("S3D_STAGE_TIMING");
-    if (tm && tm[0] == '1') { ctx->timing = true; ctx->use_graph = false; }   // event nodes inside graphs carry no timestamps
-    const char *mt = getenv("S3D_MARCH_TARGET");
-    ctx->march_target = mt ? atoi(mt) : 0;
+    CK(init_blur4_attrs());
+    if (ctx->tune.stamps) CK(cudaMalloc((void **)&ctx->d_stamps, 4 * sizeof(unsigned long long)));
     return S3D_OK;
 }
 
@@ -476,71 +433,31 @@ static bool fast_layout(const void *a, const void *b, const void *c, int pitch)
     return pitch % 8 == 0 && ((uintptr_t)a % 32) == 0 && ((uintptr_t)b % 32) == 0 && ((uintptr_t)c % 32) == 0;
 }
 
-// Split the blur axis into segments so that about `target` threads are in flight; each segment
-// re-reads 2R halo inputs, so segments are kept >= 16 long.
-static void march_segments(int target, long long cols, int len, int &seg_len, int &n_seg)
-{
-    n_seg = (int)((target + cols - 1) / cols);
-    if (n_seg < 1) n_seg = 1;
-    int max_seg = (len + 15) / 16;
-    if (n_seg > max_seg) n_seg = max_seg;
-    seg_len = (len + n_seg - 1) / n_seg;
-    n_seg = (len + seg_len - 1) / seg_len;
-}
-
+// One blur level on the fast path (pitched layout, symmetric taps of radius R <= kMaxFastR): the one-kernel level
+// for radii up to tune.f4_max_r, else the x+y kernel followed by the z march.  Returns false when nothing was
+// launched (the driver could not encode a tensor map): the caller falls back to the generic kernels.
 template <int R>
-static void launch_blur_fast(s3d_ctx *ctx, const float *in, float *tmp, float *out, int X, int Y, int Z, int pitch,
-                             const float *taps, float *dog)
+static bool launch_blur_fast(s3d_ctx *ctx, const float *in, float *tmp, float *out, int X, int Y, int Z, int pitch,
+                             const float *taps, float *dog, cudaError_t *err)
 {
-    TapsSmall t;
-    memset(&t, 0, sizeof(t));
-    for (int j = 0; j < 2 * R + 1; j++) t.w[j] = taps[j];
-    long long plane = (long long)pitch * Y;
-    const bool sym = taps_symmetric(taps, 2 * R + 1);
-    if (sym && R <= ctx->f3_max_r && plane * Z >= ctx->f3_min_voxels) {
-        cudaError_t e = cudaSuccess;
-        if (launch_blur_f3<R>(ctx->cur, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, ctx->f3_ctas, &e)) {
+    const long long plane = (long long)pitch * Y;
+    if (plane * Z >= (1ll << 31)) return false;
+    const Tuning &tn = ctx->tune;
+    if constexpr (R <= kF4MaxR) {
+        if (R <= tn.f4_max_r &&
+            (tn.f4_ty == 32 ? launch_blur_f4<R, 32>(ctx->cur, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, tn.f4_ctas, err)
+                            : launch_blur_f4<R, 16>(ctx->cur, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, tn.f4_ctas, err))) {
             ctx->launches += 1;
-            return;
+            return true;
         }
     }
-    if (ctx->blur2 && sym && plane * Z < (1ll << 31)) {
-        cudaError_t e = cudaSuccess;
-        if (launch_blur_xy2<R>(ctx->cur, in, tmp, X, Y, Z, pitch, taps, ctx->sm_count, ctx->xy2_ctas, &e)) {
-            int target2 = ctx->march_target > 0 ? ctx->march_target : ctx->sm_count * 256;
-            if (ctx->z3) launch_blur_z3<R>(ctx->cur, tmp, out, in, dog, Y, Z, pitch, taps, target2);
-            else launch_blur_z2<R>(ctx->cur, tmp, out, in, dog, Y, Z, pitch, taps, target2, ctx->z2_vec);
-            ctx->launches += 2;
-            return;
-        }
-    }
-    int target = ctx->march_target > 0 ? ctx->march_target : ctx->sm_count * 1024;
-    // x and y: one TMA-tiled kernel (in -> tmp); fall back to the two separate passes if the driver
-    // cannot encode a tensor map (or S3D_XY=0)
-    CUtensorMap map;
-    if (ctx->xy_fused && Z <= 65535 && make_volume_map_xy(&map, in, Y, Z, pitch, R)) {
-        launch_blur_xy<R>(ctx->cur, map, tmp, X, Y, Z, pitch, taps);
-        ctx->launches += 1;
-    } else {
-        long long n_chunks = plane * Z / 8;
-        blur_x_kernel<R><<<(unsigned)((n_chunks + 255) / 256), 256, 0, ctx->cur>>>(in, out, pitch, X, n_chunks, t);
-        long long cols = (long long)pitch * Z;
-        int seg_len, n_seg;
-        march_segments(target, cols, Y, seg_len, n_seg);
-        dim3 grid((unsigned)((cols + 127) / 128), (unsigned)n_seg);
-        blur_march_kernel<R, false><<<grid, 128, 0, ctx->cur>>>(out, tmp, nullptr, nullptr, cols, pitch, plane, pitch, Y, seg_len, t);
-        ctx->launches += 2;
-    }
-    // z: tmp -> out (+ DoG)
-    {
-        long long cols = plane;
-        int seg_len, n_seg;
-        march_segments(target, cols, Z, seg_len, n_seg);
-        dim3 grid((unsigned)((cols + 127) / 128), (unsigned)n_seg);
-        if (dog) blur_march_kernel<R, true><<<grid, 128, 0, ctx->cur>>>(tmp, out, in, dog, cols, plane, 0, plane, Z, seg_len, t);
-        else blur_march_kernel<R, false><<<grid, 128, 0, ctx->cur>>>(tmp, out, nullptr, nullptr, cols, plane, 0, plane, Z, seg_len, t);
-        ctx->launches += 1;
-    }
+    if (!launch_blur_xy2<R>(ctx->cur, in, tmp, X, Y, Z, pitch, taps, ctx->sm_count, tn.xy2_ctas, tn.xy2, err)) return false;
+    ctx->launches += 1;
+    if (*err != cudaSuccess) return true;
+    const int target = tn.march_target > 0 ? tn.march_target : ctx->sm_count * 256;
+    *err = launch_blur_z2<R>(ctx->cur, tmp, out, in, dog, Y, Z, pitch, taps, target, tn.z2_vec);
+    ctx->launches += 1;
+    return true;
 }
 
 static void launch_blur_generic(s3d_ctx *ctx, const float *in, float *tmp, float *out, int X, int Y, int Z, int pitch,
@@ -573,43 +490,32 @@ static s3d_status blur3d(s3d_ctx *ctx, const float *in, float *tmp, float *out, 
         return fail(ctx, S3D_ERR_INVALID, "s3d_blur3d: bad argument");
     if (in == out || in == tmp || tmp == out) return fail(ctx, S3D_ERR_INVALID, "s3d_blur3d: in/tmp/out must be distinct");
     int R = ntaps / 2;
-    bool fast = fast_layout(in, tmp, out, pitch) && (!dog || ((uintptr_t)dog % 32) == 0) && R >= 1 && R <= kMaxFastR;
-    // one-kernel level: always when asked for (S3D_FUSED=1), and for small octaves, whose cost is launch
-    // latency on a dependent chain rather than instructions
-    bool small = (long long)pitch * Y * Z <= ctx->fused_small_voxels;
-    if (fast && (ctx->fused || small)) {
-        CUtensorMap map;
-        if (make_volume_map(&map, in, Y, Z, pitch, R)) {
-            cudaError_t e = cudaSuccess;
-            switch (R) {
-            case 1: e = launch_blur_fused<1>(ctx->cur, map, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, ctx->fused_ctas); break;
-            case 2: e = launch_blur_fused<2>(ctx->cur, map, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, ctx->fused_ctas); break;
-            case 3: e = launch_blur_fused<3>(ctx->cur, map, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, ctx->fused_ctas); break;
-            case 4: e = launch_blur_fused<4>(ctx->cur, map, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, ctx->fused_ctas); break;
-            case 5: e = launch_blur_fused<5>(ctx->cur, map, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, ctx->fused_ctas); break;
-            case 6: e = launch_blur_fused<6>(ctx->cur, map, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, ctx->fused_ctas); break;
-            case 7: e = launch_blur_fused<7>(ctx->cur, map, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, ctx->fused_ctas); break;
-            default: e = launch_blur_fused<8>(ctx->cur, map, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, ctx->fused_ctas); break;
+    bool fast = fast_layout(in, tmp, out, pitch) && (!dog || ((uintptr_t)dog % 32) == 0) && R >= 1 && R <= kMaxFastR &&
+                taps_symmetric(taps, ntaps);
+    if (fast) {
+        cudaError_t e = cudaSuccess;
+        bool launched = false;
+        switch (R) {
+        case 1: launched = launch_blur_fast<1>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog, &e); break;
+        case 2: launched = launch_blur_fast<2>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog, &e); break;
+        case 3: launched = launch_blur_fast<3>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog, &e); break;
+        case 4: launched = launch_blur_fast<4>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog, &e); break;
+        case 5: launched = launch_blur_fast<5>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog, &e); break;
+        case 6: launched = launch_blur_fast<6>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog, &e); break;
+        case 7: launched = launch_blur_fast<7>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog, &e); break;
+        default: launched = launch_blur_fast<8>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog, &e); break;
+        }
+        if (launched) {
+            if (e != cudaSuccess) {
+                char b_[256];
+                snprintf(b_, sizeof(b_), "blur level (radius %d) launch failed: %s", R, cudaGetErrorString(e));
+                ctx->err = b_;
+                return S3D_ERR_CUDA;
             }
-            ctx->launches += 1;
-            CK(e);
             return S3D_OK;
         }
     }
-    if (fast) {
-        switch (R) {
-        case 1: launch_blur_fast<1>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog); break;
-        case 2: launch_blur_fast<2>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog); break;
-        case 3: launch_blur_fast<3>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog); break;
-        case 4: launch_blur_fast<4>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog); break;
-        case 5: launch_blur_fast<5>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog); break;
-        case 6: launch_blur_fast<6>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog); break;
-        case 7: launch_blur_fast<7>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog); break;
-        default: launch_blur_fast<8>(ctx, in, tmp, out, X, Y, Z, pitch, taps, dog); break;
-        }
-    } else {
-        launch_blur_generic(ctx, in, tmp, out, X, Y, Z, pitch, taps, ntaps, dog);
-    }
+    launch_blur_generic(ctx, in, tmp, out, X, Y, Z, pitch, taps, ntaps, dog);
     CK(cudaGetLastError());
     return S3D_OK;
 }
@@ -697,9 +603,9 @@ static s3d_status detect_two_pass(s3d_ctx *ctx, const float *finer, const float 
         return detect_raw_launch(ctx, finer, centre, X, Y, Z, pitch, raw_min, n_min, raw_max, n_max, cap, own0, own1);
     const int n_zblocks = (Z - 2 + kDetectZ - 1) / kDetectZ;
     dim3 block(32, 8), grid((X - 2 + 31) / 32, (Y - 2 + 7) / 8, n_zblocks);
-    if (ctx->detect_ctas > 0) {        // batch contexts: cap the resident blocks (see detect_face_kernel)
+    if (ctx->tune.detect_ctas > 0) {        // batch contexts: cap the resident blocks (see detect_face_kernel)
         long long per_layer = (long long)grid.x * grid.y;
-        long long gz = ((long long)ctx->detect_ctas * ctx->sm_count + per_layer - 1) / per_layer;
+        long long gz = ((long long)ctx->tune.detect_ctas * ctx->sm_count + per_layer - 1) / per_layer;
         if (gz < 1) gz = 1;
         if (gz < n_zblocks) grid.z = (unsigned)gz;
     }
@@ -787,7 +693,7 @@ static s3d_status plan_build(s3d_ctx *ctx, int X, int Y, int Z, const s3d_params
             q->last_use = ctx->use_clock;
             return S3D_OK;
         }
-    while ((int)ctx->plans.size() >= (ctx->max_plans > 1 ? ctx->max_plans : 1)) {
+    while ((int)ctx->plans.size() >= (ctx->tune.max_plans > 1 ? ctx->tune.max_plans : 1)) {
         Plan *lru = ctx->plans[0];
         for (Plan *q : ctx->plans) if (q->last_use < lru->last_use) lru = q;
         plan_destroy(ctx, lru);
@@ -943,7 +849,7 @@ static s3d_status plan_fill(s3d_ctx *ctx, Plan *p, int X, int Y, int Z, const s3
 // ---------------------------------------------------------------------------------------------------
 static void mark(s3d_ctx *ctx, const char *name)
 {
-    if (!ctx->timing) return;
+    if (!ctx->tune.timing) return;
     if (!strcmp(name, "start")) {     // keep only the latest extraction
         for (auto &m : ctx->marks) cudaEventDestroy(m.second);
         ctx->marks.clear();
@@ -956,7 +862,7 @@ static void mark(s3d_ctx *ctx, const char *name)
 
 static void report_marks(s3d_ctx *ctx)
 {
-    if (!ctx->timing || ctx->marks.empty()) return;
+    if (!ctx->tune.timing || ctx->marks.empty()) return;
     fprintf(stderr, "s3d stage timing (main stream, us since previous mark):\n");
     for (size_t i = 1; i < ctx->marks.size(); i++) {
         float ms = 0;
@@ -966,7 +872,7 @@ static void report_marks(s3d_ctx *ctx)
     float tot = 0;
     cudaEventElapsedTime(&tot, ctx->marks.front().second, ctx->marks.back().second);
     fprintf(stderr, "  %-28s %9.1f\n", "total", tot * 1e3f);
-    if (!ctx->use_graph) {
+    if (!ctx->tune.use_graph) {
         for (auto &m : ctx->marks) cudaEventDestroy(m.second);
         ctx->marks.clear();
     }
@@ -1009,15 +915,9 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     // Octave o+1 only needs level 3 of octave o, so every octave runs on its own branch (stream / graph
     // branch): the tail of an octave overlaps the whole chain of smaller octaves, which is launch-latency bound.
     ListDesc L{ p->n_lists, p->cand_cap, p->cand_raw, p->counts };
-    // octaves [o_small, n_oct) are small enough for the single cluster kernel (never octave 0, never in slab mode)
-    int o_small = p->n_oct;
-    if (ctx->small_kernel && !p->slab) {
-        while (o_small > 1 && (long long)p->pyr.oct[o_small - 1].pitch * p->pyr.oct[o_small - 1].Y * p->pyr.oct[o_small - 1].Z <= kSmallMaxVoxels) o_small--;
-        for (int j = 0; j < 5; j++) if (p->n_lvl_taps[j] > 2 * kMaxFastR + 1) o_small = p->n_oct;
-    }
-    for (int o = 0; o < o_small; o++) {
+    for (int o = 0; o < p->n_oct; o++) {
         const OctaveDesc &od = p->pyr.oct[o];
-        cudaStream_t so = (o == 0 || ctx->serial) ? st : ctx->side[o];
+        cudaStream_t so = (o == 0 || ctx->tune.serial) ? st : ctx->side[o];
         ctx->cur = so;
         if (o > 0) CK(cudaStreamWaitEvent(so, ctx->ev_fork[o - 1], 0));
         for (int j = 1; j < 6; j++) {
@@ -1029,23 +929,6 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
                 s = resize_launch(ctx, 0, b.p, od.X, od.Y, od.Z, od.pitch, p->g[(o + 1) * 6].p, nx.pitch);
                 if (s != S3D_OK) { ctx->cur = st; return s; }
                 CK(cudaEventRecord(ctx->ev_fork[o], so));
-                if (o + 1 == o_small) {
-                    // all remaining octaves: one cluster kernel (levels, DoGs, subsamples, detection), then one
-                    // refinement launch over their candidate lists
-                    cudaStream_t ss = ctx->side[o_small];
-                    CK(cudaStreamWaitEvent(ss, ctx->ev_fork[o], 0));
-                    SmallOctArgs sa;
-                    memset(&sa, 0, sizeof(sa));
-                    sa.o_first = o_small; sa.n_oct = p->n_oct;
-                    for (int q = 0; q < 5; q++) { sa.n_taps[q] = p->n_lvl_taps[q]; for (int t = 0; t < p->n_lvl_taps[q]; t++) sa.taps[q][t] = p->lvl_taps[q][t]; }
-                    for (int q = 0; q < p->n_oct; q++) sa.tmp[q] = p->oct_tmp[q];
-                    sa.cand_raw = p->cand_raw; sa.counts = p->counts; sa.cand_cap = p->cand_cap;
-                    small_octaves_kernel<<<kSmallClusterCtas, kSmallThreads, 0, ss>>>(p->pyr, sa);
-                    int nl = (p->n_oct - o_small) * 6;
-                    cand_refine_kernel<<<dim3(nl, 16), 256, 0, ss>>>(p->pyr, L, o_small * 6, p->kp_stage, p->stage_flags, err);
-                    ctx->launches += 2;
-                    CK(cudaEventRecord(ctx->ev_done[o_small], ss));
-                }
             }
             if (o == 0) { char nm[32]; snprintf(nm, sizeof(nm), "oct0 level %d", j); mark(ctx, nm); }
             if (j >= 2) {
@@ -1054,11 +937,11 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
                 // The branch runs beside the blur of the next level; only the refinement of centre level 3
                 // (after level 5) is exposed.
                 CK(cudaEventRecord(ctx->ev_lvl[o][j - 2], so));
-                cudaStream_t sd = ctx->serial ? st : ctx->det[o];
+                cudaStream_t sd = ctx->tune.serial ? st : ctx->det[o];
                 CK(cudaStreamWaitEvent(sd, ctx->ev_lvl[o][j - 2], 0));
                 ctx->cur = sd;
                 int c_det = j - 1, c_ref = j - 2;
-                if (c_det <= 3 && !(ctx->prof_skip & 2)) {
+                if (c_det <= 3 && !(ctx->tune.prof_skip & 2)) {
                     int l0 = (o * 3 + (c_det - 1)) * 2;
                     s = detect_two_pass(ctx, od.d[c_det - 1], od.d[c_det], od.X, od.Y, od.Z, od.pitch,
                                         p->face[o * 3 + c_det - 1], p->face_counts + o * 3 + c_det - 1, p->face_cap[o * 3 + c_det - 1],
@@ -1066,7 +949,7 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
                                         p->cand_raw + (size_t)(l0 + 1) * p->cand_cap, p->counts + l0 + 1, p->cand_cap, err, od.own0, od.own1);
                     if (s != S3D_OK) { ctx->cur = st; return s; }
                 }
-                if (c_ref >= 1 && !(ctx->prof_skip & 2)) {
+                if (c_ref >= 1 && !(ctx->tune.prof_skip & 2)) {
                     int l0 = (o * 3 + (c_ref - 1)) * 2;
                     cand_refine_kernel<<<dim3(2, 32), 256, 0, sd>>>(p->pyr, L, l0, p->kp_stage, p->stage_flags, err);
                     ctx->launches++;
@@ -1077,27 +960,26 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
         }
     }
     ctx->cur = st;
-    for (int o = 0; o < o_small; o++) CK(cudaStreamWaitEvent(st, ctx->ev_done[o], 0));
-    if (o_small < p->n_oct) CK(cudaStreamWaitEvent(st, ctx->ev_done[o_small], 0));
+    for (int o = 0; o < p->n_oct; o++) CK(cudaStreamWaitEvent(st, ctx->ev_done[o], 0));
     mark(ctx, "join (detect+refine tails)");
-    if (ctx->prof_skip & 1) { CK(cudaGetLastError()); return S3D_OK; }
+    if (ctx->tune.prof_skip & 1) { CK(cudaGetLastError()); return S3D_OK; }
     compact_kernel<<<1, 1024, 0, st>>>(L, p->kp_stage, p->stage_flags, p->kps, kp_count, p->kp_cap, err);
     mark(ctx, "compact");
     // orientation: per keypoint, then per (keypoint, primary direction)
     float eig = prm->eig_thres;
     int *work_b_count = kp_count + 3;
-    orient_a_kernel<<<ctx->sm_count * ctx->tail_a, 256, sizeof(HistSmem), st>>>(p->pyr, p->kps, kp_count, eig, p->kp_nprim, p->kp_eigs,
+    orient_a_kernel<<<ctx->sm_count * ctx->tune.tail_a, 256, sizeof(HistSmem), st>>>(p->pyr, p->kps, kp_count, eig, p->kp_nprim, p->kp_eigs,
                                                                      p->kp_ori0, p->kp_p1, p->kp_patch0, p->work_b, work_b_count);
     mark(ctx, "orient_a");
-    if (ctx->prof_skip & 8) { CK(cudaGetLastError()); return S3D_OK; }
-    orient_b_kernel<<<ctx->sm_count * ctx->tail_b, 256, sizeof(HistSmem), st>>>(p->work_b, work_b_count, p->kp_p1, p->kp_patch0, p->kp_nsec, p->kp_rots);
+    if (ctx->tune.prof_skip & 8) { CK(cudaGetLastError()); return S3D_OK; }
+    orient_b_kernel<<<ctx->sm_count * ctx->tune.tail_b, 256, sizeof(HistSmem), st>>>(p->work_b, work_b_count, p->kp_p1, p->kp_patch0, p->kp_nsec, p->kp_rots);
     mark(ctx, "orient_b");
     row_offsets_kernel<<<1, 1024, 0, st>>>(p->kp_nprim, p->kp_nsec, kp_count, p->nrows, p->row_off, p->row_map, n_features, p->row_cap, err);
     float size_factor = 1.0f;
     if (p->double_mode > 0 || p->pre_step_done > 0) size_factor /= 2; else if (p->double_mode < 0 || p->pre_step_done < 0) size_factor *= 2;
-    if (ctx->prof_skip & 4) { CK(cudaGetLastError()); return S3D_OK; }
-    int grid_d = ctx->sm_count * ctx->tail_d;
-    describe_kernel<<<grid_d, ctx->desc_threads, sizeof(DescribeSmem), st>>>(p->pyr, p->kps, n_features, p->row_map, p->kp_nsec, p->kp_eigs,
+    if (ctx->tune.prof_skip & 4) { CK(cudaGetLastError()); return S3D_OK; }
+    int grid_d = ctx->sm_count * ctx->tune.tail_d;
+    describe_kernel<<<grid_d, ctx->tune.desc_threads, sizeof(DescribeSmem), st>>>(p->pyr, p->kps, n_features, p->row_map, p->kp_nsec, p->kp_eigs,
                                                               p->kp_ori0, p->kp_rots, p->kp_patch0, prm->descriptor, size_factor, p->octave_base,
                                                               p->row_cap, p->feats, p->dbg_patches, p->dbg_prerank);
     mark(ctx, "row_offsets+describe");
@@ -1132,7 +1014,7 @@ static s3d_status run_pipeline(s3d_ctx *ctx, const s3d_params *prm)
 {
     Plan *p = ctx->plan;
     ctx->has_result = false;
-    if (!ctx->use_graph) {
+    if (!ctx->tune.use_graph) {
         ctx->launches = 0;
         s3d_status s = enqueue_pipeline(ctx, prm);
         ctx->last_launches = ctx->launches;
@@ -1419,11 +1301,11 @@ extern "C" s3d_status s3d_batch_create(int device, int n_contexts, s3d_batch **o
             delete b;
             return st;
         }
-        if (!c->xy2_ctas_forced && n_contexts > 1) c->xy2_ctas = 1;      // throughput mode, see launch_blur_xy2
+        if (!c->tune.xy2_ctas_forced && n_contexts > 1) c->tune.xy2_ctas = 1;      // throughput mode, see launch_blur_xy2
         // ... and the z march runs as one segment: the threads it lacks to cover the memory latency alone are
         // provided by the other volumes in flight, and no halo planes are read twice (S3D_MARCH_TARGET overrides)
-        if (c->march_target == 0 && n_contexts > 1) c->march_target = 1;
-        if (!c->detect_ctas_forced && n_contexts > 1) c->detect_ctas = 4;
+        if (c->tune.march_target == 0 && n_contexts > 1) c->tune.march_target = 1;
+        if (!c->tune.detect_ctas_forced && n_contexts > 1) c->tune.detect_ctas = 4;
         b->ctx.push_back(c);
     }
     *out = b;

@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 #include "../../include/s3d.h"
 
 namespace s3d {
@@ -19,46 +20,20 @@ namespace s3d {
 constexpr int kMaxFastR = 8;      // widest templated radius (17 taps, sigma 3.09 of the octave schedule)
 constexpr int kMaxTaps = 129;
 
-struct TapsSmall { float w[2 * kMaxFastR + 1]; };
-struct TapsAny { int n; float w[kMaxTaps]; };
-
-// ---------------------------------------------------------------------------------------------
-// x pass.  The volume is treated as one linear array of pitch*Y*Z floats (rows are contiguous and
-// pitch % 8 == 0, so an 8-float chunk never straddles a row).  Each thread produces 8 consecutive
-// outputs from a register window loaded with aligned 128-bit loads; neighbouring threads overlap in
-// L1.  Window groups that fall left of x=0 or right of x=pitch-1 are zero (zero padding).
-// ---------------------------------------------------------------------------------------------
-template <int R>
-__global__ void __launch_bounds__(256) blur_x_kernel(const float *__restrict__ in, float *__restrict__ out,
-                                                     int pitch, int X, long long n_chunks,
-                                                     const __grid_constant__ TapsSmall taps)
+// z0 = -0.0f, handed to the kernels at run time: the packed products are issued as fma.rn.f32x2(v, w, z0), which is
+// bit for bit the separately rounded product v*w (adding -0.0 changes nothing, not even the sign of a zero), while
+// ptxas cannot see through the addend.  It has to be opaque: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into
+// FFMA2 even with --fmad false, which would break bit parity with the reference's unfused arithmetic.
+struct TapsSmall { float w[2 * kMaxFastR + 1]; float z0; };
+static inline TapsSmall make_taps_small(const float *taps, int n)
 {
-    constexpr int RP = (R + 3) & ~3;
-    constexpr int NW = 8 + 2 * RP;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_chunks) return;
-    long long base = t * 8;
-    int x0 = (int)(base % pitch);
-    float win[NW];
-#pragma unroll
-    for (int g = 0; g < NW / 4; g++) {
-        int x = x0 - RP + 4 * g;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (x >= 0 && x < pitch) v = __ldg(reinterpret_cast<const float4 *>(in + base - RP + 4 * g));
-        win[4 * g + 0] = v.x; win[4 * g + 1] = v.y; win[4 * g + 2] = v.z; win[4 * g + 3] = v.w;
-    }
-    float o[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        float acc = 0.0f + taps.w[0] * win[k + RP - R];      // fSum = 0; fSum += ... : a window of -0.0 voxels sums to +0.0
-#pragma unroll
-        for (int j = 1; j <= 2 * R; j++) acc = acc + taps.w[j] * win[k + j + RP - R];
-        o[k] = (x0 + k < X) ? acc : 0.0f;
-    }
-    float4 *dst = reinterpret_cast<float4 *>(out + base);
-    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    TapsSmall t;
+    memset(&t, 0, sizeof(t));
+    for (int j = 0; j < n && j < 2 * kMaxFastR + 1; j++) t.w[j] = taps[j];
+    t.z0 = -0.0f;
+    return t;
 }
+struct TapsAny { int n; float w[kMaxTaps]; };
 
 // Scalar x pass for any pitch / radius (slow path; identical results).
 __global__ void blur_x_generic_kernel(const float *__restrict__ in, float *__restrict__ out,
@@ -77,95 +52,6 @@ __global__ void blur_x_generic_kernel(const float *__restrict__ in, float *__res
         }
     }
     out[i] = acc;
-}
-
-// ---------------------------------------------------------------------------------------------
-// March pass (y or z).  Threads are laid along the contiguous direction (one column each) and walk
-// the blur axis through a segment [a0, a1).  Scatter form: the T = 2R+1 partial sums of the outputs
-// around the current input live in registers; each input value is loaded once, multiplied into all
-// T accumulators (T independent FMUL+FADD pairs -> ILP), and the oldest accumulator -- which has now
-// received its taps in the order j = 0..2R, the reference's left-to-right order -- is stored.
-// The loop is unrolled by T so accumulator indices are static (no register shuffling).
-// Columns are flattened so every lane is busy: column q -> (other = q / w_inner, inner = q % w_inner),
-// first element at other*other_stride + inner.
-//   y pass: w_inner = pitch,   n_cols = pitch*Z,  other_stride = pitch*Y, stride = pitch,   len = Y
-//   z pass: w_inner = pitch*Y, n_cols = pitch*Y,                          stride = pitch*Y, len = Z
-// DOG: also writes dog = prev - out (prev = the blur's input volume), i.e. fioMultSum(prev, out, -1).
-// ---------------------------------------------------------------------------------------------
-template <int R, bool DOG>
-__global__ void __launch_bounds__(128) blur_march_kernel(const float *__restrict__ in, float *__restrict__ out,
-                                                         const float *__restrict__ prev, float *__restrict__ dog,
-                                                         long long n_cols, long long w_inner, long long other_stride,
-                                                         long long stride, int len, int seg_len,
-                                                         const __grid_constant__ TapsSmall taps)
-{
-    constexpr int T = 2 * R + 1;
-    long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n_cols) return;
-    long long other = q / w_inner;
-    long long col = other * other_stride + (q - other * w_inner);
-    const int a0 = blockIdx.y * seg_len;
-    const int a1 = min(len, a0 + seg_len);
-    const int L = a1 - a0;
-    const int n_in = L + 2 * R;
-    float acc[T];
-#pragma unroll
-    for (int s = 0; s < T; s++) acc[s] = 0.0f;
-    // Rounds of T input steps.  The loads of round k+1 (and, for DOG, the T values of `prev` that round
-    // k+1 will subtract from) are issued before round k is computed.  A round whose inputs / outputs
-    // are all inside the volume / segment takes the predicate-free path (uniform per block).
-    float nxt[T], pnx[T];
-    const float *pin = in + col + (long long)(a0 - R) * stride;     // input of step u = 0
-    const float *ppv = prev + col + (long long)(a0 - 2 * R) * stride;   // prev of the output completed at step 0
-    float *pout = out + col + (long long)(a0 - 2 * R) * stride;
-    float *pdog = dog + col + (long long)(a0 - 2 * R) * stride;
-    auto load_round = [&](int ub) {
-        const int i0 = a0 - R + ub;
-        if (i0 >= 0 && i0 + T <= len && ub + T <= n_in) {
-#pragma unroll
-            for (int s = 0; s < T; s++) nxt[s] = __ldg(pin + (long long)s * stride);
-        } else {
-#pragma unroll
-            for (int s = 0; s < T; s++) {
-                int i = i0 + s;
-                nxt[s] = (i >= 0 && i < len && ub + s < n_in) ? __ldg(pin + (long long)s * stride) : 0.0f;
-            }
-        }
-        if (DOG) {
-            const int c0 = ub - 2 * R;          // output offsets c0 .. c0+T-1 relative to a0
-            if (c0 >= 0 && c0 + T <= L) {
-#pragma unroll
-                for (int s = 0; s < T; s++) pnx[s] = __ldg(ppv + (long long)s * stride);
-            } else {
-#pragma unroll
-                for (int s = 0; s < T; s++) pnx[s] = (c0 + s >= 0 && c0 + s < L) ? __ldg(ppv + (long long)s * stride) : 0.0f;
-            }
-            ppv += (long long)T * stride;
-        }
-        pin += (long long)T * stride;
-    };
-    load_round(0);
-    for (int ub = 0; ub < n_in; ub += T) {
-        float v[T], pv[T];
-#pragma unroll
-        for (int s = 0; s < T; s++) { v[s] = nxt[s]; if (DOG) pv[s] = pnx[s]; }
-        if (ub + T < n_in) load_round(ub + T);
-        const int c0 = ub - 2 * R;
-        const bool full = (c0 >= 0 && c0 + T <= L);
-#pragma unroll
-        for (int s = 0; s < T; s++) {
-            acc[s] = taps.w[0] * v[s];
-#pragma unroll
-            for (int j = 1; j <= 2 * R; j++) acc[(s - j + 2 * T) % T] = acc[(s - j + 2 * T) % T] + taps.w[j] * v[s];
-            if (full || (c0 + s >= 0 && c0 + s < L)) {
-                float g = acc[(s + 1) % T];
-                pout[(long long)s * stride] = g;
-                if (DOG) pdog[(long long)s * stride] = pv[s] - g;   // == prev + (-1)*g, fioMultSum
-            }
-        }
-        pout += (long long)T * stride;
-        if (DOG) pdog += (long long)T * stride;
-    }
 }
 
 // Generic march (any radius): gather form straight from global memory.
