@@ -38,7 +38,7 @@ EXPORTS = [
     "s3d_batch_create", "s3d_batch_destroy", "s3d_batch_last_error", "s3d_batch_extract", "s3d_batch_extract_device",
     "s3d_batch_launches_per_volume", "s3d_host_alloc", "s3d_host_free",
     "s3d_extract_typed", "s3d_extract_typed_async", "s3d_batch_extract_typed",
-    "s3d_write_features_bin", "s3d_read_features_text",
+    "s3d_write_features_bin", "s3d_read_features_text", "s3d_match", "s3d_match_device",
 ]
 
 # NIfTI datatype codes accepted by the typed entry points (reference featExtract.cpp:18-77)
@@ -134,6 +134,8 @@ def load_library():
     L.s3d_extract_typed.argtypes = [vp, vp, i, i, i, i, vp, C.POINTER(vp), C.POINTER(i)]
     L.s3d_extract_typed_async.argtypes = [vp, vp, i, i, i, i, vp]
     L.s3d_batch_extract_typed.argtypes = [vp, C.POINTER(vp), i, i, i, i, i, vp, C.POINTER(vp), C.POINTER(i)]
+    L.s3d_match.argtypes = [vp, vp, i, vp, i, i, vp, vp]
+    L.s3d_match_device.argtypes = [vp, vp, i, vp, i, i, vp, vp]
     L.s3d_host_alloc.argtypes = [C.c_size_t]
     L.s3d_host_alloc.restype = vp
     L.s3d_host_free.argtypes = [vp]
@@ -328,6 +330,17 @@ class Engine:
 
     def halve_size(self, d_in, X, d_out):
         self._resize(self.L.s3d_halve_size, "s3d_halve_size", d_in, X, d_out)
+
+    def match(self, feats_a, feats_b, k=2):
+        """Exact k nearest neighbours of every row of feats_a among feats_b on the reference's descriptor distance
+        (s3d_match): returns (idx [nA, k] int32, dist [nA, k] float32), neighbours in (distance, index) order."""
+        a = np.ascontiguousarray(feats_a, dtype=FEATURE_DTYPE)
+        b = np.ascontiguousarray(feats_b, dtype=FEATURE_DTYPE)
+        idx = np.empty((len(a), k), np.int32)
+        dist = np.empty((len(a), k), np.float32)
+        self._ck(self.L.s3d_match(self.ctx, a.ctypes.data_as(C.c_void_p), len(a), b.ctypes.data_as(C.c_void_p), len(b), k,
+                                  idx.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p)), "s3d_match")
+        return idx, dist
 
     def detect(self, d_finer, d_centre, X, cap=1 << 16):
         """Returns (minima, maxima) as CAND_DTYPE arrays in raster order."""

@@ -20,6 +20,7 @@
 #include "s3d_blur2.cuh"
 #include "s3d_blur4.cuh"
 #include "s3d_keypoint.cuh"
+#include "s3d_match.cuh"
 
 using namespace s3d;
 
@@ -1590,4 +1591,61 @@ extern "C" s3d_status s3d_read_features_text(const char *path, s3d_feature **out
     fclose(f);
     *out = h; *n_out = n;
     return S3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// descriptor matching: exact k nearest neighbours on Feature3DInfo::DistSqrPCs
+// ---------------------------------------------------------------------------------------------------
+extern "C" s3d_status s3d_match_device(s3d_ctx *ctx, const s3d_feature *d_a, int nA, const s3d_feature *d_b, int nB, int k,
+                                       int *d_idx, float *d_dist)
+{
+    if (!ctx) return S3D_ERR_INVALID;
+    if (nA < 0 || nB < 0 || k < 1 || k > kMatchMaxK || (nA > 0 && (!d_a || !d_idx || !d_dist)) || (nB > 0 && !d_b))
+        return fail(ctx, S3D_ERR_INVALID, "s3d_match: bad argument (1 <= k <= 16)");
+    if (nA == 0) return S3D_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    // database chunks: enough CTAs for ~2 per SM, chunks of at least 256 descriptors
+    const int qblocks = (nA + kMatchThreads - 1) / kMatchThreads;
+    int n_chunks = (2 * ctx->sm_count + qblocks - 1) / qblocks;
+    if (n_chunks > (nB + 255) / 256) n_chunks = (nB + 255) / 256;
+    if (n_chunks < 1) n_chunks = 1;
+    const int chunk = nB > 0 ? (nB + n_chunks - 1) / n_chunks : 1;
+    n_chunks = nB > 0 ? (nB + chunk - 1) / chunk : 1;
+    const int K = match_list_len(k);
+    float *part_d = nullptr; int *part_i = nullptr;
+    CK(cudaMallocAsync((void **)&part_d, sizeof(float) * (size_t)n_chunks * nA * K, st));
+    CK(cudaMallocAsync((void **)&part_i, sizeof(int) * (size_t)n_chunks * nA * K, st));
+    cudaError_t e = launch_match(st, d_a, nA, d_b, nB, k, n_chunks, chunk, part_d, part_i, d_idx, d_dist);
+    ctx->launches += 2;
+    cudaFreeAsync(part_d, st);
+    cudaFreeAsync(part_i, st);
+    CK(e);
+    return S3D_OK;
+}
+
+extern "C" s3d_status s3d_match(s3d_ctx *ctx, const s3d_feature *h_a, int nA, const s3d_feature *h_b, int nB, int k,
+                                int *h_idx, float *h_dist)
+{
+    if (!ctx) return S3D_ERR_INVALID;
+    if (nA < 0 || nB < 0 || k < 1 || k > kMatchMaxK || (nA > 0 && (!h_a || !h_idx || !h_dist)) || (nB > 0 && !h_b))
+        return fail(ctx, S3D_ERR_INVALID, "s3d_match: bad argument (1 <= k <= 16)");
+    if (nA == 0) return S3D_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    s3d_feature *d_a = nullptr, *d_b = nullptr; int *d_idx = nullptr; float *d_dist = nullptr;
+    CK(cudaMallocAsync((void **)&d_a, sizeof(s3d_feature) * (size_t)nA, st));
+    CK(cudaMallocAsync((void **)&d_b, sizeof(s3d_feature) * (size_t)(nB > 0 ? nB : 1), st));
+    CK(cudaMallocAsync((void **)&d_idx, sizeof(int) * (size_t)nA * k, st));
+    CK(cudaMallocAsync((void **)&d_dist, sizeof(float) * (size_t)nA * k, st));
+    CK(cudaMemcpyAsync(d_a, h_a, sizeof(s3d_feature) * (size_t)nA, cudaMemcpyHostToDevice, st));
+    if (nB > 0) CK(cudaMemcpyAsync(d_b, h_b, sizeof(s3d_feature) * (size_t)nB, cudaMemcpyHostToDevice, st));
+    s3d_status s = s3d_match_device(ctx, d_a, nA, d_b, nB, k, d_idx, d_dist);
+    if (s == S3D_OK) {
+        CK(cudaMemcpyAsync(h_idx, d_idx, sizeof(int) * (size_t)nA * k, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_dist, d_dist, sizeof(float) * (size_t)nA * k, cudaMemcpyDeviceToHost, st));
+    }
+    cudaFreeAsync(d_a, st); cudaFreeAsync(d_b, st); cudaFreeAsync(d_idx, st); cudaFreeAsync(d_dist, st);
+    CK(cudaStreamSynchronize(st));
+    return s;
 }

@@ -246,6 +246,20 @@ s3d_status s3d_write_features_bin(const char *path, const s3d_feature *feats, in
  * featMatchMultiple uses (R/featMatchMultiple/featMatchMultiple.cpp:596).  *out is malloc'ed (s3d_free). */
 s3d_status s3d_read_features_text(const char *path, s3d_feature **out, int *n_out);
 
+/* ---- descriptor matching -----------------------------------------------------------
+ * Exact k nearest neighbours (1 <= k <= 16) of every feature of set A among the features of set B on the reference's
+ * descriptor distance Feature3DInfo::DistSqrPCs (R/src_common/MultiScale.h:60-73: sequential float sum of squared
+ * differences over the 64 descriptor entries).  Replaces the FLANN kd-tree search of the matcher
+ * (R/feat_common/featMatchUtilities.cpp:1449-1455 build parameters, :1559 flann_build_index, :1612
+ * flann_find_nearest_neighbors_index with g_nn neighbours, sorted) by an exhaustive one: out_idx / out_dist are
+ * [nA][k], neighbours in (distance, index) order -- ties go to the lower index -- and the distances are bit for
+ * bit DistSqrPCs.  Entries beyond nB neighbours are index -1, distance +inf.
+ * s3d_match takes host arrays and synchronises; s3d_match_device takes device arrays and is stream-ordered. */
+s3d_status s3d_match(s3d_ctx *ctx, const s3d_feature *h_feats_a, int n_a, const s3d_feature *h_feats_b, int n_b, int k,
+                     int *h_out_idx, float *h_out_dist);
+s3d_status s3d_match_device(s3d_ctx *ctx, const s3d_feature *d_feats_a, int n_a, const s3d_feature *d_feats_b, int n_b, int k,
+                            int *d_out_idx, float *d_out_dist);
+
 #ifdef __cplusplus
 }
 #endif

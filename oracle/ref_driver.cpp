@@ -17,6 +17,9 @@
 #include <cstring>
 #include <cmath>
 #include <vector>
+#include <algorithm>
+#include <utility>
+#include <cmath>
 #include <iostream>
 #include <chrono>
 #include <unistd.h>
@@ -322,6 +325,26 @@ int ref_read_text(const char *path, ref_feature **feats)
         memcpy(o.pc, vec[i].m_pfPC, sizeof(o.pc));
     }
     return n;
+}
+
+/* Exhaustive k nearest neighbours on the reference's own distance function Feature3DInfo::DistSqrPCs
+ * (MultiScale.h:60-73), the metric the reference hands to FLANN (featMatchUtilities.cpp:1612).  Neighbours in
+ * (distance, index) order; a, b: ref_feature records. */
+int ref_knn(const ref_feature *a, int nA, const ref_feature *b, int nB, int k, int *idx, float *dist)
+{
+    std::vector<Feature3DInfo> fa((size_t)nA), fb((size_t)nB);
+    for (int i = 0; i < nA; i++) memcpy(fa[i].m_pfPC, a[i].pc, sizeof(float) * 64);
+    for (int i = 0; i < nB; i++) memcpy(fb[i].m_pfPC, b[i].pc, sizeof(float) * 64);
+    for (int q = 0; q < nA; q++) {
+        std::vector<std::pair<float, int> > all((size_t)nB);
+        for (int j = 0; j < nB; j++) all[j] = std::make_pair(fa[q].DistSqrPCs(fb[j], 64), j);
+        std::stable_sort(all.begin(), all.end(), [](const std::pair<float, int> &x, const std::pair<float, int> &y) { return x.first < y.first; });
+        for (int s = 0; s < k; s++) {
+            idx[(size_t)q * k + s] = s < nB ? all[s].second : -1;
+            dist[(size_t)q * k + s] = s < nB ? all[s].first : INFINITY;
+        }
+    }
+    return 0;
 }
 
 void ref_free(void *p) { free(p); }

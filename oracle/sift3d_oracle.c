@@ -1098,3 +1098,35 @@ int s3o_extract(const float *vol, int X, int Y, int Z, int double_mode, int desc
 }
 
 void s3o_free(void *p) { free(p); }
+
+/* ---------------------------------------------------------------------------------------------------
+ * Descriptor matching (section 8(f) N2).
+ * Feature3DInfo::DistSqrPCs (MultiScale.h:60-73): float fSumSqr = 0; for i: fDiff = a[i] - b[i]; fSumSqr += fDiff*fDiff.
+ * The reference feeds this metric to FLANN kd-trees (featMatchUtilities.cpp:1449-1455, 1559, 1612: approximate);
+ * the restatement is the exhaustive search FLANN approximates, neighbours sorted by (distance, index).
+ * --------------------------------------------------------------------------------------------------- */
+float s3o_dist_sqr_pcs(const float *a, const float *b)
+{
+    float fSumSqr = 0;
+    for (int i = 0; i < S3O_NPC; i++) {
+        float fDiff = a[i] - b[i];
+        fSumSqr += fDiff * fDiff;
+    }
+    return fSumSqr;
+}
+
+void s3o_knn(const float *a, int nA, const float *b, int nB, int k, int *idx, float *dist)
+{
+    for (int q = 0; q < nA; q++) {
+        int *bi = idx + (size_t)q * k;
+        float *bd = dist + (size_t)q * k;
+        for (int s = 0; s < k; s++) { bi[s] = -1; bd[s] = INFINITY; }
+        for (int j = 0; j < nB; j++) {
+            float d = s3o_dist_sqr_pcs(a + (size_t)q * S3O_NPC, b + (size_t)j * S3O_NPC);
+            if (!(d < bd[k - 1])) continue;          /* ties keep the lower index */
+            int s = k - 1;
+            while (s > 0 && d < bd[s - 1]) { bd[s] = bd[s - 1]; bi[s] = bi[s - 1]; s--; }
+            bd[s] = d; bi[s] = j;
+        }
+    }
+}

@@ -81,6 +81,12 @@ int  s3o_extract(const float *vol, int X, int Y, int Z, int double_mode, int des
                  s3o_keypoint **keypoints, int *n_keypoints);
 void s3o_free(void *p);
 
+/* Descriptor matching: exact k nearest neighbours of every descriptor of set A among
+ * set B on Feature3DInfo::DistSqrPCs (MultiScale.h:60-73), neighbours in (distance, index) order; entries beyond
+ * nB neighbours are index -1 / distance +inf.  a, b: [n][S3O_NPC] descriptors. */
+float s3o_dist_sqr_pcs(const float *a, const float *b);
+void s3o_knn(const float *a, int nA, const float *b, int nB, int k, int *idx, float *dist);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,15 @@ class Oracle:
         L.s3o_canonical_orientations.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.s3o_descriptor_sift.argtypes = [C.c_void_p, C.c_void_p]
         L.s3o_descriptor_brief.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.s3o_knn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+
+    def knn(self, pcs_a, pcs_b, k):
+        """Exhaustive kNN on DistSqrPCs; pcs_*: [n, 64] float32 descriptors."""
+        a = np.ascontiguousarray(pcs_a, np.float32); b = np.ascontiguousarray(pcs_b, np.float32)
+        idx = np.empty((len(a), k), np.int32); dist = np.empty((len(a), k), np.float32)
+        self.lib.s3o_knn(a.ctypes.data_as(C.c_void_p), len(a), b.ctypes.data_as(C.c_void_p), len(b), k,
+                         idx.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p))
+        return idx, dist
 
     # --- voxel stages (vol: numpy (Z, Y, X) float32) ---
     def taps(self, sigma):
@@ -187,6 +196,8 @@ class Reference:
             L.ref_write_bin.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_float]
             L.ref_read_text.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         L.ref_free.argtypes = [C.c_void_p]
+        if hasattr(L, "ref_knn"):
+            L.ref_knn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
 
     def taps(self, sigma):
         buf = np.zeros(129, np.float32)
@@ -256,6 +267,14 @@ class Reference:
             "prerank": _take(prerank, n * 64, np.float32, self.lib.ref_free).reshape(n, 64),
             "seconds": sec.value,
         }
+
+    def knn(self, feats_a, feats_b, k):
+        """Exhaustive kNN with the reference's own Feature3DInfo::DistSqrPCs; feats_*: Feature records."""
+        a = np.ascontiguousarray(feats_a); b = np.ascontiguousarray(feats_b)
+        idx = np.empty((len(a), k), np.int32); dist = np.empty((len(a), k), np.float32)
+        self.lib.ref_knn(a.ctypes.data_as(C.c_void_p), len(a), b.ctypes.data_as(C.c_void_p), len(b), k,
+                         idx.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p))
+        return idx, dist
 
     def write_text(self, feats, path, shape_xyz):
         f = np.ascontiguousarray(feats, dtype=FEATURE_DTYPE)

@@ -372,3 +372,28 @@ def test_negative_zero_voxels_bit_exact(pkg, oracle, monkeypatch, env):
         assert eng.extract(vol).tobytes() == oracle.extract(vol)["features"].tobytes()
     finally:
         eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [1, 2, 3, 8, 16])
+def test_match_knn_bit_exact(pkg, oracle, engine, k):
+    """s3d_match: exact k nearest neighbours on the reference's DistSqrPCs -- indices and
+    distances equal to the oracle's exhaustive search, ties to the lower index, short databases padded with -1/inf."""
+    rng = np.random.default_rng(11)
+    a = engine.extract(pkg.phantom.blob_phantom((64, 64, 64), 0, 60))
+    b = engine.extract(pkg.phantom.blob_phantom((64, 64, 64), 1, 60))
+    assert len(a) > 30 and len(b) > 30
+    nb = min(len(b), 100)
+    big = np.zeros(5000, pkg.FEATURE_DTYPE)
+    big["pc"] = np.stack([rng.permutation(64) for _ in range(5000)]).astype(np.float32)
+    big[100:100 + nb] = b[:nb]; big[4000:4000 + nb] = b[:nb]       # duplicated rows across database chunks: ties
+    free = np.zeros(300, pkg.FEATURE_DTYPE); free["pc"] = rng.normal(size=(300, 64)).astype(np.float32)
+    for fa, fb in [(a, b), (a, a), (b, big), (free, free[::-1].copy()), (a[:5], b[:3]), (a[:1], b[:1])]:
+        idx, dist = engine.match(fa, fb, k)
+        want_idx, want_dist = oracle.knn(fa["pc"], fb["pc"], k)
+        assert idx.tobytes() == want_idx.tobytes()
+        assert dist.tobytes() == want_dist.tobytes()
+    idx, dist = engine.match(a, a, 1)
+    assert (idx[:, 0] <= np.arange(len(a))).all() and (dist == 0).all()     # a row's nearest neighbour in its own set is itself (or an earlier twin)
+    with pytest.raises(pkg.S3DError):
+        engine.match(a, b, 17)

@@ -37,3 +37,19 @@ def test_extract(pkg, oracle, reference, double_mode, desc):
     assert len(b["features"]) > 0
     for k in ("features", "patches", "prerank"):
         assert same(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("k", [1, 2, 5])
+def test_knn_on_the_reference_distance(pkg, oracle, reference, k):
+    """Exhaustive kNN: the restatement of Feature3DInfo::DistSqrPCs + (distance, index) order against the same
+    search driven by the reference's own member function; rank descriptors (many ties) and free floats."""
+    rng = np.random.default_rng(5)
+    ranks = lambda n: np.stack([rng.permutation(64) for _ in range(n)]).astype(np.float32)
+    for pa, pb in [(ranks(40), ranks(90)), (rng.normal(size=(33, 64)).astype(np.float32), rng.normal(size=(70, 64)).astype(np.float32)),
+                   (ranks(7), ranks(3))]:
+        pb[1] = pb[0]                                      # exact duplicates in the database: ties go to the lower index
+        fa = np.zeros(len(pa), pkg.FEATURE_DTYPE); fa["pc"] = pa
+        fb = np.zeros(len(pb), pkg.FEATURE_DTYPE); fb["pc"] = pb
+        oi, od = oracle.knn(pa, pb, k)
+        ri, rd = reference.knn(fa, fb, k)
+        assert same(oi, ri) and same(od, rd)
