@@ -72,3 +72,25 @@ def test_cli_rejects_bad_arguments(tmp_path):
     assert r.returncode != 0 and b"unknown command line argument" in r.stdout
     r = subprocess.run([OURS, str(tmp_path / "missing.nii"), "o.key"], stdout=subprocess.PIPE)
     assert r.returncode != 0 and b"could not read input file" in r.stdout
+
+
+REF_S3D = os.path.join(ROOT, "oracle", "_ref", "featExtract_ref_s3d")
+
+
+@pytest.mark.parametrize("flags", [[], ["-2+"], ["-2-"]], ids=["plain", "double", "halve"])
+def test_stage_level_drop_in_under_the_reference_pipeline(pkg, engine, tmp_path, flags):
+    """INTEGRATION.md level B: the reference's OWN pipeline (unmodified src_common + featExtract.cpp) run with -d0,
+    its four CUDA launchers replaced by oracle/shim/s3d_launchers.cpp on top of s3d_blur3d / s3d_dog /
+    s3d_subsample2 / s3d_detect, must write the same bytes as the reference's CPU path."""
+    if not (os.path.exists(REF_S3D) and os.path.exists(REF)):
+        pytest.skip("reference binaries not built")
+    shape = (72, 64, 80) if flags == ["-2-"] else (40, 44, 36) if flags == ["-2+"] else (56, 60, 52)
+    vol = pkg.phantom.blob_phantom(shape, 31, 45)
+    nii = str(tmp_path / "in.nii")
+    pkg.phantom.write_nifti(nii, vol)
+    run(REF, flags + [nii, "cpu.key"], str(tmp_path))
+    run(REF_S3D, flags + ["-d0", nii, "s3d.key"], str(tmp_path))
+    a = open(tmp_path / "cpu.key", "rb").read()
+    b = open(tmp_path / "s3d.key", "rb").read()
+    assert a.count(b"\n") > 8, "reference produced no features"
+    assert a == b
