@@ -11,6 +11,6 @@ The directory name starts with a digit, so import it with
 """
 from . import phantom  # noqa: F401
 from .api import (  # noqa: F401
-    CAND_DTYPE, FEATURE_DTYPE, KEYPOINT_DTYPE, Batch, Engine, Params, S3DError, build_library, gaussian_taps,
+    CAND_DTYPE, FEATURE_DTYPE, KEYPOINT_DTYPE, Batch, Engine, Multi, Params, S3DError, build_library, gaussian_taps,
     library_path, load_library,
 )

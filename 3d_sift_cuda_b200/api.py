@@ -39,6 +39,8 @@ EXPORTS = [
     "s3d_batch_launches_per_volume", "s3d_host_alloc", "s3d_host_free",
     "s3d_extract_typed", "s3d_extract_typed_async", "s3d_batch_extract_typed",
     "s3d_write_features_bin", "s3d_read_features_text", "s3d_match", "s3d_match_device",
+    "s3d_multi_create", "s3d_multi_destroy", "s3d_multi_last_error", "s3d_multi_gpu_count", "s3d_multi_batch_extract",
+    "s3d_multi_extract_slab",
 ]
 
 # NIfTI datatype codes accepted by the typed entry points (reference featExtract.cpp:18-77)
@@ -136,6 +138,14 @@ def load_library():
     L.s3d_batch_extract_typed.argtypes = [vp, C.POINTER(vp), i, i, i, i, i, vp, C.POINTER(vp), C.POINTER(i)]
     L.s3d_match.argtypes = [vp, vp, i, vp, i, i, vp, vp]
     L.s3d_match_device.argtypes = [vp, vp, i, vp, i, i, vp, vp]
+    L.s3d_multi_create.argtypes = [i, vp, i, C.POINTER(vp)]
+    L.s3d_multi_destroy.argtypes = [vp]
+    L.s3d_multi_destroy.restype = None
+    L.s3d_multi_last_error.argtypes = [vp]
+    L.s3d_multi_last_error.restype = C.c_char_p
+    L.s3d_multi_gpu_count.argtypes = [vp]
+    L.s3d_multi_batch_extract.argtypes = [vp, C.POINTER(vp), i, i, i, i, vp, C.POINTER(vp), C.POINTER(i)]
+    L.s3d_multi_extract_slab.argtypes = [vp, vp, i, i, i, vp, C.POINTER(vp), C.POINTER(i)]
     L.s3d_host_alloc.argtypes = [C.c_size_t]
     L.s3d_host_alloc.restype = vp
     L.s3d_host_free.argtypes = [vp]
@@ -460,6 +470,61 @@ class Batch:
 
     def launches_per_volume(self):
         return self.L.s3d_batch_launches_per_volume(self.b)
+
+
+class Multi:
+    """Several GPUs of one box behind one handle (s3d_multi_*): batch sharding and z-slab decomposition from a
+    single process, one host thread per GPU inside the library.  ``devices`` may list a device more than once."""
+
+    def __init__(self, devices, contexts_per_gpu=4):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        st = self.L.s3d_multi_create(len(devices), devs, contexts_per_gpu, C.byref(self.h))
+        if st != 0:
+            msg = self.L.s3d_multi_last_error(self.h).decode() if self.h else ""
+            raise S3DError("s3d_multi_create failed (status %d): %s" % (st, msg))
+
+    def close(self):
+        if self.h:
+            self.L.s3d_multi_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st, what):
+        if st != 0:
+            raise S3DError("%s failed (status %d): %s" % (what, st, self.L.s3d_multi_last_error(self.h).decode()))
+
+    def extract_slab(self, volume, params=None):
+        """One volume split into z slabs over the handle's GPUs; rows in the reference's order."""
+        p = (params or Params()).c
+        v = np.ascontiguousarray(volume, np.float32)
+        Z, Y, X = v.shape
+        out, n = C.c_void_p(), C.c_int()
+        self._ck(self.L.s3d_multi_extract_slab(self.h, v.ctypes.data_as(C.c_void_p), X, Y, Z, C.byref(p), C.byref(out), C.byref(n)),
+                 "s3d_multi_extract_slab")
+        return _copy_out(out, n.value, FEATURE_DTYPE, self.L.s3d_free)
+
+    def batch_extract(self, volumes, params=None):
+        """Volume i on GPU i mod n; list of row arrays in input order."""
+        p = (params or Params()).c
+        vols = [np.ascontiguousarray(v, np.float32) for v in volumes]
+        if not vols:
+            return []
+        Z, Y, X = vols[0].shape
+        assert all(v.shape == vols[0].shape for v in vols), "volumes of one batch share a shape"
+        ptrs = (C.c_void_p * len(vols))(*[v.ctypes.data_as(C.c_void_p) for v in vols])
+        rows = (C.c_void_p * len(vols))()
+        n_rows = (C.c_int * len(vols))()
+        st = self.L.s3d_multi_batch_extract(self.h, ptrs, len(vols), X, Y, Z, C.byref(p), rows, n_rows)
+        out = [_copy_out(C.c_void_p(rows[k]), n_rows[k], FEATURE_DTYPE, self.L.s3d_free) if rows[k] else None for k in range(len(vols))]
+        self._ck(st, "s3d_multi_batch_extract")
+        return out
 
 
 def write_features_bin(path, feats, eig_thres=-1.0):

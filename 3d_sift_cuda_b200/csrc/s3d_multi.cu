@@ -233,74 +233,75 @@ static void slab_thread(SlabShared &S, int r)
     long long vox = (long long)S.X0 * S.Y0 * (S.Z0 / n + 2 * halo);
     int kp_cap = S.prm.max_keypoints > 0 ? S.prm.max_keypoints : (int)std::min<long long>(1 << 20, std::max<long long>(16384, vox / 2048));
     std::vector<void *> to_free;
-    auto run = [&]() {
-        for (int o = 0; o < K; o++) {
-            const int own0 = S.bounds[r] >> o, own1 = (r + 1 < n) ? (S.bounds[r + 1] >> o) : Zo;
-            float *d_buf = nullptr; int z_off = 0, nz = 0;
-            const size_t plane = (size_t)Xo * Yo;
-            if (!S.failed()) {
-                if (o == 0) {
-                    const int hi_ = halo + kInitBlurRadius;
-                    const int lo = std::max(0, own0 - hi_), hi = std::min(Zo, own1 + hi_);
-                    z_off = lo; nz = hi - lo;
-                    const size_t in_plane = (size_t)S.X * S.Y;
-                    if (S.prm.double_mode == 0) {
-                        SLAB_CU(cudaMallocAsync((void **)&d_buf, sizeof(float) * plane * nz, st));
-                        SLAB_CU(cudaMemcpyAsync(d_buf, S.vol + in_plane * lo, sizeof(float) * plane * nz, cudaMemcpyHostToDevice, st));
-                        to_free.push_back(d_buf);
-                    } else if (S.prm.double_mode == 1) {      // fioDoubleSize: doubled plane 2z+dz needs original planes z, z+1 (clamped)
-                        const int o0 = lo / 2, o1 = std::min(S.Z, (hi - 1) / 2 + 2);
-                        float *d_src = nullptr, *d_dst = nullptr;
-                        SLAB_CU(cudaMallocAsync((void **)&d_src, sizeof(float) * in_plane * (o1 - o0), st));
-                        SLAB_CU(cudaMallocAsync((void **)&d_dst, sizeof(float) * plane * 2 * (o1 - o0), st));
-                        SLAB_CU(cudaMemcpyAsync(d_src, S.vol + in_plane * o0, sizeof(float) * in_plane * (o1 - o0), cudaMemcpyHostToDevice, st));
-                        SLAB_S3(s3d_double_size(ctx, d_src, S.X, S.Y, o1 - o0, S.X, d_dst, 2 * S.X));
-                        to_free.push_back(d_src); to_free.push_back(d_dst);
-                        d_buf = d_dst + plane * (lo - 2 * o0);
-                    } else {                                   // fioSubSample2DCenterPixel
-                        const int o0 = 2 * lo, o1 = 2 * hi;
-                        float *d_src = nullptr;
-                        SLAB_CU(cudaMallocAsync((void **)&d_src, sizeof(float) * in_plane * (o1 - o0), st));
-                        SLAB_CU(cudaMallocAsync((void **)&d_buf, sizeof(float) * plane * nz, st));
-                        SLAB_CU(cudaMemcpyAsync(d_src, S.vol + in_plane * o0, sizeof(float) * in_plane * (o1 - o0), cudaMemcpyHostToDevice, st));
-                        SLAB_S3(s3d_halve_size(ctx, d_src, S.X, S.Y, o1 - o0, S.X, d_buf, Xo));
-                        to_free.push_back(d_src); to_free.push_back(d_buf);
-                    }
-                } else {
-                    const int lo_h = r > 0 ? halo : 0, hi_h = (r + 1 < n) ? halo : 0;
-                    z_off = own0 - lo_h; nz = lo_h + (own1 - own0) + hi_h;
+    // Every octave has exactly two barrier waits per thread, reached whether or not a phase failed (a failing phase
+    // records the error and returns; the other threads see S.failed() and skip their phases too).
+    for (int o = 0; o < K; o++) {
+        const int own0 = S.bounds[r] >> o, own1 = (r + 1 < n) ? (S.bounds[r + 1] >> o) : Zo;
+        float *d_buf = nullptr; int z_off = 0, nz = 0;
+        const size_t plane = (size_t)Xo * Yo;
+        auto assemble = [&]() {       // [halo | own | halo] of this octave's input
+            if (o == 0) {
+                const int hi_ = halo + kInitBlurRadius;
+                const int lo = std::max(0, own0 - hi_), hi = std::min(Zo, own1 + hi_);
+                z_off = lo; nz = hi - lo;
+                const size_t in_plane = (size_t)S.X * S.Y;
+                if (S.prm.double_mode == 0) {
                     SLAB_CU(cudaMallocAsync((void **)&d_buf, sizeof(float) * plane * nz, st));
                     to_free.push_back(d_buf);
-                    if (lo_h) SLAB_CU(cudaMemcpyPeerAsync(d_buf, dev, S.own_g0[r - 1] + plane * (S.own_n[r - 1] - halo), S.m->dev[r - 1], sizeof(float) * plane * halo, st));
-                    SLAB_CU(cudaMemcpyAsync(d_buf + plane * lo_h, S.own_g0[r], sizeof(float) * plane * (own1 - own0), cudaMemcpyDeviceToDevice, st));
-                    if (hi_h) SLAB_CU(cudaMemcpyPeerAsync(d_buf + plane * (lo_h + own1 - own0), dev, S.own_g0[r + 1], S.m->dev[r + 1], sizeof(float) * plane * halo, st));
-                    SLAB_CU(cudaStreamSynchronize(st));
+                    SLAB_CU(cudaMemcpyAsync(d_buf, S.vol + in_plane * lo, sizeof(float) * plane * nz, cudaMemcpyHostToDevice, st));
+                } else if (S.prm.double_mode == 1) {      // fioDoubleSize: doubled plane 2z+dz needs original planes z, z+1 (clamped)
+                    const int o0 = lo / 2, o1 = std::min(S.Z, (hi - 1) / 2 + 2);
+                    float *d_src = nullptr, *d_dst = nullptr;
+                    SLAB_CU(cudaMallocAsync((void **)&d_src, sizeof(float) * in_plane * (o1 - o0), st));
+                    to_free.push_back(d_src);
+                    SLAB_CU(cudaMallocAsync((void **)&d_dst, sizeof(float) * plane * 2 * (o1 - o0), st));
+                    to_free.push_back(d_dst);
+                    SLAB_CU(cudaMemcpyAsync(d_src, S.vol + in_plane * o0, sizeof(float) * in_plane * (o1 - o0), cudaMemcpyHostToDevice, st));
+                    SLAB_S3(s3d_double_size(ctx, d_src, S.X, S.Y, o1 - o0, S.X, d_dst, 2 * S.X));
+                    d_buf = d_dst + plane * (lo - 2 * o0);
+                } else {                                   // fioSubSample2DCenterPixel
+                    const int o0 = 2 * lo, o1 = 2 * hi;
+                    float *d_src = nullptr;
+                    SLAB_CU(cudaMallocAsync((void **)&d_src, sizeof(float) * in_plane * (o1 - o0), st));
+                    to_free.push_back(d_src);
+                    SLAB_CU(cudaMallocAsync((void **)&d_buf, sizeof(float) * plane * nz, st));
+                    to_free.push_back(d_buf);
+                    SLAB_CU(cudaMemcpyAsync(d_src, S.vol + in_plane * o0, sizeof(float) * in_plane * (o1 - o0), cudaMemcpyHostToDevice, st));
+                    SLAB_S3(s3d_halve_size(ctx, d_src, S.X, S.Y, o1 - o0, S.X, d_buf, Xo));
                 }
-            }
-            S.bar.wait();            // every slab holds its halos: the previous octave's own parts can go
-            if (o > 0 && S.own_g0[r]) { cudaFreeAsync(S.own_g0[r], st); S.own_g0[r] = nullptr; }
-            if (!S.failed()) slab_run_octave(S, r, o, ctx, d_buf, Xo, Yo, nz, z_off, Zo, own0, own1, kp_cap);
-            // own part of the next octave's level 0: 2x2x2 mean of the own planes of level 3
-            if (!S.failed()) {
-                const int n_next = (own1 >> 1) - (own0 >> 1);
-                float *d_g3 = nullptr, *d_next = nullptr;
-                SLAB_CU(cudaMallocAsync((void **)&d_g3, sizeof(float) * plane * 2 * n_next, st));
-                SLAB_CU(cudaMallocAsync((void **)&d_next, sizeof(float) * (size_t)(Xo / 2) * (Yo / 2) * n_next, st));
-                SLAB_S3(s3d_copy_level_device(ctx, 0, 0, 3, own0 - z_off, own0 - z_off + 2 * n_next, d_g3));
-                SLAB_S3(s3d_subsample2(ctx, d_g3, Xo, Yo, 2 * n_next, Xo, d_next, Xo / 2));
-                SLAB_CU(cudaFreeAsync(d_g3, st));
-                for (void *p : to_free) cudaFreeAsync(p, st);
-                to_free.clear();
+            } else {
+                const int lo_h = r > 0 ? halo : 0, hi_h = (r + 1 < n) ? halo : 0;
+                z_off = own0 - lo_h; nz = lo_h + (own1 - own0) + hi_h;
+                SLAB_CU(cudaMallocAsync((void **)&d_buf, sizeof(float) * plane * nz, st));
+                to_free.push_back(d_buf);
+                if (lo_h) SLAB_CU(cudaMemcpyPeerAsync(d_buf, dev, S.own_g0[r - 1] + plane * (S.own_n[r - 1] - halo), S.m->dev[r - 1], sizeof(float) * plane * halo, st));
+                SLAB_CU(cudaMemcpyAsync(d_buf + plane * lo_h, S.own_g0[r], sizeof(float) * plane * (own1 - own0), cudaMemcpyDeviceToDevice, st));
+                if (hi_h) SLAB_CU(cudaMemcpyPeerAsync(d_buf + plane * (lo_h + own1 - own0), dev, S.own_g0[r + 1], S.m->dev[r + 1], sizeof(float) * plane * halo, st));
                 SLAB_CU(cudaStreamSynchronize(st));
-                S.own_g0[r] = d_next; S.own_n[r] = n_next;
             }
-            S.bar.wait();            // every slab's next level 0 is complete
-            Xo /= 2; Yo /= 2; Zo /= 2;
-        }
-    };
-    run();
-    // a failing slab leaves run() early: keep the barrier counts in step
-    // (every octave has exactly two waits; count what this thread still owes)
+        };
+        auto next_level0 = [&]() {    // own part of the next octave's level 0: 2x2x2 mean of the own planes of level 3
+            const int n_next = (own1 >> 1) - (own0 >> 1);
+            float *d_g3 = nullptr, *d_next = nullptr;
+            SLAB_CU(cudaMallocAsync((void **)&d_g3, sizeof(float) * plane * 2 * n_next, st));
+            to_free.push_back(d_g3);
+            SLAB_CU(cudaMallocAsync((void **)&d_next, sizeof(float) * (size_t)(Xo / 2) * (Yo / 2) * n_next, st));
+            S.own_g0[r] = d_next; S.own_n[r] = n_next;
+            SLAB_S3(s3d_copy_level_device(ctx, 0, 0, 3, own0 - z_off, own0 - z_off + 2 * n_next, d_g3));
+            SLAB_S3(s3d_subsample2(ctx, d_g3, Xo, Yo, 2 * n_next, Xo, d_next, Xo / 2));
+            SLAB_CU(cudaStreamSynchronize(st));
+        };
+        if (!S.failed()) assemble();
+        S.bar.wait();            // every slab holds its halos: the previous octave's own parts can go
+        if (o > 0 && S.own_g0[r]) { cudaFreeAsync(S.own_g0[r], st); S.own_g0[r] = nullptr; }
+        if (!S.failed()) slab_run_octave(S, r, o, ctx, d_buf, Xo, Yo, nz, z_off, Zo, own0, own1, kp_cap);
+        if (!S.failed()) next_level0();
+        for (void *p : to_free) cudaFreeAsync(p, st);
+        to_free.clear();
+        S.bar.wait();            // every slab's next level 0 is complete
+        Xo /= 2; Yo /= 2; Zo /= 2;
+    }
+    cudaStreamSynchronize(st);
 }
 
 } // namespace
@@ -333,7 +334,7 @@ extern "C" s3d_status s3d_multi_extract_slab(s3d_multi *m, const float *h_volume
     S.cnt.assign(n, std::vector<std::vector<long long>>(K, std::vector<long long>(6, 0)));
     {
         std::vector<std::thread> th;
-        for (int r = 0; r < n; r++) th.emplace_back([&S, r] { slab_thread_entry:; slab_thread(S, r); });
+        for (int r = 0; r < n; r++) th.emplace_back([&S, r] { slab_thread(S, r); });
         for (auto &t : th) t.join();
     }
     auto cleanup = [&]() {

@@ -42,15 +42,14 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
 
 static PFN_encodeTiled get_encode_tiled()
 {
-    static PFN_encodeTiled fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // resolved once; the initialisation of a function-local static is thread safe (contexts live on several host threads)
+    static PFN_encodeTiled fn = []() -> PFN_encodeTiled {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = (PFN_encodeTiled)p;
-    }
+            return (PFN_encodeTiled)p;
+        return nullptr;
+    }();
     return fn;
 }
 

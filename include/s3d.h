@@ -246,6 +246,33 @@ s3d_status s3d_write_features_bin(const char *path, const s3d_feature *feats, in
  * featMatchMultiple uses (R/featMatchMultiple/featMatchMultiple.cpp:596).  *out is malloc'ed (s3d_free). */
 s3d_status s3d_read_features_text(const char *path, s3d_feature **out, int *n_out);
 
+/* ---- multi-GPU (SURVEY.md section 8(b) last row, 8(e); BASELINE.json configs 4 and 5) ---------------------------
+ * One host thread per GPU above the single-GPU entry points, for hosts that are one process -- like the
+ * reference's featExtract (R/featExtract/featExtract.cpp:273-585, one volume, one device chosen by
+ * check_best_device :237-263).  The reference has no multi-GPU mode and its launchers overflow at 1024^3
+ * (R/cuda_common/SIFT_cuda_Tools.cu:187 computes byte counts in int), so there is nothing to match but the rows.
+ *   s3d_multi_create        : devices[r] = CUDA device of GPU r (NULL = 0..n_gpus-1; a device may be listed twice,
+ *                             which runs two slabs / shards on it); contexts_per_gpu is for batch mode (0 = 4).
+ *   s3d_multi_batch_extract : volume i runs on GPU i mod n through an s3d_batch; no communication; rows[i]
+ *                             (malloc'ed, s3d_free) and n_rows[i] in input order -- identical to s3d_extract.
+ *   s3d_multi_extract_slab  : ONE volume, split into contiguous z slabs (planes aligned to 2^K).  Per octave every
+ *                             GPU runs [halo | own | halo] (48 planes of halo), subsamples its own part of level 3
+ *                             and pulls the next octave's halos from its two neighbours with cudaMemcpyPeerAsync
+ *                             (NVLink P2P); octaves too thin to split collapse onto GPU 0; rows are merged by
+ *                             offsets computed from per-(octave, level, min/max) counts.  *out is malloc'ed
+ *                             (s3d_free), rows in the reference's order, bit-identical to the whole-volume run.
+ *                             The octave-run / slab fields of params must be zero; max_keypoints = 0 sizes the
+ *                             capacity from the slab and grows it on S3D_ERR_CAPACITY. */
+typedef struct s3d_multi s3d_multi;
+s3d_status s3d_multi_create(int n_gpus, const int *devices, int contexts_per_gpu, s3d_multi **multi);
+void s3d_multi_destroy(s3d_multi *multi);
+const char *s3d_multi_last_error(const s3d_multi *multi);
+int s3d_multi_gpu_count(const s3d_multi *multi);
+s3d_status s3d_multi_batch_extract(s3d_multi *multi, const float *const *h_volumes, int n_volumes, int X, int Y, int Z,
+                                   const s3d_params *params, s3d_feature **rows, int *n_rows);
+s3d_status s3d_multi_extract_slab(s3d_multi *multi, const float *h_volume, int X, int Y, int Z, const s3d_params *params,
+                                  s3d_feature **out, int *n_out);
+
 /* ---- descriptor matching -----------------------------------------------------------
  * Exact k nearest neighbours (1 <= k <= 16) of every feature of set A among the features of set B on the reference's
  * descriptor distance Feature3DInfo::DistSqrPCs (R/src_common/MultiScale.h:60-73: sequential float sum of squared

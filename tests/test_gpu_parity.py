@@ -397,3 +397,58 @@ def test_match_knn_bit_exact(pkg, oracle, engine, k):
     assert (idx[:, 0] <= np.arange(len(a))).all() and (dist == 0).all()     # a row's nearest neighbour in its own set is itself (or an earlier twin)
     with pytest.raises(pkg.S3DError):
         engine.match(a, b, 17)
+
+
+@pytest.mark.parametrize("double_mode,nslabs,shape", [(0, 2, (64, 56, 230)), (0, 3, (48, 52, 330)), (1, 2, (40, 36, 120)), (-1, 2, (80, 72, 420))])
+def test_multi_slab_cabi_bit_exact(pkg, engine, double_mode, nslabs, shape):
+    """s3d_multi_extract_slab (C-ABI, one host thread per slab, halos by peer copies): with every slab on the one
+    GPU of the test box the whole multi-rank path runs -- slab plan, halo exchange between octaves, collapse onto
+    slab 0, offset-based row merge -- and must reproduce the whole-volume rows byte for byte."""
+    vol = pkg.phantom.blob_phantom(shape, 17, 160)
+    whole = engine.extract(vol, pkg.Params(double_mode=double_mode))
+    assert len(whole) > 50
+    m = pkg.Multi([0] * nslabs)
+    try:
+        slab = m.extract_slab(vol, pkg.Params(double_mode=double_mode))
+        assert slab.tobytes() == whole.tobytes()
+        again = m.extract_slab(vol, pkg.Params(double_mode=double_mode, descriptor=2))      # resident plans are reused
+        assert again.tobytes() == engine.extract(vol, pkg.Params(double_mode=double_mode, descriptor=2)).tobytes()
+    finally:
+        m.close()
+
+
+def test_multi_slab_against_the_oracle(pkg, oracle):
+    """Config 5 in small: a -2+ volume through the slab decomposition (2 slabs) against the ORACLE, not the engine."""
+    vol = pkg.phantom.blob_phantom((64, 64, 128), 3, 200)
+    want = oracle.extract(vol, 1, 0)["features"]
+    m = pkg.Multi([0, 0])
+    try:
+        got = m.extract_slab(vol, pkg.Params(double_mode=1))
+    finally:
+        m.close()
+    assert len(want) > 100
+    assert got.tobytes() == want.tobytes()
+
+
+def test_multi_slab_capacity_grows(pkg, engine):
+    """max_keypoints = 0 sizes the capacity from the slab and a too-small explicit capacity is grown, not fatal."""
+    vol = pkg.phantom.blob_phantom((64, 56, 230), 17, 160)
+    whole = engine.extract(vol)
+    m = pkg.Multi([0, 0])
+    try:
+        assert m.extract_slab(vol, pkg.Params(max_keypoints=8)).tobytes() == whole.tobytes()
+    finally:
+        m.close()
+
+
+def test_multi_batch_matches_single(pkg, engine):
+    """s3d_multi_batch_extract: volume i on GPU i mod n (here two shards on one GPU), rows in input order."""
+    vols = [pkg.phantom.blob_phantom((64, 56, 48), s, 40) for s in range(7)]
+    m = pkg.Multi([0, 0], contexts_per_gpu=2)
+    try:
+        rows = m.batch_extract(vols)
+    finally:
+        m.close()
+    assert len(rows) == 7
+    for v, r in zip(vols, rows):
+        assert r.tobytes() == engine.extract(v).tobytes()
