@@ -6,8 +6,13 @@
 //                processing (reference :327-339, 436-473, 507-538)
 //     -2+ / -2-  double / halve the input image (reference :368-388)
 //     -d[0-9]    CUDA device (reference :312-325; here every run is a GPU run, default device 0)
+//     -dA,B,...  several devices: one volume is split into z slabs over them (s3d_multi_extract_slab), a list of
+//                volumes (-l) is sharded over them (s3d_multi_batch_extract)
+//     -l <file>  batch mode: every line of <file> is "<input image> <output features>"
 //     -b -br -bn BRIEF / RRIEF / NRRIEF descriptor instead of SIFT-Rank (README; dead code in the reference)
 //     -r X Y Z   input is raw IEEE float32, little endian, x fastest, of these dimensions
+//     -r         ... dimensions guessed from the signal (the idea of the reference's unused fioReadRaw,
+//                R/src_common/FeatureIO.cpp:3006-3227, made deterministic)
 //
 // Kept host code: argument parsing, NIfTI/raw loading, isotropic resampling, the world-coordinate
 // transform and the text feature file.  Output is byte-identical to the reference's CPU path.
@@ -34,9 +39,10 @@ static int print_options()
     printf("  -w         : output feature geometry in world coordinates, NIFTI qto_xyz matrix (default is voxel units).\n");
     printf("  -2+        : double input image size.\n");
     printf("  -2-        : halve input image size.\n");
-    printf("  -d[0-9]    : set device id to be used.\n");
+    printf("  -d[0-9]    : set device id to be used; -dA,B,... : several devices (z slabs of one volume, shards of a list).\n");
+    printf("  -l <file>  : batch mode, one \"<input image> <output features>\" pair per line of <file>.\n");
     printf("  -b -br -bn : BRIEF / RRIEF / NRRIEF descriptor (default: gradient orientation histogram).\n");
-    printf("  -r X Y Z   : raw float32 input of the given dimensions.\n");
+    printf("  -r X Y Z   : raw float32 input of the given dimensions (-r alone: guess them).\n");
     return 0;
 }
 
@@ -76,90 +82,70 @@ static void mult3f(const float a[9], const float b[9], float o[9])
         }
 }
 
-// _fioDetermineInterpCoord / fioGetPixelTrilinearInterp (reference FeatureIO.cpp:757-850), host copy used
-// only for the isotropic resampling of anisotropic inputs (reference featExtract.cpp:118-204).
-static void interp_coord(float fX, float fMaxX, int &iX, float &fW)
+// Dimensions of a raw float32 volume from the signal itself: a row length X makes s[i] and s[i + X] neighbours
+// (small mean absolute difference), likewise a plane size X*Y.  Deterministic restatement of the idea behind the
+// reference's get_image_dimensions (R/src_common/FeatureIO.cpp:3006-3175, random templates, never called).
+static bool guess_raw_dims(const float *s, size_t n, int &X, int &Y, int &Z)
 {
-    if (fX < 0.5f) { iX = 0; fW = 1.0f; }
-    else if (fX >= fMaxX - 0.5f) { iX = (int)(fMaxX - 2); fW = 0.0f; }
-    else { float mh = fX - 0.5f; iX = (int)floor(mh); fW = 1.0f - (mh - ((float)iX)); }
-}
-static float trilinear(const float *img, int X, int Y, int Z, float x, float y, float z)
-{
-    int iX, iY, iZ; float wx, wy, wz;
-    interp_coord(x, (float)X, iX, wx); interp_coord(y, (float)Y, iY, wy); interp_coord(z, (float)Z, iZ, wz);
-    const float *p = img + ((size_t)iZ * Y + iY) * X + iX;
-    size_t pl = (size_t)X * Y;
-    float fn00 = wx * p[0] + (1.0f - wx) * p[1];
-    float fn01 = wx * p[pl] + (1.0f - wx) * p[pl + 1];
-    float fn10 = wx * p[X] + (1.0f - wx) * p[X + 1];
-    float fn11 = wx * p[pl + X] + (1.0f - wx) * p[pl + X + 1];
-    float fnn0 = wy * fn00 + (1.0f - wy) * fn10;
-    float fnn1 = wy * fn01 + (1.0f - wy) * fn11;
-    return wz * fnn0 + (1.0f - wz) * fnn1;
+    auto cost = [&](size_t lag) {
+        const size_t samples = 40000, span = n - lag;
+        const size_t step = span / samples > 0 ? span / samples : 1;
+        double acc = 0; size_t cnt = 0;
+        for (size_t i = 0; i < span; i += step) { acc += fabs((double)s[i] - (double)s[i + lag]); cnt++; }
+        return cnt ? acc / (double)cnt : 1e300;
+    };
+    size_t bestX = 0; double bc = 1e300;
+    for (size_t L = 8; L <= 8192 && L * 4 <= n; L++)
+        if (n % L == 0) { double c = cost(L); if (c < bc) { bc = c; bestX = L; } }
+    if (!bestX) return false;
+    const size_t rows = n / bestX;
+    size_t bestY = 0; bc = 1e300;
+    for (size_t k = 2; k <= 8192 && k * 2 <= rows; k++)
+        if (rows % k == 0) { double c = cost(bestX * k); if (c < bc) { bc = c; bestY = k; } }
+    if (!bestY) return false;
+    X = (int)bestX; Y = (int)bestY; Z = (int)(rows / bestY);
+    return Z >= 2;
 }
 
-int main(int argc, char **argv)
-{
-    if (argc < 3) { print_options(); return -1; }
-    int device = 0, iArg = 1, bDouble = 0, bWorld = 0, bIso = 0, descriptor = S3D_DESC_SIFT;
+struct Options {
+    std::vector<int> devices;
+    int bDouble = 0, bWorld = 0, bIso = 0, descriptor = S3D_DESC_SIFT;
     int rawX = 0, rawY = 0, rawZ = 0;
+    bool raw = false;
     float fEigThres = 140;
-    while (iArg < argc && argv[iArg][0] == '-') {
-        switch (argv[iArg][1]) {
-        case '2':
-            bDouble = 1;
-            if (argv[iArg][2] == '-') bDouble = -1;
-            iArg++;
-            break;
-        case 'd': {
-            int n = s3d_device_count();
-            int d = argv[iArg][2] - '0';
-            if (argv[iArg][2] == 0) d = 0;
-            if (d < 0 || d > 9 || d >= (n > 0 ? n : 1)) {
-                printf("Error: unknown device: %d\n", d);
-                print_options();
-                return -1;
-            }
-            device = d;
-            iArg++;
-            break;
-        }
-        case 'w': case 'W':
-            bWorld = 1; bIso = 1;
-            if (argv[iArg][2] == 's' || argv[iArg][2] == 'S') bWorld = 2;
-            iArg++;
-            break;
-        case 'b':
-            descriptor = argv[iArg][2] == 'r' ? S3D_DESC_RRIEF : argv[iArg][2] == 'n' ? S3D_DESC_NRRIEF : S3D_DESC_BRIEF;
-            iArg++;
-            break;
-        case 'r':
-            if (iArg + 3 >= argc) { print_options(); return -1; }
-            rawX = atoi(argv[iArg + 1]); rawY = atoi(argv[iArg + 2]); rawZ = atoi(argv[iArg + 3]);
-            iArg += 4;
-            break;
-        default:
-            printf("Error: unknown command line argument: %s\n", argv[iArg]);
-            print_options();
-            return -1;
-        }
-    }
-    if (argc - iArg < 2) { print_options(); return -1; }
-    const char *inPath = argv[iArg], *outPath = argv[iArg + 1];
-    printf("Extracting features: %s\n", inPath);
+};
 
+struct Job {
+    std::string in, out;
     niftimin::Image im;
-    if (rawX > 0) {
-        if (rawY <= 0 || rawZ <= 0) { printf("Error: bad raw dimensions\n"); return -1; }
-        im.nx = rawX; im.ny = rawY; im.nz = rawZ;
-        im.data.resize((size_t)rawX * rawY * rawZ);
+    std::vector<float> vol;          // float volume at extraction input resolution (empty while `typed`)
+    bool typed = false;              // voxels go to the device in their file datatype (single-device path only)
+    int X = 0, Y = 0, Z = 0;         // input of the extraction (after isotropic resampling)
+    int eX = 0, eY = 0, eZ = 0;      // extraction resolution (after -2+/-2-)
+};
+
+// read + (isotropic resampling on the device when needed); allow_typed: keep integer voxels for s3d_extract_typed
+static int load_job(Job &j, const Options &o, s3d_ctx *ctx, bool allow_typed)
+{
+    niftimin::Image &im = j.im;
+    const char *inPath = j.in.c_str();
+    if (o.raw) {
         FILE *f = fopen(inPath, "rb");
-        if (!f || fread(im.data.data(), sizeof(float), im.data.size(), f) != im.data.size()) {
-            printf("Error: could not read input file: %s\n", inPath);
-            return -1;
-        }
+        if (!f) { printf("Error: could not read input file: %s\n", inPath); return -1; }
+        fseek(f, 0, SEEK_END);
+        const long bytes = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        im.data.resize((size_t)(bytes > 0 ? bytes : 0) / sizeof(float));
+        const bool ok = !im.data.empty() && fread(im.data.data(), sizeof(float), im.data.size(), f) == im.data.size();
         fclose(f);
+        if (!ok) { printf("Error: could not read input file: %s\n", inPath); return -1; }
+        int rx = o.rawX, ry = o.rawY, rz = o.rawZ;
+        if (rx <= 0) {
+            if (!guess_raw_dims(im.data.data(), im.data.size(), rx, ry, rz)) { printf("Error: could not determine raw dimensions: %s\n", inPath); return -1; }
+            printf("Raw dimensions (guessed): %d %d %d\n", rx, ry, rz);
+        }
+        if (ry <= 0 || rz <= 0 || (size_t)rx * ry * rz > im.data.size()) { printf("Error: bad raw dimensions\n"); return -1; }
+        im.nx = rx; im.ny = ry; im.nz = rz;
         memset(&im.qto_xyz, 0, sizeof(Mat44));
         im.qto_xyz.m[0][0] = im.qto_xyz.m[1][1] = im.qto_xyz.m[2][2] = im.qto_xyz.m[3][3] = 1.0f;
         im.sto_xyz = im.qto_xyz;
@@ -168,77 +154,56 @@ int main(int argc, char **argv)
         return -1;
     }
     // NIfTI voxels stay in their file datatype when they can go to the device as they are (the cast to float
-    // then runs there, s3d_extract_typed); the host-side isotropic resampling needs floats
-    const bool need_iso = bIso && (im.dx != im.dy || im.dy != im.dz || im.dx != im.dz);
-    const bool typed = !im.raw.empty() && !need_iso && im.datatype != 16;
-    if (!im.raw.empty() && !typed) {
+    // then runs there, s3d_extract_typed); the isotropic resampling needs floats
+    const bool need_iso = o.bIso && (im.dx != im.dy || im.dy != im.dz || im.dx != im.dz);
+    j.typed = allow_typed && !im.raw.empty() && !need_iso && im.datatype != 16;
+    if (!im.raw.empty() && !j.typed) {
         im.data.resize((size_t)im.nx * im.ny * im.nz * im.nt);
         niftimin::cast_to_float(im.raw.data(), im.datatype, im.data.size(), im.data.data());
         im.raw.clear();
     }
-
-    int X = im.nx, Y = im.ny, Z = im.nz;
-    std::vector<float> vol;
-    // isotropic resampling (reference featExtract.cpp:118-204)
-    if (bIso && (im.dx != im.dy || im.dy != im.dz || im.dx != im.dz)) {
+    j.X = im.nx; j.Y = im.ny; j.Z = im.nz;
+    if (need_iso) {
+        // isotropic resampling (reference featExtract.cpp:118-204): matrices on the host, voxels on the device
         float fMin = im.dx;
         if (im.dy < fMin) fMin = im.dy;
         if (im.dz < fMin) fMin = im.dz;
-        int nX = (int)(im.nx * im.dx / fMin), nY = (int)(im.ny * im.dy / fMin), nZ = (int)(im.nz * im.dz / fMin);
-        float rf[3] = { fMin / im.dx, fMin / im.dy, fMin / im.dz };
-        for (int i = 0; i < 3; i++)
-            for (int j = 0; j < 3; j++) {
-                im.qto_xyz.m[i][j] *= rf[j];
-                if (im.sform_code > 0) im.sto_xyz.m[i][j] *= rf[j];
+        const int nX = (int)(im.nx * im.dx / fMin), nY = (int)(im.ny * im.dy / fMin), nZ = (int)(im.nz * im.dz / fMin);
+        const float rf[3] = { fMin / im.dx, fMin / im.dy, fMin / im.dz };
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) {
+                im.qto_xyz.m[a][b] *= rf[b];
+                if (im.sform_code > 0) im.sto_xyz.m[a][b] *= rf[b];
             }
-        vol.resize((size_t)nX * nY * nZ);
-        for (int z = 0; z < nZ; z++)
-            for (int y = 0; y < nY; y++)
-                for (int x = 0; x < nX; x++)
-                    vol[((size_t)z * nY + y) * nX + x] = trilinear(im.data.data(), X, Y, Z, (float)(x * rf[0] + 0.5), (float)(y * rf[1] + 0.5), (float)(z * rf[2] + 0.5));
-        X = nX; Y = nY; Z = nZ;
+        if (nX < 1 || nY < 1 || nZ < 1 || j.X < 2 || j.Y < 2 || j.Z < 2) { printf("Could not read volume: %s\n", inPath); return -1; }
+        j.vol.resize((size_t)nX * nY * nZ);
+        if (s3d_resample_iso_host(ctx, im.data.data(), j.X, j.Y, j.Z, j.vol.data(), nX, nY, nZ, rf[0], rf[1], rf[2]) != S3D_OK) {
+            printf("Error: could not resample %s: %s\n", inPath, s3d_last_error(ctx));
+            return -1;
+        }
+        j.X = nX; j.Y = nY; j.Z = nZ;
         im.dx = im.dy = im.dz = fMin;
-    } else if (!typed) {
-        vol.assign(im.data.begin(), im.data.begin() + (size_t)X * Y * Z);
+    } else if (!j.typed) {
+        j.vol.assign(im.data.begin(), im.data.begin() + (size_t)j.X * j.Y * j.Z);
     }
-    int eX = X, eY = Y, eZ = Z;   // extraction resolution (after -2+/-2-)
-    if (bDouble == 1) { eX *= 2; eY *= 2; eZ *= 2; }
-    else if (bDouble == -1) { eX /= 2; eY /= 2; eZ /= 2; }
-    if (eZ <= 1) { printf("Could not read volume: %s\n", inPath); return -1; }
-    printf("Input image: i=%d j=%d k=%d\n", eX, eY, eZ);
+    im.data.clear(); im.data.shrink_to_fit();
+    j.eX = j.X; j.eY = j.Y; j.eZ = j.Z;
+    if (o.bDouble == 1) { j.eX *= 2; j.eY *= 2; j.eZ *= 2; }
+    else if (o.bDouble == -1) { j.eX /= 2; j.eY /= 2; j.eZ /= 2; }
+    if (j.eZ <= 1) { printf("Could not read volume: %s\n", inPath); return -1; }
+    printf("Input image: i=%d j=%d k=%d\n", j.eX, j.eY, j.eZ);
+    return 0;
+}
 
-    s3d_ctx *ctx = nullptr;
-    if (s3d_ctx_create(device, &ctx) != S3D_OK) {
-        printf("Error: could not initialise CUDA device %d: %s\n", device, ctx ? s3d_last_error(ctx) : "no device");
-        return -1;
-    }
-    s3d_params prm;
-    memset(&prm, 0, sizeof(prm));
-    prm.double_mode = bDouble; prm.descriptor = descriptor; prm.eig_thres = fEigThres;
-    s3d_feature *feats = nullptr;
-    int n = 0;
-    auto run = [&]() {
-        return typed ? s3d_extract_typed(ctx, im.raw.data(), im.datatype, X, Y, Z, &prm, &feats, &n)
-                     : s3d_extract(ctx, vol.data(), X, Y, Z, &prm, &feats, &n);
-    };
-    s3d_status st = run();
-    if (st == S3D_ERR_CAPACITY) {   // retry once with room for a very dense volume
-        prm.max_keypoints = 1 << 18;
-        prm.max_features = 1 << 21;
-        st = run();
-    }
-    if (st != S3D_OK) {
-        printf("Error: could not extract features, %s.\n", st == S3D_ERR_NOMEM ? "insufficient memory" : s3d_last_error(ctx));
-        s3d_ctx_destroy(ctx);
-        return -1;
-    }
-
-    // world coordinates (reference featExtract.cpp:436-473, 507-538)
+// world coordinates (reference featExtract.cpp:436-473, 507-538) + the text feature file
+static int finish_job(Job &j, const Options &o, s3d_feature *feats, int n)
+{
+    niftimin::Image &im = j.im;
     Mat44 m_current;
     memset(&m_current, 0, sizeof(m_current));
-    if (bWorld) {
+    if (o.bWorld) {
         const Mat44 *pm = &im.qto_xyz;
-        if (bWorld == 2) {
+        if (o.bWorld == 2) {
             if (im.sform_code > 0) pm = &im.sto_xyz;
             else printf("Error: sform_code <= 0, output to qto_xyz instead of sto_xyz");
         }
@@ -256,7 +221,7 @@ int main(int argc, char **argv)
             float in[4] = { f.x, f.y, f.z, 1 }, out[4];
             for (int i = 0; i < 4; i++) {
                 out[i] = 0;
-                for (int j = 0; j < 4; j++) out[i] += m_current.m[i][j] * in[j];
+                for (int q = 0; q < 4; q++) out[i] += m_current.m[i][q] * in[q];
             }
             f.x = out[0]; f.y = out[1]; f.z = out[2];
             f.scale *= fScaleSum;
@@ -266,13 +231,12 @@ int main(int argc, char **argv)
             invert3f(oo, f.ori);
         }
     }
-
     char c1[200], c2[200], c3[400];
-    snprintf(c1, sizeof(c1), "Extraction Voxel Resolution (ijk) : %d %d %d", eX, eY, eZ);
+    snprintf(c1, sizeof(c1), "Extraction Voxel Resolution (ijk) : %d %d %d", j.eX, j.eY, j.eZ);
     snprintf(c2, sizeof(c2), "Extraction Voxel Size (mm)  (ijk) : %f %f %f", 1.0f * im.dx, 1.0f * im.dy, 1.0f * im.dz);
-    if (bWorld) {
+    if (o.bWorld) {
         snprintf(c3, sizeof(c3), "Feature Coordinate Space: millimeters (%s) : %f %f %f %f %f %f %f %f %f %f %f %f 0.0 0.0 0.0 1.0",
-                 bWorld == 1 ? "qto_xyz" : "sto_xyz",
+                 o.bWorld == 1 ? "qto_xyz" : "sto_xyz",
                  1.0f * m_current.m[0][0], 1.0f * m_current.m[0][1], 1.0f * m_current.m[0][2], 1.0f * m_current.m[0][3],
                  1.0f * m_current.m[1][0], 1.0f * m_current.m[1][1], 1.0f * m_current.m[1][2], 1.0f * m_current.m[1][3],
                  1.0f * m_current.m[2][0], 1.0f * m_current.m[2][1], 1.0f * m_current.m[2][2], 1.0f * m_current.m[2][3]);
@@ -280,12 +244,175 @@ int main(int argc, char **argv)
         snprintf(c3, sizeof(c3), "Feature Coordinate Space: voxels: 1.0 0.0 0.0 0.0 0.0 1.0 0.0 0.0 0.0 0.0 1.0 0.0 0.0 0.0 0.0 1.0");
     }
     const char *comments[3] = { c1, c2, c3 };
-    if (s3d_write_features_text(outPath, feats, n, fEigThres, 3, comments) != S3D_OK) {
-        printf("Error: could not write %s\n", outPath);
+    if (s3d_write_features_text(j.out.c_str(), feats, n, o.fEigThres, 3, comments) != S3D_OK) {
+        printf("Error: could not write %s\n", j.out.c_str());
         return -1;
     }
-    s3d_free(feats);
-    s3d_ctx_destroy(ctx);
+    return 0;
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 3) { print_options(); return -1; }
+    Options o;
+    int iArg = 1;
+    const char *listPath = nullptr;
+    while (iArg < argc && argv[iArg][0] == '-') {
+        switch (argv[iArg][1]) {
+        case '2':
+            o.bDouble = 1;
+            if (argv[iArg][2] == '-') o.bDouble = -1;
+            iArg++;
+            break;
+        case 'd': {
+            const int n = s3d_device_count();
+            o.devices.clear();
+            const char *p = argv[iArg] + 2;
+            if (*p == 0) o.devices.push_back(0);
+            while (*p) {
+                int d = *p - '0';
+                if (d < 0 || d > 9 || d >= (n > 0 ? n : 1)) {
+                    printf("Error: unknown device: %d\n", d);
+                    print_options();
+                    return -1;
+                }
+                o.devices.push_back(d);
+                p++;
+                if (*p == ',') p++;
+                else if (*p) { printf("Error: unknown device: %s\n", argv[iArg]); print_options(); return -1; }
+            }
+            iArg++;
+            break;
+        }
+        case 'l':
+            if (iArg + 1 >= argc) { print_options(); return -1; }
+            listPath = argv[iArg + 1];
+            iArg += 2;
+            break;
+        case 'w': case 'W':
+            o.bWorld = 1; o.bIso = 1;
+            if (argv[iArg][2] == 's' || argv[iArg][2] == 'S') o.bWorld = 2;
+            iArg++;
+            break;
+        case 'b':
+            o.descriptor = argv[iArg][2] == 'r' ? S3D_DESC_RRIEF : argv[iArg][2] == 'n' ? S3D_DESC_NRRIEF : S3D_DESC_BRIEF;
+            iArg++;
+            break;
+        case 'r':
+            o.raw = true;
+            if (iArg + 3 < argc && atoi(argv[iArg + 1]) > 0 && atoi(argv[iArg + 2]) > 0 && atoi(argv[iArg + 3]) > 0 && argc - (iArg + 4) >= 2) {
+                o.rawX = atoi(argv[iArg + 1]); o.rawY = atoi(argv[iArg + 2]); o.rawZ = atoi(argv[iArg + 3]);
+                iArg += 4;
+            } else {
+                iArg += 1;          // dimensions are guessed from the signal
+            }
+            break;
+        default:
+            printf("Error: unknown command line argument: %s\n", argv[iArg]);
+            print_options();
+            return -1;
+        }
+    }
+    if (o.devices.empty()) o.devices.push_back(0);
+    std::vector<Job> jobs;
+    if (listPath) {
+        FILE *f = fopen(listPath, "r");
+        if (!f) { printf("Error: could not read list file: %s\n", listPath); return -1; }
+        char a[4096], b[4096];
+        while (fscanf(f, "%4095s %4095s", a, b) == 2) { Job j; j.in = a; j.out = b; jobs.push_back(std::move(j)); }
+        fclose(f);
+        if (jobs.empty()) { printf("Error: empty list file: %s\n", listPath); return -1; }
+    } else {
+        if (argc - iArg < 2) { print_options(); return -1; }
+        Job j; j.in = argv[iArg]; j.out = argv[iArg + 1];
+        jobs.push_back(std::move(j));
+    }
+    const bool multi = o.devices.size() > 1 || listPath != nullptr;
+
+    s3d_params prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.double_mode = o.bDouble; prm.descriptor = o.descriptor; prm.eig_thres = o.fEigThres;
+
+    if (!multi) {
+        // ---- one volume, one device: the reference's mode of operation
+        Job &j = jobs[0];
+        printf("Extracting features: %s\n", j.in.c_str());
+        s3d_ctx *ctx = nullptr;
+        if (s3d_ctx_create(o.devices[0], &ctx) != S3D_OK) {
+            printf("Error: could not initialise CUDA device %d: %s\n", o.devices[0], ctx ? s3d_last_error(ctx) : "no device");
+            return -1;
+        }
+        if (load_job(j, o, ctx, /*allow_typed=*/true) < 0) { s3d_ctx_destroy(ctx); return -1; }
+        s3d_feature *feats = nullptr;
+        int n = 0;
+        auto run = [&]() {
+            return j.typed ? s3d_extract_typed(ctx, j.im.raw.data(), j.im.datatype, j.X, j.Y, j.Z, &prm, &feats, &n)
+                           : s3d_extract(ctx, j.vol.data(), j.X, j.Y, j.Z, &prm, &feats, &n);
+        };
+        s3d_status st = run();
+        if (st == S3D_ERR_CAPACITY) {   // retry once with room for a very dense volume
+            prm.max_keypoints = 1 << 18;
+            prm.max_features = 1 << 21;
+            st = run();
+        }
+        if (st != S3D_OK) {
+            printf("Error: could not extract features, %s.\n", st == S3D_ERR_NOMEM ? "insufficient memory" : s3d_last_error(ctx));
+            s3d_ctx_destroy(ctx);
+            return -1;
+        }
+        const int rc = finish_job(j, o, feats, n);
+        s3d_free(feats);
+        s3d_ctx_destroy(ctx);
+        if (rc < 0) return -1;
+        printf("\nDone.\n");
+        return 0;
+    }
+
+    // ---- several devices and / or a list of volumes
+    s3d_multi *m = nullptr;
+    if (s3d_multi_create((int)o.devices.size(), o.devices.data(), 4, &m) != S3D_OK) {
+        printf("Error: could not initialise CUDA devices: %s\n", m ? s3d_multi_last_error(m) : "no device");
+        return -1;
+    }
+    s3d_ctx *ctx0 = nullptr;       // for the device-side resampling of the loader
+    if (s3d_ctx_create(o.devices[0], &ctx0) != S3D_OK) { printf("Error: could not initialise CUDA device %d\n", o.devices[0]); return -1; }
+    for (Job &j : jobs) {
+        printf("Extracting features: %s\n", j.in.c_str());
+        if (load_job(j, o, ctx0, /*allow_typed=*/false) < 0) return -1;
+    }
+    s3d_ctx_destroy(ctx0);
+    int rc = 0;
+    if (!listPath) {
+        // one volume over several devices: z slabs
+        Job &j = jobs[0];
+        s3d_feature *feats = nullptr;
+        int n = 0;
+        s3d_status st = s3d_multi_extract_slab(m, j.vol.data(), j.X, j.Y, j.Z, &prm, &feats, &n);
+        if (st != S3D_OK) { printf("Error: could not extract features, %s.\n", s3d_multi_last_error(m)); s3d_multi_destroy(m); return -1; }
+        rc = finish_job(j, o, feats, n);
+        s3d_free(feats);
+    } else {
+        // a list: runs of equal-shaped volumes are sharded over the devices
+        size_t i0 = 0;
+        while (i0 < jobs.size() && rc == 0) {
+            size_t i1 = i0 + 1;
+            while (i1 < jobs.size() && jobs[i1].X == jobs[i0].X && jobs[i1].Y == jobs[i0].Y && jobs[i1].Z == jobs[i0].Z) i1++;
+            const int nb = (int)(i1 - i0);
+            std::vector<const float *> vols(nb);
+            std::vector<s3d_feature *> rows(nb, nullptr);
+            std::vector<int> n_rows(nb, 0);
+            for (int k = 0; k < nb; k++) vols[k] = jobs[i0 + k].vol.data();
+            s3d_status st = s3d_multi_batch_extract(m, vols.data(), nb, jobs[i0].X, jobs[i0].Y, jobs[i0].Z, &prm, rows.data(), n_rows.data());
+            if (st != S3D_OK) { printf("Error: could not extract features, %s.\n", s3d_multi_last_error(m)); rc = -1; }
+            for (int k = 0; k < nb; k++) {
+                if (rc == 0 && finish_job(jobs[i0 + k], o, rows[k], n_rows[k]) < 0) rc = -1;
+                if (rows[k]) s3d_free(rows[k]);
+            }
+            i0 = i1;
+        }
+    }
+    s3d_multi_destroy(m);
+    if (rc < 0) return -1;
     printf("\nDone.\n");
     return 0;
 }

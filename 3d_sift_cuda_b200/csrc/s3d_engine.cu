@@ -557,6 +557,42 @@ static s3d_status resize_launch(s3d_ctx *ctx, int kind, const float *in, int X, 
     return S3D_OK;
 }
 
+// Isotropic resampling on the device (section 8(f) N1; reference featExtract.cpp:118-204, a host triple loop there)
+extern "C" s3d_status s3d_resample_iso(s3d_ctx *ctx, const float *d_in, int X, int Y, int Z, int pitch,
+                                       float *d_out, int nX, int nY, int nZ, int out_pitch, float rf_x, float rf_y, float rf_z)
+{
+    if (!ctx) return S3D_ERR_INVALID;
+    if (!d_in || !d_out || X < 2 || Y < 2 || Z < 2 || pitch < X || nX < 1 || nY < 1 || nZ < 1 || out_pitch < nX)
+        return fail(ctx, S3D_ERR_INVALID, "s3d_resample_iso: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    dim3 block(32, 8), grid((out_pitch + 31) / 32, (nY + 7) / 8, nZ);
+    resample_iso_kernel<<<grid, block, 0, ctx->stream>>>(d_in, X, Y, Z, pitch, d_out, nX, nY, nZ, out_pitch, rf_x, rf_y, rf_z);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return S3D_OK;
+}
+
+// host-array form of s3d_resample_iso: upload, resample, download, synchronise (what the CLI's loader calls)
+extern "C" s3d_status s3d_resample_iso_host(s3d_ctx *ctx, const float *h_in, int X, int Y, int Z,
+                                            float *h_out, int nX, int nY, int nZ, float rf_x, float rf_y, float rf_z)
+{
+    if (!ctx) return S3D_ERR_INVALID;
+    if (!h_in || !h_out) return fail(ctx, S3D_ERR_INVALID, "s3d_resample_iso_host: null array");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t n_in = (size_t)X * Y * Z, n_out = (size_t)nX * nY * nZ;
+    float *d_in = nullptr, *d_out = nullptr;
+    CK(cudaMallocAsync((void **)&d_in, n_in * sizeof(float), st));
+    CK(cudaMallocAsync((void **)&d_out, n_out * sizeof(float), st));
+    CK(cudaMemcpyAsync(d_in, h_in, n_in * sizeof(float), cudaMemcpyHostToDevice, st));
+    s3d_status s = s3d_resample_iso(ctx, d_in, X, Y, Z, X, d_out, nX, nY, nZ, nX, rf_x, rf_y, rf_z);
+    if (s == S3D_OK) CK(cudaMemcpyAsync(h_out, d_out, n_out * sizeof(float), cudaMemcpyDeviceToHost, st));
+    cudaFreeAsync(d_in, st);
+    cudaFreeAsync(d_out, st);
+    CK(cudaStreamSynchronize(st));
+    return s;
+}
+
 extern "C" s3d_status s3d_subsample2(s3d_ctx *ctx, const float *d_in, int X, int Y, int Z, int pitch, float *d_out, int out_pitch)
 {
     if (!ctx) return S3D_ERR_INVALID;

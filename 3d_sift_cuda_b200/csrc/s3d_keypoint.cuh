@@ -129,6 +129,21 @@ __device__ __forceinline__ float trilinear_get(const float *__restrict__ img, in
     return wz * fnn0 + (1.0f - wz) * fnn1;
 }
 
+// Isotropic resampling of an anisotropic input (section 8(f) N1; reference featExtract.cpp:118-204): output voxel
+// (x,y,z) = fioGetPixelTrilinearInterp(in, x*rf0 + 0.5, y*rf1 + 0.5, z*rf2 + 0.5) with the reference's types:
+// int * float is a float product, + 0.5 is a double sum, and the sum is narrowed to the float parameter.
+__global__ void resample_iso_kernel(const float *__restrict__ in, int X, int Y, int Z, int pitch,
+                                    float *__restrict__ out, int nX, int nY, int nZ, int opitch, float rf0, float rf1, float rf2)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z;
+    if (x >= opitch || y >= nY || z >= nZ) return;
+    float v = 0.0f;
+    if (x < nX)
+        v = trilinear_get(in, X, Y, Z, pitch, (float)((double)((float)x * rf0) + 0.5), (float)((double)((float)y * rf1) + 0.5),
+                          (float)((double)((float)z * rf2) + 0.5));
+    out[((long long)z * nY + y) * opitch + x] = v;
+}
+
 // invert_3x3<float,double> (reference MultiScale.h:192-222)
 __device__ void invert3(const float *m, float *o)
 {

@@ -246,6 +246,17 @@ s3d_status s3d_write_features_bin(const char *path, const s3d_feature *feats, in
  * featMatchMultiple uses (R/featMatchMultiple/featMatchMultiple.cpp:596).  *out is malloc'ed (s3d_free). */
 s3d_status s3d_read_features_text(const char *path, s3d_feature **out, int *n_out);
 
+/* ---- input path on the device ----------------------------------------------------
+ * Isotropic resampling of an anisotropic volume: out(x,y,z) = trilinear(in, x*rf_x + 0.5, y*rf_y + 0.5, z*rf_z + 0.5),
+ * rf = min voxel size / voxel size per axis, output dims = (int)(n * d / d_min).  Replaces the host triple loop of
+ * fioReadNifti (R/featExtract/featExtract.cpp:183-199, fioGetPixelTrilinearInterp R/src_common/FeatureIO.cpp:757-850);
+ * same bits.  Device arrays, stream-ordered; the matrix bookkeeping (:146-176) stays with the caller. */
+s3d_status s3d_resample_iso(s3d_ctx *ctx, const float *d_in, int X, int Y, int Z, int pitch,
+                            float *d_out, int nX, int nY, int nZ, int out_pitch, float rf_x, float rf_y, float rf_z);
+/* the same on dense HOST arrays: upload, resample, download, synchronise */
+s3d_status s3d_resample_iso_host(s3d_ctx *ctx, const float *h_in, int X, int Y, int Z,
+                                 float *h_out, int nX, int nY, int nZ, float rf_x, float rf_y, float rf_z);
+
 /* ---- multi-GPU (SURVEY.md section 8(b) last row, 8(e); BASELINE.json configs 4 and 5) ---------------------------
  * One host thread per GPU above the single-GPU entry points, for hosts that are one process -- like the
  * reference's featExtract (R/featExtract/featExtract.cpp:273-585, one volume, one device chosen by

@@ -94,3 +94,49 @@ def test_stage_level_drop_in_under_the_reference_pipeline(pkg, engine, tmp_path,
     b = open(tmp_path / "s3d.key", "rb").read()
     assert a.count(b"\n") > 8, "reference produced no features"
     assert a == b
+
+
+def test_cli_slab_mode_over_listed_devices(pkg, engine, tmp_path):
+    """featExtract -d0,0: ONE volume split into z slabs over the listed devices (here the same GPU twice) through
+    s3d_multi_extract_slab must write the reference CLI's bytes."""
+    if not (os.path.exists(OURS) and os.path.exists(REF)):
+        pytest.skip("CLI binaries not built")
+    vol = pkg.phantom.blob_phantom((48, 44, 230), 7, 120)
+    nii = str(tmp_path / "in.nii")
+    pkg.phantom.write_nifti(nii, vol)
+    run(REF, [nii, "ref.key"], str(tmp_path))
+    run(OURS, ["-d0,0", nii, "slab.key"], str(tmp_path))
+    a = open(tmp_path / "ref.key", "rb").read()
+    assert a.count(b"\n") > 8
+    assert a == open(tmp_path / "slab.key", "rb").read()
+
+
+def test_cli_list_mode_shards_volumes(pkg, engine, tmp_path):
+    """featExtract -l list [-dA,B]: every "<input> <output>" line of the list is extracted (runs of equal shapes are
+    sharded over the devices through s3d_multi_batch_extract); each output equals the reference CLI's."""
+    if not (os.path.exists(OURS) and os.path.exists(REF)):
+        pytest.skip("CLI binaries not built")
+    shapes = [(56, 60, 52)] * 3 + [(40, 44, 36)] * 2
+    lines = []
+    for k, shp in enumerate(shapes):
+        nii = str(tmp_path / ("in%d.nii" % k))
+        pkg.phantom.write_nifti(nii, pkg.phantom.blob_phantom(shp, 40 + k, 45), pixdim=(1.0, 1.0, 1.0 if k else 2.0))
+        run(REF, ["-w", nii, "ref%d.key" % k], str(tmp_path))
+        lines.append("%s %s" % (nii, str(tmp_path / ("out%d.key" % k))))
+    (tmp_path / "list.txt").write_text("\n".join(lines) + "\n")
+    run(OURS, ["-w", "-d0,0", "-l", "list.txt"], str(tmp_path))
+    for k in range(len(shapes)):
+        assert open(tmp_path / ("ref%d.key" % k), "rb").read() == open(tmp_path / ("out%d.key" % k), "rb").read(), k
+
+
+def test_cli_guesses_raw_dimensions(pkg, oracle, engine, tmp_path):
+    """-r without dimensions: they are recovered from the signal (FeatureIO.cpp:3006-3227 idea, deterministic)."""
+    if not os.path.exists(OURS):
+        pytest.skip("CLI not built")
+    vol = pkg.phantom.blob_phantom((72, 56, 40), 3, 60)
+    raw = str(tmp_path / "in.f32")
+    vol.tofile(raw)
+    run(OURS, ["-r", raw, "o.key"], str(tmp_path))
+    want = str(tmp_path / "w.key")
+    pkg.api.write_features_text(want, oracle.extract(vol, 0, 0)["features"], (72, 56, 40))
+    assert open(tmp_path / "o.key", "rb").read() == open(want, "rb").read()
