@@ -436,9 +436,11 @@ class Batch:
         Z, Y, X = h_volumes[0].shape
         rows = (C.c_void_p * n)()
         cnt = (C.c_int * n)()
-        self._ck(self.L.s3d_batch_extract(self.b, self._ptrs(h_volumes), n, X, Y, Z, C.byref(params.c), rows, cnt),
-                 "s3d_batch_extract")
-        return [_copy_out(C.c_void_p(rows[k]), cnt[k], FEATURE_DTYPE, self.L.s3d_free) for k in range(n)]
+        st = self.L.s3d_batch_extract(self.b, self._ptrs(h_volumes), n, X, Y, Z, C.byref(params.c), rows, cnt)
+        # wrap (and thereby own) whatever was malloc'ed before a failing volume stopped the batch, then report
+        out = [_copy_out(C.c_void_p(rows[k]), cnt[k], FEATURE_DTYPE, self.L.s3d_free) if rows[k] else np.zeros(0, FEATURE_DTYPE) for k in range(n)]
+        self._ck(st, "s3d_batch_extract")
+        return out
 
     def extract_typed(self, h_volumes, params=None):
         """Like extract() for host volumes of one NIfTI scalar dtype (numpy arrays or pinned torch tensors)."""
@@ -455,9 +457,10 @@ class Batch:
         Z, Y, X = v0.shape
         rows = (C.c_void_p * n)()
         cnt = (C.c_int * n)()
-        self._ck(self.L.s3d_batch_extract_typed(self.b, self._ptrs(h_volumes), code, n, X, Y, Z, C.byref(params.c), rows, cnt),
-                 "s3d_batch_extract_typed")
-        return [_copy_out(C.c_void_p(rows[k]), cnt[k], FEATURE_DTYPE, self.L.s3d_free) for k in range(n)]
+        st = self.L.s3d_batch_extract_typed(self.b, self._ptrs(h_volumes), code, n, X, Y, Z, C.byref(params.c), rows, cnt)
+        out = [_copy_out(C.c_void_p(rows[k]), cnt[k], FEATURE_DTYPE, self.L.s3d_free) if rows[k] else np.zeros(0, FEATURE_DTYPE) for k in range(n)]
+        self._ck(st, "s3d_batch_extract_typed")
+        return out
 
     def extract_device(self, d_volumes, shape_xyz, params=None):
         """List of dense device volumes -> (n_keypoints, n_rows) per volume; rows stay on the device."""

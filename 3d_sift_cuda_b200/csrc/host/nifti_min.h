@@ -128,6 +128,9 @@ static inline int read(const std::string &path, Image &img, bool keep_raw = fals
     if (dim[0] < 1 || dim[0] > 7) { gzclose(f); return -1; }
     img.nx = dim[1]; img.ny = dim[0] >= 2 ? dim[2] : 1; img.nz = dim[0] >= 3 ? dim[3] : 1; img.nt = dim[0] >= 4 ? dim[4] : 1;
     if (img.nt < 1) img.nt = 1;
+    // trust nothing in the header (nifti_image_read rejects such files too): every used dimension must be positive
+    // and the voxel count must stay addressable
+    if (img.nx < 1 || img.ny < 1 || img.nz < 1 || (double)img.nx * img.ny * img.nz * img.nt > 1.0e10) { gzclose(f); return -1; }
     img.dx = pixdim[1]; img.dy = pixdim[2]; img.dz = pixdim[3];
     float qfac = (pixdim[0] < 0.0f) ? -1.0f : 1.0f;
     if (img.qform_code > 0) {
@@ -157,6 +160,7 @@ static inline int read(const std::string &path, Image &img, bool keep_raw = fals
     case 64: bpv = 8; break;
     default: gzclose(f); return -2;
     }
+    if (single && !(vox_offset >= 352.0f)) { gzclose(f); return -1; }     // single-file images keep their data behind the 348 + 4 byte header
     if (single) {
         long skip = (long)vox_offset - 348;
         std::vector<unsigned char> junk(4096);

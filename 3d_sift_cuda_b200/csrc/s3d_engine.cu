@@ -1033,6 +1033,9 @@ static s3d_status check_params(s3d_ctx *ctx, const float *vol, int X, int Y, int
     if (X < 1 || Y < 1 || Z < 1) return fail(ctx, S3D_ERR_INVALID, "bad dimensions");
     if (prm->double_mode < -1 || prm->double_mode > 1) return fail(ctx, S3D_ERR_INVALID, "double_mode must be -1, 0 or +1");
     if (prm->descriptor < 0 || prm->descriptor > 3) return fail(ctx, S3D_ERR_INVALID, "unknown descriptor");
+    // capacities bound the per-keypoint work arrays (121 rotations x 9 floats and an 11^3 patch per keypoint)
+    if (prm->max_keypoints < 0 || prm->max_keypoints > (1 << 21) || prm->max_features < 0 || prm->max_features > (1 << 25))
+        return fail(ctx, S3D_ERR_INVALID, "max_keypoints must be <= 2^21 and max_features <= 2^25");
     if (prm->double_mode != 0 && (X < 2 || Y < 2 || Z < 2)) return fail(ctx, S3D_ERR_INVALID, "volume too small for -2+/-2-");
     if (prm->input_is_g0 && prm->double_mode != 0) return fail(ctx, S3D_ERR_INVALID, "input_is_g0 excludes -2+/-2-");
     if (prm->pre_step_done < -1 || prm->pre_step_done > 1 || (prm->pre_step_done != 0 && prm->double_mode != 0))
@@ -1372,9 +1375,7 @@ static s3d_status batch_run(s3d_batch *b, const void *const *vols, int n, int X,
         pending[c] = -1;
         if (j < 0) return S3D_OK;
         s3d_status st;
-        static int no_rows = -1;      // S3D_BATCH_NO_ROWS=1 (profiling only): counts instead of rows in host mode
-        if (no_rows < 0) { const char *e = getenv("S3D_BATCH_NO_ROWS"); no_rows = (e && e[0] == '1') ? 1 : 0; }
-        if (rows && !no_rows) {
+        if (rows) {
             int nr = 0;
             st = s3d_fetch_features(b->ctx[c], &rows[j], &nr);
             if (n_rows) n_rows[j] = nr;
@@ -1389,14 +1390,8 @@ static s3d_status batch_run(s3d_batch *b, const void *const *vols, int n, int X,
         return st;
     };
     s3d_status first_err = S3D_OK;
-    static int stagger_us = -1;
-    if (stagger_us < 0) { const char *e = getenv("S3D_BATCH_STAGGER_US"); stagger_us = e ? atoi(e) : 0; }
     for (int i = 0; i < n && first_err == S3D_OK; i++) {
         const int c = i % nc;
-        if (stagger_us > 0 && i > 0 && i < nc) {      // experiment: de-phase the contexts' first volumes
-            struct timespec ts = { 0, (long)stagger_us * 1000L };
-            nanosleep(&ts, nullptr);
-        }
         s3d_status st = collect(c);
         if (st == S3D_OK)
             st = from_host ? s3d_extract_typed_async(b->ctx[c], vols[i], dtype, X, Y, Z, prm)

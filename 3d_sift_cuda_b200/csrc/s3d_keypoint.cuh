@@ -927,7 +927,7 @@ __global__ void __launch_bounds__(256) orient_a_kernel(const __grid_constant__ P
             for (int q = 0; q < S.nprim; q++) work_b[w0 + q] = kpi * PD + q;
         }
         if (threadIdx.x < 3) kp_eigs[kpi * 3 + threadIdx.x] = S.eigs[threadIdx.x];
-        if (threadIdx.x < 9) kp_ori0[kpi * 9 + threadIdx.x] = S.ori0[threadIdx.x];
+        if (threadIdx.x < 9) kp_ori0[(size_t)kpi * 9 + threadIdx.x] = S.ori0[threadIdx.x];
         PHASE(13);
     }
 }
@@ -1003,7 +1003,7 @@ __global__ void __launch_bounds__(256) orient_b_kernel(const int *__restrict__ w
                 p3[0] = p1[1] * p2[2] - p1[2] * p2[1];
                 p3[1] = -p1[0] * p2[2] + p1[2] * p2[0];
                 p3[2] = p1[0] * p2[1] - p1[1] * p2[0];
-                float *m = kp_rots + (wi * PD + j) * 9;
+                float *m = kp_rots + ((size_t)wi * PD + j) * 9;
                 for (int k = 0; k < 3; k++) { m[k] = p1[k]; m[3 + k] = p2[k]; m[6 + k] = p3[k]; }
             }
             unsigned bal = __ballot_sync(0x7ffu, take);
@@ -1105,7 +1105,7 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ P
         if (threadIdx.x == 0) {
             const float *src;
             if (r == 0) {
-                src = kp_ori0 + kpi * 9;
+                src = kp_ori0 + (size_t)kpi * 9;
             } else {
                 int left = r - 1, pi = 0;
                 while (left >= kp_nsec[(long long)kpi * PD + pi]) { left -= kp_nsec[(long long)kpi * PD + pi]; pi++; }

@@ -4,11 +4,12 @@ orientation + SIFT-Rank descriptors) on synthetic MNI-sized phantoms.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one 182x218x182 fp32 volume through the whole path on each GPU (BASELINE.json config 2;
-with N > 1 this is config 4's batch sharding: every rank extracts its own volumes, no data-path
-collective, weak scaling).  The K steps of a run go through the batch entry point of the C-ABI
-(s3d_batch_*: --contexts extraction contexts in flight per GPU, default 6), timed as ONE region between two CUDA
-events with barrier + synchronize on both sides.  Prints ONE JSON line on rank 0:
+One "step" = one batch of --batch (default 32) 182x218x182 fp32 volumes through the whole path on each GPU:
+BASELINE.json config 4 ("batch of 256 MNI-sized volumes sharded per GPU") is exactly one step at 8 GPUs, and
+per-GPU work is the same at every N (weak scaling; every rank extracts its own volumes, no data-path
+collective).  The K steps of a run go through the batch entry point of the C-ABI (s3d_batch_*: --contexts
+extraction contexts in flight per GPU, default 6), timed as ONE region between two CUDA events with
+barrier + synchronize on both sides.  Prints ONE JSON line on rank 0:
 
   value      volumes/s, whole job, volumes already resident in HBM when the timed region starts
              (s3d_batch_extract_device; inputs rotate through a pool larger than L2; max over ranks)
@@ -19,6 +20,12 @@ events with barrier + synchronize on both sides.  Prints ONE JSON line on rank 0
              (read G_{j-1}, write G_j, write DoG = 12 B/voxel) / measured duration vs MEASURED_PEAKS.json;
              `levels` lists all six levels of octave 0
   cpu_baseline  the reference's own CPU path (oracle/_ref) on the host cores, bounded sample
+  pcie       pinned host -> device copy bandwidth of one 28.9 MB volume, all ranks copying at the same time
+             (per GPU and aggregate): the ceiling `e2e` can reach with fp32 input
+  slab       (N > 1) BASELINE config 5: one 512^3 volume with -2+ (1024^3 pyramid) split into z slabs over the
+             N GPUs through s3d_multi_extract_slab (one host thread per GPU inside the library, halos by peer
+             copies over NVLink; called from rank 0 while the other ranks wait on a CPU barrier), ms per volume,
+             rows, and whether they are identical to the single-GPU whole-volume run
 
 --impl reference times the reference's CPU implementation (oracle/_ref, else the oracle port) with
 all usable host cores on the same workload and prints the same JSON shape.
@@ -146,9 +153,10 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / timed,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "gvoxels_per_s": value * N0 / 1e9,
-        "config": {"workload": WORKLOAD, "shape_xyz": list(SHAPE), "rows_per_volume": rows, "timed_steps": timed,
-                   "note": "reference CPU path (featExtract without -d): %d worker processes, one volume each per step "
-                           "(a step = %d volumes); bounded sample: %d of the %d requested steps were timed" % (procs, procs, timed, args.steps)},
+        "config": {"workload": WORKLOAD, "shape_xyz": list(SHAPE), "descriptor": "SIFT-Rank"},
+        "run": {"rows_per_volume": rows, "timed_steps": timed,
+                "note": "reference CPU path (featExtract without -d): %d worker processes, one volume each per step "
+                        "(a step = %d volumes: a bounded sample of the workload); %d of the %d requested steps were timed" % (procs, procs, timed, args.steps)},
         "cpu_baseline": {"value": value, "unit": "volumes/s", "cores": procs, "kind": cb.kind(),
                          "sample": "%d steps x %d volumes (one per worker process)" % (timed, procs)},
         "e2e": {"value": value, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -253,15 +261,17 @@ def run_ours(args):
 
     # ---- device-resident throughput (value): K volumes through s3d_batch_extract_device -------------
     batch.extract_device([d_vols[i % npool] for i in range(max(args.warmup, 2 * nctx))], SHAPE, params)
-    launches_per_step = batch.launches_per_volume() + 1      # graph nodes + the input re-pitch kernel in front of the graph
+    launches_per_volume = batch.launches_per_volume() + 1      # graph nodes + the input re-pitch kernel in front of the graph
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    seq = [d_vols[i % npool] for i in range(args.steps)]
+    nvol = args.steps * args.batch                      # volumes per GPU in every timed region
+    seq = [d_vols[i % npool] for i in range(nvol)]
     total_ms, (nks, nfs) = timed(lambda: batch.extract_device(seq, SHAPE, params))
     nk, nf = nks[0], nfs[0]
     ms_per_step = total_ms / args.steps
-    value = world * 1e3 / ms_per_step
+    ms_per_volume = total_ms / nvol
+    value = world * 1e3 / ms_per_volume
 
     # ---- latency of one volume alone on the GPU (one context, L2 flushed between steps) ---------------
     for i in range(3):
@@ -269,7 +279,7 @@ def run_ours(args):
     eng.sync()
     evs = []
     with torch.cuda.stream(st):
-        for i in range(min(args.steps, 50)):
+        for i in range(30):
             flush.zero_()                                  # evict L2 (untimed)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(st)
@@ -283,31 +293,45 @@ def run_ours(args):
     # s3d_batch_extract: every step's 28.9 MB volume is copied from pinned host memory (H2D) and its feature
     # rows are copied back (D2H) inside the timed region; the contexts overlap the copies with compute.
     batch.extract([h_vols[i % npool] for i in range(max(4, 2 * nctx))], params)
-    hseq = [h_vols[i % npool] for i in range(args.steps)]
+    hseq = [h_vols[i % npool] for i in range(nvol)]
     e2e_ms, rows = timed(lambda: batch.extract(hseq, params))
     d2h = sum(r.nbytes + 12 for r in rows)
-    e2e = {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": N0 * 4,
+    e2e = {"value": world * nvol / (e2e_ms * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": N0 * 4 * args.batch,
            "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_ms / args.steps,
+           "h2d_gbs_per_gpu": N0 * 4 * nvol / (e2e_ms * 1e-3) / 1e9,
            "note": "s3d_batch_extract with %d contexts per GPU: pinned H2D of every volume and D2H of its rows inside the timed region" % nctx}
     # typed input: the same phantoms stored as int16, the commonest NIfTI datatype of MNI-space
     # images -- raw voxels cross PCIe (14.4 MB per volume), the cast to float runs on the device
     i16_vols = [torch.from_numpy(np.rint(v * 128.0).astype(np.int16)).pin_memory() for v in vols]
     batch.extract_typed([i16_vols[i % npool] for i in range(max(4, 2 * nctx))], params)
-    iseq = [i16_vols[i % npool] for i in range(args.steps)]
+    iseq = [i16_vols[i % npool] for i in range(nvol)]
     i16_ms, irows = timed(lambda: batch.extract_typed(iseq, params))
-    e2e_i16 = {"value": world * args.steps / (i16_ms * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": N0 * 2,
+    e2e_i16 = {"value": world * nvol / (i16_ms * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": N0 * 2 * args.batch,
                "d2h_bytes_per_step": sum(r.nbytes + 12 for r in irows) // args.steps, "ms_per_step": i16_ms / args.steps,
+               "h2d_gbs_per_gpu": N0 * 2 * nvol / (i16_ms * 1e-3) / 1e9,
                "rows_per_volume": len(irows[0]),
                "note": "s3d_batch_extract_typed, int16 voxels (phantom x128 rounded to integers: a different input than the "
                        "float32 runs, same shape and content), %d contexts per GPU" % nctx}
     # same thing strictly one step at a time (latency of a single featExtract-style call with host buffers)
     barrier()
     t0 = time.perf_counter()
-    for i in range(min(args.steps, 50)):
+    for i in range(30):
         eng.extract_host_async(h_vols[i % npool], params)
         eng.fetch_features()
     torch.cuda.synchronize()
-    e2e["serial_ms_per_step"] = 1e3 * dmod.max_over_ranks(time.perf_counter() - t0, device=dev) / min(args.steps, 50)
+    e2e["serial_ms_per_volume"] = 1e3 * dmod.max_over_ranks(time.perf_counter() - t0, device=dev) / 30
+
+    # ---- the PCIe ceiling of e2e: pinned H2D of one volume, every rank copying at the same time ------
+    dst = torch.empty_like(d_vols[0])
+    for _ in range(3):
+        dst.copy_(h_vols[0], non_blocking=True)
+    ncopy = 40
+    pcie_ms, _ = timed(lambda: [dst.copy_(h_vols[i % npool], non_blocking=True) for i in range(ncopy)])
+    gbs = N0 * 4 * ncopy / (pcie_ms * 1e-3) / 1e9
+    pcie = {"h2d_gbs_per_gpu": gbs, "h2d_gbs_aggregate": gbs * world, "bytes_per_copy": N0 * 4, "copies": ncopy,
+            "volumes_per_s_ceiling_fp32": world * gbs * 1e9 / (N0 * 4), "volumes_per_s_ceiling_int16": world * gbs * 1e9 / (N0 * 2),
+            "note": "pinned host -> device cudaMemcpyAsync of one volume, %d rank(s) copying concurrently, slowest rank" % world}
+    del dst
     clocks = sampler.stop() if rank == 0 else None   # sampled across all timed regions
 
     # ---- roofline of the dominant stage: the blur levels of octave 0 (x+y kernel, z kernel with fused DoG) ----
@@ -376,10 +400,51 @@ def run_ours(args):
                 "levels": levels,
                 "octave0_blur_chain": {"algorithmic_bytes": tot_alg, "ms": tot_ms, "achieved": tot_alg / (tot_ms * 1e-3) / 1e9,
                                        "frac": tot_alg / (tot_ms * 1e-3) / 1e9 / peak},
-                "pipeline": {"algorithmic_bytes": algorithmic_bytes(SHAPE), "ms": ms_per_step,
-                             "achieved": algorithmic_bytes(SHAPE) / (ms_per_step * 1e-3) / 1e9,
-                             "frac": algorithmic_bytes(SHAPE) / (ms_per_step * 1e-3) / 1e9 / peak,
+                "pipeline": {"algorithmic_bytes": algorithmic_bytes(SHAPE), "ms": ms_per_volume,
+                             "achieved": algorithmic_bytes(SHAPE) / (ms_per_volume * 1e-3) / 1e9,
+                             "frac": algorithmic_bytes(SHAPE) / (ms_per_volume * 1e-3) / 1e9 / peak,
                              "note": "whole step incl. keypoint stages vs SURVEY 8(d) algorithmic bytes"}}
+
+    # ---- BASELINE config 5 (N > 1): one 512^3 volume with -2+ split into z slabs over the N GPUs ------------
+    slab = None
+    if world > 1 and not args.no_slab:
+        cpu_group = dist.new_group(backend="gloo")      # the other ranks wait on the CPU: their GPUs belong to rank 0's slabs now
+        eng.close(); batch.close()
+        del d_vols, h_vols, i16_vols, flush
+        torch.cuda.empty_cache()
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            try:
+                S = args.slab_size
+                big = pkg.phantom.brain_phantom((S, S, S), 1, args.slab_blobs)
+                prm5 = pkg.Params(double_mode=1)
+                m = pkg.Multi(list(range(world)))
+                t0 = time.perf_counter()
+                rows5 = m.extract_slab(big, prm5)          # first call: plans and graphs are built
+                first_ms = 1e3 * (time.perf_counter() - t0)
+                reps = []
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    again = m.extract_slab(big, prm5)
+                    reps.append(1e3 * (time.perf_counter() - t0))
+                m.close()
+                slab = {"workload": "one %d^3 volume with -2+ (%d^3 pyramid), %d blobs, z slabs over %d GPUs (s3d_multi_extract_slab)" % (S, 2 * S, args.slab_blobs, world),
+                        "ms_per_volume": min(reps), "ms_per_volume_all": reps, "first_call_ms": first_ms, "rows": int(len(rows5)),
+                        "deterministic": bool(again.tobytes() == rows5.tobytes()),
+                        "timing": "host wall clock around the call: pageable host volume in, host rows out"}
+                if not args.no_slab_check:
+                    e1 = pkg.Engine(0)
+                    p1 = pkg.Params(double_mode=1, max_keypoints=1 << 18, max_features=1 << 21)
+                    e1.extract(big, p1)
+                    t0 = time.perf_counter()
+                    whole = e1.extract(big, p1)
+                    slab["single_gpu_ms_per_volume"] = 1e3 * (time.perf_counter() - t0)
+                    slab["identical_to_single_gpu"] = bool(whole.tobytes() == rows5.tobytes())
+                    slab["speedup_vs_single_gpu"] = slab["single_gpu_ms_per_volume"] / slab["ms_per_volume"]
+                    e1.close()
+            except Exception as exc:      # noqa: BLE001
+                slab = {"error": repr(exc)[:300]}
+        dist.barrier(group=cpu_group)
 
     if rank == 0:
         line = {
@@ -387,17 +452,21 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "gvoxels_per_s": value * N0 / 1e9,
-            "config": {"workload": WORKLOAD, "shape_xyz": list(SHAPE), "phantom": "brain_phantom(seed=1.., nblobs=400)",
-                       "parallelism": ("volumes sharded over %d GPUs, no data-path collective; " % world if world > 1 else "single GPU; ")
-                                      + "%d extraction contexts (streams) in flight per GPU (s3d_batch)" % nctx,
-                       "contexts_per_gpu": nctx,
-                       "l2": "inputs larger than L2: a pool of 8 distinct volumes (231 MB) is rotated and every context "
-                             "owns a 0.44 GB pyramid; the one-volume latency below flushes L2 (256 MiB write) between steps",
-                       "keypoints_per_volume": nk, "rows_per_volume": nf},
-            "latency_ms_per_volume": lat_ms,
-            "clocks": clocks, "e2e": e2e, "e2e_int16": e2e_i16, "gpu_launches": launches_per_step * args.steps,
-            "launches_per_step": launches_per_step, "roofline": roof, "cpu_baseline": cpu, "ref_cuda_baseline": ref_cuda,
+            "config": {"workload": WORKLOAD, "shape_xyz": list(SHAPE), "descriptor": "SIFT-Rank"},
+            "run": {"phantom": "brain_phantom(seed=1.., nblobs=400)",
+                    "parallelism": ("volumes sharded over %d GPUs, no data-path collective; " % world if world > 1 else "single GPU; ")
+                                   + "%d extraction contexts (streams) in flight per GPU (s3d_batch)" % nctx,
+                    "contexts_per_gpu": nctx, "volumes_per_step_per_gpu": args.batch, "volumes_per_step": args.batch * world,
+                    "step": "one batch of %d volumes per GPU (BASELINE config 4 = 256 volumes = one step at 8 GPUs)" % args.batch,
+                    "l2": "inputs larger than L2: a pool of 8 distinct volumes (231 MB) is rotated and every context "
+                          "owns a 0.44 GB pyramid; the one-volume latency below flushes L2 (256 MiB write) between steps",
+                    "keypoints_per_volume": nk, "rows_per_volume": nf},
+            "ms_per_volume": ms_per_volume, "latency_ms_per_volume": lat_ms,
+            "clocks": clocks, "e2e": e2e, "e2e_int16": e2e_i16, "pcie": pcie, "gpu_launches": launches_per_volume * nvol,
+            "launches_per_volume": launches_per_volume, "roofline": roof, "cpu_baseline": cpu, "ref_cuda_baseline": ref_cuda,
         }
+        if slab is not None:
+            line["slab"] = slab
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -410,8 +479,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32, help="volumes per GPU per step (config 4: 256 volumes / 8 GPUs)")
+    ap.add_argument("--slab-size", type=int, default=512, help="edge of the config-5 volume (run with -2+)")
+    ap.add_argument("--slab-blobs", type=int, default=8000)
+    ap.add_argument("--no-slab", action="store_true", help="skip the config-5 z-slab measurement at N > 1")
+    ap.add_argument("--no-slab-check", action="store_true", help="skip the single-GPU whole-volume comparison of the slab rows")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--contexts", type=int, default=6, help="extraction contexts in flight per GPU")
