@@ -189,6 +189,7 @@ blur_xy2_kernel(const __grid_constant__ CUtensorMap in_map, float *__restrict__ 
                     *reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
             }
         }
+        fence_proxy_async();  // the x pass read stage s with LDS; TMA refills it behind the barrier
         __syncthreads();      // XB complete, stage s free: refill it with the tile after next
         if (t == 0) {
             const int nid = id + 2 * stride;

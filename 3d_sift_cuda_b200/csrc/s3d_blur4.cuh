@@ -168,6 +168,7 @@ blur_f4_kernel(const __grid_constant__ CUtensorMap in_map, const float *__restri
                 for (int k = 0; k < KX / 4; k++)
                     *reinterpret_cast<float4 *>(dst + 4 * k) = make_float4(o[2 * k].x, o[2 * k].y, o[2 * k + 1].x, o[2 * k + 1].y);
             }
+            fence_proxy_async();     // this warp's reads of the ring stage come before its later TMA refill
             __syncwarp();
             if (lane == 0) mbar_arrive(&xb_full[xbs]);
             if (++stage == NS) { stage = 0; sphase ^= 1; }
@@ -212,6 +213,7 @@ blur_f4_kernel(const __grid_constant__ CUtensorMap in_map, const float *__restri
                     for (int k = 0; k < KY; k++) if (k < rows_ok) mn[k] = ldgv<VT>(in + off + (long long)k * pitch);
                 }
             }
+            if (MRING) fence_proxy_async();     // the minuend was read from a ring stage that TMA refills after this arrival
             __syncwarp();
             if (lane == 0) mbar_arrive(&xb_empty[xbs]);
             if (++xbs == kF4NXB) { xbs = 0; xphase ^= 1; }

@@ -177,6 +177,9 @@ struct Tuning {
     bool stamps = false;         // S3D_STAMPS=1: %globaltimer stamps around the graph (s3d_debug_stamps)
     int prof_skip = 0;           // S3D_PROF_SKIP (profiling only, results invalid): 1 no keypoint tail, 2 no detection/refinement, 4 no describe, 8 no orient_b
     int f4_max_r = 6;            // S3D_F4_MAXR: one-kernel level (s3d_blur4.cuh) for radii up to this; wider levels use x+y / z kernels (s3d_blur2.cuh)
+    long long f4_min_voxels = 2000000;   // S3D_F4_MIN_VOXELS: smaller volumes (octaves >= 1 at MNI size) use the x+y / z kernels: the one-kernel level walks its
+                                 // z segment plane by plane, a latency chain that a small volume cannot hide behind other CTAs (measured: 11-25 us against 4 + 6 us)
+    long long detect2_min_voxels = 1500000;   // S3D_DETECT2_MIN_VOXELS: smaller volumes run the single-kernel extremum test instead of face test + full test
     int f4_ty = 16;              // S3D_F4_TY=16|32: tile rows of the one-kernel level (two / one resident CTAs per SM)
     int f4_ctas = 0;             // S3D_F4_CTAS: CTAs the one-kernel level aims for (0 = resident CTAs per SM x SMs)
     int xy2_ctas = 2;            // S3D_XY2_CTAS_PER_SM: persistent x+y CTAs per SM (contexts of an s3d_batch use 1)
@@ -209,6 +212,8 @@ static Tuning tuning_from_env()
     int v = env_int("S3D_F4_MAXR", t.f4_max_r);
     if (v >= 0) t.f4_max_r = v < kF4MaxR ? v : kF4MaxR;
     if (env_int("S3D_F4_TY", 16) == 32) t.f4_ty = 32;
+    { const char *mv = getenv("S3D_F4_MIN_VOXELS"); if (mv && mv[0]) t.f4_min_voxels = atoll(mv); }
+    { const char *mv = getenv("S3D_DETECT2_MIN_VOXELS"); if (mv && mv[0]) t.detect2_min_voxels = atoll(mv); }
     t.f4_ctas = env_int("S3D_F4_CTAS", 0);
     v = env_int("S3D_XY2_CTAS_PER_SM", 0);
     if (v >= 1 && v <= 4) { t.xy2_ctas = v; t.xy2_ctas_forced = true; }
@@ -445,7 +450,7 @@ static bool launch_blur_fast(s3d_ctx *ctx, const float *in, float *tmp, float *o
     if (plane * Z >= (1ll << 31)) return false;
     const Tuning &tn = ctx->tune;
     if constexpr (R <= kF4MaxR) {
-        if (R <= tn.f4_max_r &&
+        if (R <= tn.f4_max_r && plane * Z >= tn.f4_min_voxels &&
             (tn.f4_ty == 32 ? launch_blur_f4<R, 32>(ctx->cur, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, tn.f4_ctas, err)
                             : launch_blur_f4<R, 16>(ctx->cur, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, tn.f4_ctas, err))) {
             ctx->launches += 1;
@@ -636,7 +641,8 @@ static s3d_status detect_two_pass(s3d_ctx *ctx, const float *finer, const float 
                                   int own0, int own1)
 {
     if (X < 3 || Y < 3 || Z < 3) return S3D_OK;
-    if ((long long)pitch * Y * Z >= (1ll << 32))      // 32-bit voxel offsets
+    // 32-bit voxel offsets in the face list; small volumes: one launch instead of two latency-bound ones
+    if ((long long)pitch * Y * Z >= (1ll << 32) || (long long)pitch * Y * Z < ctx->tune.detect2_min_voxels)
         return detect_raw_launch(ctx, finer, centre, X, Y, Z, pitch, raw_min, n_min, raw_max, n_max, cap, own0, own1);
     const int n_zblocks = (Z - 2 + kDetectZ - 1) / kDetectZ;
     dim3 block(32, 8), grid((X - 2 + 31) / 32, (Y - 2 + 7) / 8, n_zblocks);

@@ -28,6 +28,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Orders this thread's earlier generic-proxy accesses to shared memory (LDS / STS) before later async-proxy
+// accesses (TMA) to the same bytes.  Needed by every thread that READ a staging buffer with LDS before it signals
+// (mbarrier arrive, __syncthreads) that the buffer may be refilled by TMA: without it the refill can overtake
+// loads that are still queued -- seen as sporadically wrong DoG minuends at 512^3+ when other kernels shared the SMs.
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 // one (box_w, box_h, 1) box of a 3-D tensor map into shared memory; elements outside the tensor are zero-filled
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar)
 {

@@ -200,10 +200,10 @@ def test_octave_run_from_level0_matches_whole(pkg, engine):
     assert len(want) > 0 and tail.tobytes() == want.tobytes()
 
 
-@pytest.mark.parametrize("env", [{}, {"S3D_F4_MAXR": "8"}, {"S3D_F4_MAXR": "0"},
+@pytest.mark.parametrize("env", [{"S3D_F4_MIN_VOXELS": "0"}, {"S3D_F4_MAXR": "8", "S3D_F4_MIN_VOXELS": "0"}, {"S3D_F4_MAXR": "0"},
                                  {"S3D_F4_MAXR": "0", "S3D_Z2_VEC": "2", "S3D_XY2_TX": "32", "S3D_XY2_TY": "48"},
                                  {"S3D_F4_MAXR": "0", "S3D_Z2_VEC": "4", "S3D_MARCH_TARGET": "200000"},
-                                 {"S3D_F4_MAXR": "0", "S3D_XY2_KY": "8"}, {"S3D_F4_MAXR": "3", "S3D_F4_CTAS": "400"}, {"S3D_F4_TY": "32"}])
+                                 {"S3D_F4_MAXR": "0", "S3D_XY2_KY": "8"}, {"S3D_F4_MAXR": "3", "S3D_F4_CTAS": "400", "S3D_F4_MIN_VOXELS": "0"}, {"S3D_F4_TY": "32", "S3D_F4_MIN_VOXELS": "0"}])
 def test_every_blur_path_bit_exact(pkg, oracle, monkeypatch, env):
     """Each selectable blur path -- the one-kernel level (s3d_blur4.cuh) with 4 and 2 rows per thread and with
     short z segments, the x+y / z kernels (s3d_blur2.cuh) with 2 and 4 columns per thread, forced tiles, 8-output
@@ -345,7 +345,7 @@ def test_baseline_configs_full_size_bit_exact(pkg, oracle, engine, config, descr
     assert (np.sort(feats["pc"], axis=1) == np.arange(64, dtype=np.float32)).all()
 
 
-@pytest.mark.parametrize("env", [{}, {"S3D_F4_MAXR": "8"}, {"S3D_F4_MAXR": "0"}])
+@pytest.mark.parametrize("env", [{}, {"S3D_F4_MIN_VOXELS": "0", "S3D_DETECT2_MIN_VOXELS": "0"}, {"S3D_F4_MAXR": "0"}])
 def test_negative_zero_voxels_bit_exact(pkg, oracle, monkeypatch, env):
     """Masked images carry -0.0 voxels (negative value x 0).  The reference starts every tap sum from +0.0
     (GaussBlur3D.cpp:54-58), so a window of -0.0 voxels blurs to +0.0: the levels must match bit for bit."""
@@ -452,3 +452,24 @@ def test_multi_batch_matches_single(pkg, engine):
     assert len(rows) == 7
     for v, r in zip(vols, rows):
         assert r.tobytes() == engine.extract(v).tobytes()
+
+
+def test_large_volume_is_deterministic_and_path_independent(pkg, monkeypatch):
+    """512^3 pyramid (256^3 with -2+): the one-kernel blur levels run concurrently with the other octaves' kernels.
+    Repeated runs must give identical rows, equal to the x+y / z kernel path (a missing generic->async proxy fence
+    before the TMA refill of a ring stage once showed up only at this scale, as sporadically wrong DoG voxels)."""
+    vol = pkg.phantom.brain_phantom((256, 256, 256), 1, 1000)
+    prm = pkg.Params(double_mode=1, max_keypoints=1 << 16, max_features=1 << 19)
+    eng = pkg.Engine(0)
+    try:
+        runs = [eng.extract(vol, prm) for _ in range(3)]
+    finally:
+        eng.close()
+    assert len(runs[0]) > 1000
+    assert all(r.tobytes() == runs[0].tobytes() for r in runs)
+    monkeypatch.setenv("S3D_F4_MAXR", "0")
+    eng = pkg.Engine(0)
+    try:
+        assert eng.extract(vol, prm).tobytes() == runs[0].tobytes()
+    finally:
+        eng.close()
