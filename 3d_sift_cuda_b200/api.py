@@ -40,7 +40,7 @@ EXPORTS = [
     "s3d_extract_typed", "s3d_extract_typed_async", "s3d_batch_extract_typed",
     "s3d_write_features_bin", "s3d_read_features_text", "s3d_match", "s3d_match_device",
     "s3d_multi_create", "s3d_multi_destroy", "s3d_multi_last_error", "s3d_multi_gpu_count", "s3d_multi_batch_extract",
-    "s3d_multi_extract_slab", "s3d_resample_iso", "s3d_resample_iso_host",
+    "s3d_multi_extract_slab", "s3d_resample_iso", "s3d_resample_iso_host", "s3d_level_device_ptr",
 ]
 
 # NIfTI datatype codes accepted by the typed entry points (reference featExtract.cpp:18-77)
@@ -148,6 +148,7 @@ def load_library():
     L.s3d_multi_extract_slab.argtypes = [vp, vp, i, i, i, vp, C.POINTER(vp), C.POINTER(i)]
     L.s3d_resample_iso.argtypes = [vp, vp, i, i, i, i, vp, i, i, i, i, f, f, f]
     L.s3d_resample_iso_host.argtypes = [vp, vp, i, i, i, vp, i, i, i, f, f, f]
+    L.s3d_level_device_ptr.argtypes = [vp, i, i, i, C.POINTER(vp), C.POINTER(i), C.POINTER(i * 3)]
     L.s3d_host_alloc.argtypes = [C.c_size_t]
     L.s3d_host_alloc.restype = vp
     L.s3d_host_free.argtypes = [vp]

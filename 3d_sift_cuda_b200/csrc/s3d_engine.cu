@@ -146,6 +146,9 @@ struct Plan {
     float *tmp1 = nullptr;            // scratch of the initial blur (octave-0 size)
     float *oct_tmp[kMaxOct] = {};     // per-octave blur scratch (octaves run on concurrent branches)
     s3d_cand *cand_raw = nullptr;     // [list][cand_cap], list = (oct*3 + (c-1))*2 + is_max (atomic order)
+    s3d_cand *cand_sorted = nullptr;  // large volumes: the lists grouped by z plane (cand_bucket_kernel), else null
+    int *plane_off = nullptr;         // [list][plane_stride] plane offsets of the grouped lists
+    int plane_stride = 0;
     unsigned int *face[kMaxOct * 3] = {};   // per (octave, centre level): voxels passing the face test
     int face_cap[kMaxOct * 3] = {};
     int *face_counts = nullptr;
@@ -179,6 +182,7 @@ struct Tuning {
     int f4_max_r = 6;            // S3D_F4_MAXR: one-kernel level (s3d_blur4.cuh) for radii up to this; wider levels use x+y / z kernels (s3d_blur2.cuh)
     long long f4_min_voxels = 2000000;   // S3D_F4_MIN_VOXELS: smaller volumes (octaves >= 1 at MNI size) use the x+y / z kernels: the one-kernel level walks its
                                  // z segment plane by plane, a latency chain that a small volume cannot hide behind other CTAs (measured: 11-25 us against 4 + 6 us)
+    long long bucket_min_voxels = 16000000;   // S3D_BUCKET_MIN_VOXELS: from this pyramid size on the candidate lists are grouped by plane before they are ranked
     long long detect2_min_voxels = 1500000;   // S3D_DETECT2_MIN_VOXELS: smaller volumes run the single-kernel extremum test instead of face test + full test
     int f4_ty = 16;              // S3D_F4_TY=16|32: tile rows of the one-kernel level (two / one resident CTAs per SM)
     int f4_ctas = 0;             // S3D_F4_CTAS: CTAs the one-kernel level aims for (0 = resident CTAs per SM x SMs)
@@ -213,6 +217,7 @@ static Tuning tuning_from_env()
     if (v >= 0) t.f4_max_r = v < kF4MaxR ? v : kF4MaxR;
     if (env_int("S3D_F4_TY", 16) == 32) t.f4_ty = 32;
     { const char *mv = getenv("S3D_F4_MIN_VOXELS"); if (mv && mv[0]) t.f4_min_voxels = atoll(mv); }
+    { const char *mv = getenv("S3D_BUCKET_MIN_VOXELS"); if (mv && mv[0]) t.bucket_min_voxels = atoll(mv); }
     { const char *mv = getenv("S3D_DETECT2_MIN_VOXELS"); if (mv && mv[0]) t.detect2_min_voxels = atoll(mv); }
     t.f4_ctas = env_int("S3D_F4_CTAS", 0);
     v = env_int("S3D_XY2_CTAS_PER_SM", 0);
@@ -846,6 +851,12 @@ static s3d_status plan_fill(s3d_ctx *ctx, Plan *p, int X, int Y, int Z, const s3
     if (p->n_lists > 0) {
         PA(&p->cand_raw, (size_t)p->n_lists * p->cand_cap);
         PA(&p->kp_stage, (size_t)p->n_lists * p->cand_cap);
+        // volumes whose candidate lists can get long: group the lists by plane before ranking (12000 planes = 48 KB of counters)
+        if ((long long)X0 * Y0 * Z0 >= ctx->tune.bucket_min_voxels && Z0 + 2 <= 12000) {
+            p->plane_stride = Z0 + 2;
+            PA(&p->cand_sorted, (size_t)p->n_lists * p->cand_cap);
+            PA(&p->plane_off, (size_t)p->n_lists * p->plane_stride);
+        }
         PA(&p->stage_flags, (size_t)p->n_lists * p->cand_cap);
     }
     PA(&p->counts, p->n_lists + 8 + kMaxOct * 3);
@@ -994,7 +1005,12 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
                 }
                 if (c_ref >= 1 && !(ctx->tune.prof_skip & 2)) {
                     int l0 = (o * 3 + (c_ref - 1)) * 2;
-                    cand_refine_kernel<<<dim3(2, 32), 256, 0, sd>>>(p->pyr, L, l0, p->kp_stage, p->stage_flags, err);
+                    if (p->cand_sorted) {
+                        cand_bucket_kernel<<<2, 1024, (od.Z + 2) * sizeof(int), sd>>>(L, l0, od.Z, p->cand_sorted, p->plane_off, p->plane_stride);
+                        ctx->launches++;
+                    }
+                    cand_refine_kernel<<<dim3(2, p->cand_sorted ? 128 : 32), 256, 0, sd>>>(p->pyr, L, l0, p->kp_stage, p->stage_flags, err,
+                                                                                          p->cand_sorted, p->plane_off, p->plane_stride);
                     ctx->launches++;
                 }
                 if (j == 5) CK(cudaEventRecord(ctx->ev_done[o], sd));
@@ -1462,6 +1478,22 @@ extern "C" s3d_status s3d_get_level(s3d_ctx *ctx, int octave, int is_dog, int le
                              cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
+    return S3D_OK;
+}
+
+// Device pointer and row pitch (floats) of a pyramid level of the last extraction (valid until the next one on this
+// context): lets a caller feed planes of a level straight into a stage call (the slab orchestration subsamples its
+// own planes of level 3 in place instead of copying them out first).
+extern "C" s3d_status s3d_level_device_ptr(s3d_ctx *ctx, int octave, int is_dog, int level, const float **d_ptr, int *pitch, int dims[3])
+{
+    if (!ctx || !d_ptr) return S3D_ERR_INVALID;
+    if (!ctx->plan || !ctx->has_result) return fail(ctx, S3D_ERR_INVALID, "no extraction result");
+    Plan *p = ctx->plan;
+    if (octave < 0 || octave >= p->n_oct || level < 0 || level >= (is_dog ? 5 : 6)) return fail(ctx, S3D_ERR_INVALID, "bad octave / level");
+    const Vol &v = is_dog ? p->d[octave * 5 + level] : p->g[octave * 6 + level];
+    *d_ptr = v.p;
+    if (pitch) *pitch = v.pitch;
+    if (dims) { dims[0] = v.X; dims[1] = v.Y; dims[2] = v.Z; }
     return S3D_OK;
 }
 

@@ -525,9 +525,53 @@ struct ListDesc {            // list = (octave*3 + (c-1))*2 + is_max
 // One WARP per candidate: the lanes split the rank count over the list (coalesced 16-byte loads) and the 27
 // neighbours of the deferred validation; lanes 0..3 then run the four parabola fits (x, y, z, scale) side by
 // side.  (One thread per candidate made this kernel a 15-20 us latency chain: n sequential loads per thread.)
+// Large volumes: rank by counting over the whole list is O(n^2) (1.0 s of a 1.2 s extraction at 1024^3 with 2e5
+// candidates per list).  cand_bucket_kernel first groups a list by z plane -- one CTA per list: plane histogram in
+// shared memory, exclusive scan, scatter (order inside a plane is arbitrary) -- and writes the plane offsets; the
+// refinement kernel then counts only inside the candidate's plane: rank = plane_off[z] + #(same plane, smaller (y,x)).
+__global__ void __launch_bounds__(1024) cand_bucket_kernel(ListDesc L, int list_begin, int Z, s3d_cand *__restrict__ sorted,
+                                                           int *__restrict__ plane_off, int plane_stride)
+{
+    extern __shared__ int s_hist[];            // [Z + 1] counts -> exclusive offsets; then used as cursors
+    __shared__ int s_warp[32];
+    const int list = list_begin + blockIdx.x;
+    const int n = min(L.counts[list], L.cap);
+    const s3d_cand *raw = L.raw + (long long)list * L.cap;
+    s3d_cand *dst = sorted + (long long)list * L.cap;
+    int *poff = plane_off + (long long)list * plane_stride;
+    for (int z = threadIdx.x; z <= Z; z += blockDim.x) s_hist[z] = 0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) atomicAdd(&s_hist[raw[k].z], 1);
+    __syncthreads();
+    // exclusive scan over the Z + 1 plane counts, 1024 elements per round
+    int carry = 0;
+    for (int base = 0; base <= Z; base += blockDim.x) {
+        const int z = base + threadIdx.x;
+        const int v = z <= Z ? s_hist[z] : 0;
+        int x = v;
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+        if (lane == 31) s_warp[wid] = x;
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int w = 0; w < 32; w++) { if (w < wid) woff += s_warp[w]; tot += s_warp[w]; }
+        if (z <= Z) { const int ex = carry + woff + x - v; s_hist[z] = ex; poff[z] = ex; }
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) poff[Z + 1] = carry;
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const s3d_cand c = raw[k];
+        dst[atomicAdd(&s_hist[c.z], 1)] = c;
+    }
+}
+
 __global__ void __launch_bounds__(256) cand_refine_kernel(const __grid_constant__ PyramidDesc pyr, ListDesc L, int list_begin,
                                                           s3d_keypoint *__restrict__ stage, unsigned char *__restrict__ flags,
-                                                          int *err)
+                                                          int *err, const s3d_cand *__restrict__ sorted, const int *__restrict__ plane_off,
+                                                          int plane_stride)
 {
     const int list = list_begin + blockIdx.x;
     const int octave = list / 6, c = (list / 2) % 3 + 1, is_max = list & 1;
@@ -541,16 +585,34 @@ __global__ void __launch_bounds__(256) cand_refine_kernel(const __grid_constant_
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     for (int k = blockIdx.y * warps_per_block + (threadIdx.x >> 5); k < n; k += gridDim.y * warps_per_block) {
-        const s3d_cand cd = raw[k];
-        const long long key = ((long long)cd.z * Y + cd.y) * X + cd.x;
-        int cnt = 0;
-        for (int j = lane; j < n; j += 32) {
-            const s3d_cand q = raw[j];
-            cnt += (((long long)q.z * Y + q.y) * X + q.x) < key;
-        }
+        int rank;
+        s3d_cand cd;
+        if (sorted) {      // list grouped by plane: count inside the candidate's plane only
+            const s3d_cand *srt = sorted + (long long)list * L.cap;
+            const int *poff = plane_off + (long long)list * plane_stride;
+            cd = srt[k];
+            const int b0 = poff[cd.z], b1 = poff[cd.z + 1];
+            const int key = cd.y * X + cd.x;
+            int cnt = 0;
+            for (int j = b0 + lane; j < b1; j += 32) {
+                const s3d_cand q = srt[j];
+                cnt += (q.y * X + q.x) < key;
+            }
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-        const int rank = cnt;
+            for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+            rank = b0 + cnt;
+        } else {
+            cd = raw[k];
+            const long long key = ((long long)cd.z * Y + cd.y) * X + cd.x;
+            int cnt = 0;
+            for (int j = lane; j < n; j += 32) {
+                const s3d_cand q = raw[j];
+                cnt += (((long long)q.z * Y + q.y) * X + q.x) < key;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+            rank = cnt;
+        }
         const long long i = (long long)cd.z * plane + (long long)cd.y * pitch + cd.x;
         const float cv = cd.value;
         bool mine = true;

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <string>
@@ -30,6 +31,8 @@ namespace {
 constexpr int kSlabHalo = 48;        // planes of level 0 kept valid around the owned range, per octave: blur radii
                                      // 3+4+5+6+8 = 26, +1 detection/validation, + the 11^3 patch reach on level 3
 constexpr int kInitBlurRadius = 4;   // initial blur: 9 taps (7 after -2+), reference MultiScale.cpp:288-298
+
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 struct Barrier {                     // reusable host barrier for the per-GPU threads
     std::mutex m; std::condition_variable cv; int n = 1, waiting = 0; unsigned long gen = 0;
@@ -90,6 +93,16 @@ extern "C" s3d_status s3d_multi_create(int n_gpus, const int *devices, int conte
     for (int r = 0; r < n_gpus; r++) {
         s3d_status st = s3d_ctx_create(m->dev[r], &m->ctx[r]);
         if (st != S3D_OK) { m->err = m->ctx[r] ? s3d_last_error(m->ctx[r]) : "s3d_ctx_create failed"; return st; }
+    }
+    // the slab path allocates its per-octave staging buffers stream-ordered (cudaMallocAsync); keep what it frees in the
+    // pool instead of handing gigabytes back to the driver at every synchronisation (measured: 125-480 ms per call)
+    for (int r = 0; r < n_gpus; r++) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, m->dev[r]) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
     }
     // direct peer copies between neighbouring slabs when the hardware allows it (cudaMemcpyPeerAsync works either way)
     for (int r = 0; r + 1 < n_gpus; r++) {
@@ -232,6 +245,9 @@ static void slab_thread(SlabShared &S, int r)
     // keypoint capacity: data dependent; start from the slab's share of one keypoint per 2048 voxels and grow on demand
     long long vox = (long long)S.X0 * S.Y0 * (S.Z0 / n + 2 * halo);
     int kp_cap = S.prm.max_keypoints > 0 ? S.prm.max_keypoints : (int)std::min<long long>(1 << 20, std::max<long long>(16384, vox / 2048));
+    const bool timing = getenv("S3D_SLAB_TIMING") != nullptr;      // per-phase host wall clock of every slab on stderr
+    double t_asm = 0, t_run = 0, t_next = 0, t_bar = 0, t0 = now_ms();
+    auto lap = [&](double &acc) { if (timing) { cudaStreamSynchronize(st); const double t = now_ms(); acc += t - t0; t0 = t; } };
     std::vector<void *> to_free;
     // Every octave has exactly two barrier waits per thread, reached whether or not a phase failed (a failing phase
     // records the error and returns; the other threads see S.failed() and skip their phases too).
@@ -282,26 +298,31 @@ static void slab_thread(SlabShared &S, int r)
         };
         auto next_level0 = [&]() {    // own part of the next octave's level 0: 2x2x2 mean of the own planes of level 3
             const int n_next = (own1 >> 1) - (own0 >> 1);
-            float *d_g3 = nullptr, *d_next = nullptr;
-            SLAB_CU(cudaMallocAsync((void **)&d_g3, sizeof(float) * plane * 2 * n_next, st));
-            to_free.push_back(d_g3);
+            float *d_next = nullptr;
+            const float *g3 = nullptr; int g3_pitch = 0;
             SLAB_CU(cudaMallocAsync((void **)&d_next, sizeof(float) * (size_t)(Xo / 2) * (Yo / 2) * n_next, st));
             S.own_g0[r] = d_next; S.own_n[r] = n_next;
-            SLAB_S3(s3d_copy_level_device(ctx, 0, 0, 3, own0 - z_off, own0 - z_off + 2 * n_next, d_g3));
-            SLAB_S3(s3d_subsample2(ctx, d_g3, Xo, Yo, 2 * n_next, Xo, d_next, Xo / 2));
+            SLAB_S3(s3d_level_device_ptr(ctx, 0, 0, 3, &g3, &g3_pitch, nullptr));
+            SLAB_S3(s3d_subsample2(ctx, g3 + (size_t)(own0 - z_off) * Yo * g3_pitch, Xo, Yo, 2 * n_next, g3_pitch, d_next, Xo / 2));
             SLAB_CU(cudaStreamSynchronize(st));
         };
         if (!S.failed()) assemble();
+        lap(t_asm);
         S.bar.wait();            // every slab holds its halos: the previous octave's own parts can go
+        lap(t_bar);
         if (o > 0 && S.own_g0[r]) { cudaFreeAsync(S.own_g0[r], st); S.own_g0[r] = nullptr; }
         if (!S.failed()) slab_run_octave(S, r, o, ctx, d_buf, Xo, Yo, nz, z_off, Zo, own0, own1, kp_cap);
+        lap(t_run);
         if (!S.failed()) next_level0();
+        lap(t_next);
         for (void *p : to_free) cudaFreeAsync(p, st);
         to_free.clear();
         S.bar.wait();            // every slab's next level 0 is complete
+        lap(t_bar);
         Xo /= 2; Yo /= 2; Zo /= 2;
     }
     cudaStreamSynchronize(st);
+    if (timing) fprintf(stderr, "s3d slab %d: assemble %.1f ms, octave run + fetch %.1f ms, next level 0 %.1f ms, barriers %.1f ms (K = %d, keypoint capacity %d)\n", r, t_asm, t_run, t_next, t_bar, K, kp_cap);
 }
 
 } // namespace
@@ -328,6 +349,8 @@ extern "C" s3d_status s3d_multi_extract_slab(s3d_multi *m, const float *h_volume
         return st;
     }
     const int K = S.K;
+    const bool timing = getenv("S3D_SLAB_TIMING") != nullptr;
+    double tt0 = now_ms();
     S.bar.n = n;
     S.own_g0.assign(n, nullptr); S.own_n.assign(n, 0);
     S.rows.assign(n, std::vector<s3d_feature *>(K, nullptr));
@@ -345,6 +368,7 @@ extern "C" s3d_status s3d_multi_extract_slab(s3d_multi *m, const float *h_volume
         if (S.tail) s3d_free(S.tail);
     };
     if (S.status != S3D_OK) { m->err = S.err; cleanup(); return S.status; }
+    const double t_slabs = now_ms() - tt0; tt0 = now_ms();
 
     // ---- collapse: the remaining octaves run on GPU 0 from the gathered level 0 of octave K
     const int Xk = S.X0 >> K, Yk = S.Y0 >> K, Zk = S.Z0 >> K;
@@ -373,6 +397,7 @@ extern "C" s3d_status s3d_multi_extract_slab(s3d_multi *m, const float *h_volume
         if (s != S3D_OK) { m->err = s3d_last_error(ctx); cleanup(); return s; }
     }
 
+    const double t_tail = now_ms() - tt0; tt0 = now_ms();
     // ---- merge: octave, level, minima then maxima, then slabs in z order (= raster order); offsets from the counts
     long long total = 0;
     S.off.assign(K, std::vector<std::vector<long long>>(6, std::vector<long long>(n, 0)));
@@ -401,6 +426,7 @@ extern "C" s3d_status s3d_multi_extract_slab(s3d_multi *m, const float *h_volume
         for (auto &t : th) t.join();
     }
     cleanup();
+    if (timing) fprintf(stderr, "s3d slab mode: slab octaves %.1f ms, collapsed tail %.1f ms, merge + cleanup %.1f ms, %lld rows\n", t_slabs, t_tail, now_ms() - tt0, total);
     *out = res;
     *n_out = (int)total;
     return S3D_OK;

@@ -227,6 +227,9 @@ s3d_status s3d_get_patches(s3d_ctx *ctx, float **patches, float **prerank, int *
  * (X*Y*(z1-z0) floats, the reference's layout).  Used by the slab orchestration to hand level 3 to the
  * next octave. */
 s3d_status s3d_copy_level_device(s3d_ctx *ctx, int octave, int is_dog, int level, int z0, int z1, float *d_dst);
+/* Device pointer, row pitch (floats) and dimensions of a pyramid level of the last extraction (valid until the next
+ * extraction on this context); dims = X, Y, Z of the buffer (slab mode: the local planes). */
+s3d_status s3d_level_device_ptr(s3d_ctx *ctx, int octave, int is_dog, int level, const float **d_ptr, int *pitch, int dims[3]);
 /* Per feature row of the last extraction: index of its keypoint (s3d_get_keypoints order). */
 s3d_status s3d_get_row_keypoints(s3d_ctx *ctx, int **row_kp, int *n_out);
 /* Number of kernel launches (graph nodes included) issued by the last extraction. */

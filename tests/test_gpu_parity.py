@@ -473,3 +473,18 @@ def test_large_volume_is_deterministic_and_path_independent(pkg, monkeypatch):
         assert eng.extract(vol, prm).tobytes() == runs[0].tobytes()
     finally:
         eng.close()
+
+
+def test_bucketed_candidate_ranking_bit_exact(pkg, oracle, monkeypatch):
+    """Large volumes rank their candidates inside z-plane buckets (cand_bucket_kernel) instead of over the whole
+    list; forced on for small volumes here, the rows must still be the oracle's, in the oracle's order."""
+    monkeypatch.setenv("S3D_BUCKET_MIN_VOXELS", "0")
+    eng = pkg.Engine(0)
+    try:
+        for vol, dm in ((pkg.phantom.blob_phantom((64, 64, 64), 0, 60), 0), (pkg.phantom.brain_phantom((91, 109, 91), 1, 100), 0),
+                        (pkg.phantom.blob_phantom((40, 44, 36), 31, 45), 1)):
+            want = oracle.extract(vol, dm, 0)["features"]
+            assert len(want) > 5
+            assert eng.extract(vol, pkg.Params(double_mode=dm)).tobytes() == want.tobytes()
+    finally:
+        eng.close()

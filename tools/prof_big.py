@@ -9,10 +9,10 @@ S = int(os.environ.get("PROF_SIZE", "512"))
 dm = int(os.environ.get("PROF_DOUBLE", "1"))
 blobs = int(os.environ.get("PROF_BLOBS", "8000"))
 t0 = time.perf_counter()
-vol = pkg.phantom.brain_phantom((S, S, S), 1, blobs)
+vol = pkg.phantom.brain_phantom((S, S, S), 1, blobs) if os.environ.get("PROF_KIND", "brain") == "brain" else pkg.phantom.blob_phantom((S, S, S), 17, blobs)
 print("phantom %.1f s" % (time.perf_counter() - t0), flush=True)
 e = pkg.Engine(0)
-prm = pkg.Params(double_mode=dm, max_keypoints=1 << 18, max_features=1 << 21)
+prm = pkg.Params(double_mode=dm, max_keypoints=1 << 19, max_features=1 << 22)
 for it in range(2):
     t0 = time.perf_counter()
     rows = e.extract(vol, prm)
