@@ -178,13 +178,14 @@ struct Tuning {
     bool serial = false;         // S3D_SERIAL=1: no octave / detection branches, every kernel on the main stream
     bool timing = false;         // S3D_STAGE_TIMING=1: no graph, events at stage boundaries of the main stream
     bool stamps = false;         // S3D_STAMPS=1: %globaltimer stamps around the graph (s3d_debug_stamps)
-    int prof_skip = 0;           // S3D_PROF_SKIP (profiling only, results invalid): 1 no keypoint tail, 2 no detection/refinement, 4 no describe, 8 no orient_b
+    int prof_skip = 0;           // S3D_PROF_SKIP (profiling only, results invalid): 1 no keypoint tail, 2 no detection/refinement, 4 no describe, 8 no orient_b, 16 no level-5 blur
     int f4_max_r = 6;            // S3D_F4_MAXR: one-kernel level (s3d_blur4.cuh) for radii up to this; wider levels use x+y / z kernels (s3d_blur2.cuh)
     long long f4_min_voxels = 2000000;   // S3D_F4_MIN_VOXELS: smaller volumes (octaves >= 1 at MNI size) use the x+y / z kernels: the one-kernel level walks its
                                  // z segment plane by plane, a latency chain that a small volume cannot hide behind other CTAs (measured: 11-25 us against 4 + 6 us)
     long long bucket_min_voxels = 16000000;   // S3D_BUCKET_MIN_VOXELS: from this pyramid size on the candidate lists are grouped by plane before they are ranked
     long long detect2_min_voxels = 1500000;   // S3D_DETECT2_MIN_VOXELS: smaller volumes run the single-kernel extremum test instead of face test + full test
     int f4_ty = 16;              // S3D_F4_TY=16|32: tile rows of the one-kernel level (two / one resident CTAs per SM)
+    bool f4_ctas_forced = false;
     int f4_ctas = 0;             // S3D_F4_CTAS: CTAs the one-kernel level aims for (0 = resident CTAs per SM x SMs)
     int xy2_ctas = 2;            // S3D_XY2_CTAS_PER_SM: persistent x+y CTAs per SM (contexts of an s3d_batch use 1)
     bool xy2_ctas_forced = false;
@@ -220,6 +221,7 @@ static Tuning tuning_from_env()
     { const char *mv = getenv("S3D_BUCKET_MIN_VOXELS"); if (mv && mv[0]) t.bucket_min_voxels = atoll(mv); }
     { const char *mv = getenv("S3D_DETECT2_MIN_VOXELS"); if (mv && mv[0]) t.detect2_min_voxels = atoll(mv); }
     t.f4_ctas = env_int("S3D_F4_CTAS", 0);
+    t.f4_ctas_forced = t.f4_ctas > 0;
     v = env_int("S3D_XY2_CTAS_PER_SM", 0);
     if (v >= 1 && v <= 4) { t.xy2_ctas = v; t.xy2_ctas_forced = true; }
     v = env_int("S3D_XY2_SMEM_KB", t.xy2.max_kb);
@@ -976,7 +978,9 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
         if (o > 0) CK(cudaStreamWaitEvent(so, ctx->ev_fork[o - 1], 0));
         for (int j = 1; j < 6; j++) {
             Vol &a = p->g[o * 6 + j - 1], &b = p->g[o * 6 + j], &dd = p->d[o * 5 + j - 1];
-            s3d_status s = blur3d(ctx, a.p, p->oct_tmp[o], b.p, od.X, od.Y, od.Z, od.pitch, p->lvl_taps[j - 1], p->n_lvl_taps[j - 1], dd.p);
+            s3d_status s = S3D_OK;
+            if (!(j == 5 && (ctx->tune.prof_skip & 16)))      // profiling only: what the top level of every octave costs
+                s = blur3d(ctx, a.p, p->oct_tmp[o], b.p, od.X, od.Y, od.Z, od.pitch, p->lvl_taps[j - 1], p->n_lvl_taps[j - 1], dd.p);
             if (s != S3D_OK) { ctx->cur = st; return s; }
             if (j == 3 && o + 1 < p->n_oct) {
                 const OctaveDesc &nx = p->pyr.oct[o + 1];
@@ -1368,6 +1372,8 @@ extern "C" s3d_status s3d_batch_create(int device, int n_contexts, s3d_batch **o
         // provided by the other volumes in flight, and no halo planes are read twice (S3D_MARCH_TARGET overrides)
         if (c->tune.march_target == 0 && n_contexts > 1) c->tune.march_target = 1;
         if (!c->tune.detect_ctas_forced && n_contexts > 1) c->tune.detect_ctas = 4;
+        // the one-kernel blur level: one resident CTA per SM instead of two (measured 529 -> 509 us per volume with 6 contexts)
+        if (!c->tune.f4_ctas_forced && n_contexts > 1) c->tune.f4_ctas = c->sm_count;
         b->ctx.push_back(c);
     }
     *out = b;

@@ -334,12 +334,12 @@ def run_ours(args):
     del dst
     clocks = sampler.stop() if rank == 0 else None   # sampled across all timed regions
 
-    # ---- roofline of the dominant stage: the blur levels of octave 0 (x+y kernel, z kernel with fused DoG) ----
+    # ---- roofline of the dominant stage: the blur levels of octave 0 (one-kernel level up to 13 taps; x+y kernel + z kernel at 17) ----
     # Algorithmic bytes of a level = read G_{j-1}, write G_j, write DoG = 12 B/voxel (the initial blur writes no
     # DoG: 8 B/voxel).  Each level is timed alone with CUDA events on the engine's stream, L2 flushed before
     # every launch (cold) and back to back in a -> b -> a chains (warm, as inside the pipeline).  The headline
     # entry is the heaviest level (17 taps); `levels` lists all six.  `traffic` = dram bytes read + written per
-    # level from the ncu --set full capture summarised in profiles/r1_blur_level_traffic.json.
+    # level from the ncu --set full capture summarised in profiles/r2_blur_level_traffic.json.
     roof = None
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -350,7 +350,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         traffic = {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_blur_level_traffic.json")))["levels"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_blur_level_traffic.json")))["levels"]
         except Exception:
             pass
         levels = []
@@ -383,8 +383,8 @@ def run_ours(args):
             cold = sum(x.elapsed_time(y) for x, y in lev) / reps
             warm = e0.elapsed_time(e1) / reps
             alg = (12.0 if with_dog else 8.0) * N0
-            tr = traffic.get(str(len(taps))) if with_dog else None      # the capture ran every level with the DoG output
-            levels.append({"level": name, "taps": len(taps), "algorithmic_bytes": alg, "ms_cold": cold, "ms_warm": warm,
+            tr = traffic.get(name)      # ncu capture of the same stage-level call (every level run with its DoG output)
+            levels.append({"level": name, "taps": len(taps), "kernels": (tr or {}).get("kernels"), "algorithmic_bytes": alg, "ms_cold": cold, "ms_warm": warm,
                            "achieved_cold": alg / (cold * 1e-3) / 1e9, "frac_cold": alg / (cold * 1e-3) / 1e9 / peak,
                            "achieved_warm": alg / (warm * 1e-3) / 1e9, "frac_warm": alg / (warm * 1e-3) / 1e9 / peak,
                            "traffic": (tr["dram_read"] + tr["dram_write"]) if tr else None})
@@ -395,7 +395,8 @@ def run_ours(args):
         tot_ms = sum(l["ms_cold"] for l in levels)
         roof = {"bound": "hbm", "achieved": top["achieved_cold"], "peak": peak, "unit": "GB/s", "frac": top["frac_cold"],
                 "traffic": top["traffic"],
-                "kernel": "blur level 4->5 (blur_xy2_kernel<8> + blur_z2_kernel<8,DoG>: x, y, z passes, 17 taps, fused DoG) at 182x218x182, L2 flushed before each launch",
+                "kernel": "blur level 4->5 (blur_xy2_kernel<8,16> + blur_z2_kernel<8,DoG,float2>: x, y, z passes, 17 taps, fused DoG) at 182x218x182, L2 flushed before each launch; "
+                          "levels 0-4 (7-13 taps) run the one-kernel level blur_f4_kernel, see `levels`",
                 "ms_per_launch": top["ms_cold"], "algorithmic_bytes": top["algorithmic_bytes"], "peak_source": peak_src,
                 "levels": levels,
                 "octave0_blur_chain": {"algorithmic_bytes": tot_alg, "ms": tot_ms, "achieved": tot_alg / (tot_ms * 1e-3) / 1e9,

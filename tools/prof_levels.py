@@ -30,7 +30,7 @@ for cfg in configs:
     cold, warm = [], []
     for s in sigmas:
         taps = pkg.gaussian_taps(s)
-        for _ in range(3):
+        for _ in range(0 if os.environ.get("NCU_ONE") else 3):
             e.blur3d(a, tmp, b, X, taps, dog)
         e.sync()
         ms = 0.0
@@ -42,7 +42,9 @@ for cfg in configs:
                 e.sync()
                 ms += e0.elapsed_time(e1)
         cold.append(ms / REPS * 1e3)
-        N = 20
+        N = 0 if os.environ.get("NCU_ONE") else 20
+        if N == 0:
+            warm.append(float('nan')); continue
         with torch.cuda.stream(st):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(st)
