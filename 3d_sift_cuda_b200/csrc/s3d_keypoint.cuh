@@ -1127,18 +1127,22 @@ __global__ void __launch_bounds__(1024) row_offsets_kernel(const int *__restrict
 // orientation, then the descriptor loop of featExtract's main() (reference featExtract.cpp:477-505):
 // NormalizeData, descriptor, rank transform, size factor.
 // ------------------------------------------------------------------------------------------------
+// A CTA describes kDescGroup rows per round: their patches are gathered one after the other by all threads, then
+// NORMALISED TOGETHER -- the two 1331-term sequential sums of Feature3D::NormalizeData must be walked by one thread
+// each (parity), so one thread per row walks them side by side instead of one thread for one row while the CTA
+// waits (normalize was 32 % of this kernel, profiles/r1_phases_e_current.txt) -- then described one after the other.
+constexpr int kDescGroup = 4;
 struct DescribeSmem {
-    float patch[PVP];
+    float patch[kDescGroup][PVP];
     float dx[PVP], dy[PVP], dz[PVP];   // SIFT: gradients -> (mag, bin); BRIEF: blur scratch
     float taps[12];
     float wlo[12];
     float inv[9];
-    float ori[9];
-    float red[2];
+    float ori[kDescGroup][9];
+    float red[kDescGroup][2];
     float pc[64];
     float pc2[64];
 };
-
 __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ PyramidDesc pyr,
                                                        const s3d_keypoint *__restrict__ kps, const int *__restrict__ n_features,
                                                        const int *__restrict__ row_map,
@@ -1157,7 +1161,12 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ P
         S.wlo[threadIdx.x] = threadIdx.x < PD ? c_tab.desc_w[threadIdx.x] : 0.0f;
     }
     PHASE_INIT();
-    for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    for (int row0 = blockIdx.x * kDescGroup; row0 < n_rows; row0 += gridDim.x * kDescGroup) {
+      const int ng = min(kDescGroup, n_rows - row0);
+      // ---- phase A: orientation + patch of every row of the group
+      for (int g = 0; g < ng; g++) {
+        const int row = row0 + g;
         const int wi = row_map[row];
         const int kpi = wi / kMaxRowsPerKp, r = wi % kMaxRowsPerKp;
         __syncthreads();
@@ -1174,27 +1183,59 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ P
                 src = kp_rots + (((long long)kpi * PD + pi) * PD + left) * 9;
             }
             float m[9];
-            for (int q = 0; q < 9; q++) { m[q] = src[q]; S.ori[q] = m[q]; }
+            for (int q = 0; q < 9; q++) { m[q] = src[q]; S.ori[g][q] = m[q]; }
             if (r > 0) invert3(m, S.inv);
         }
         PHASE(16);
 
         if (r == 0) {
-            for (int i = threadIdx.x; i < PV; i += blockDim.x) S.patch[i] = kp_patch0[(long long)kpi * PV + i];
+            for (int i = threadIdx.x; i < PV; i += blockDim.x) S.patch[g][i] = kp_patch0[(long long)kpi * PV + i];
         } else {
             __syncthreads();
-            gather_patch(o.g[kp.level], o.X, o.Y, o.Zg, o.z_off, o.pitch, kp.x, kp.y, kp.z, kp.scale, S.inv, S.patch);
+            gather_patch(o.g[kp.level], o.X, o.Y, o.Zg, o.z_off, o.pitch, kp.x, kp.y, kp.z, kp.scale, S.inv, S.patch[g]);
         }
         __syncthreads();
-        if (dbg_patches) for (int i = threadIdx.x; i < PV; i += blockDim.x) dbg_patches[(long long)row * PV + i] = S.patch[i];
+        if (dbg_patches) for (int i = threadIdx.x; i < PV; i += blockDim.x) dbg_patches[(long long)row * PV + i] = S.patch[g][i];
         PHASE(17);
-
-        normalize_patch(S.patch, S.dx, S.red);
-        PHASE(18);
+      }
+      // ---- phase B: Feature3D::NormalizeData (reference MultiScale.cpp:127-205) of the whole group: lane 0 of warp w
+      //      walks the sequential sums of rows w, w + n_warps, ...; same operations in the same order as
+      //      normalize_patch (mean, v = p - mean, sum of v*v, p = v * (1 / sqrt(sum)))
+      __syncthreads();
+      if (lane == 0)
+          for (int g = warp; g < ng; g += n_warps) {
+              const float *p = S.patch[g];
+              const float mean = seq_sum(p, PV) / (float)(PD * PD * PD);
+              float e = 0.0f;
+              int i = 0;
+              for (; i + 4 <= PV; i += 4) {
+                  const float4 u = *reinterpret_cast<const float4 *>(p + i);
+                  const float v0 = u.x - mean, v1 = u.y - mean, v2 = u.z - mean, v3 = u.w - mean;
+                  e = e + v0 * v0; e = e + v1 * v1; e = e + v2 * v2; e = e + v3 * v3;
+              }
+              for (; i < PV; i++) { const float v = p[i] - mean; e = e + v * v; }
+              S.red[g][0] = mean;
+              S.red[g][1] = 1.0f / sqrtf(e);
+          }
+      __syncthreads();
+      for (int g = 0; g < ng; g++) {
+          const float mean = S.red[g][0], fDiv = S.red[g][1];
+          for (int i = threadIdx.x; i < PV; i += blockDim.x) { const float v = S.patch[g][i] - mean; S.patch[g][i] = v * fDiv; }
+      }
+      __syncthreads();
+      PHASE(18);
+      // ---- phase C: descriptor of every row of the group
+      for (int g = 0; g < ng; g++) {
+        const int row = row0 + g;
+        const int wi = row_map[row];
+        const int kpi = wi / kMaxRowsPerKp, r = wi % kMaxRowsPerKp;
+        const s3d_keypoint kp = kps[kpi];
+        float *const patch = S.patch[g];
+        __syncthreads();
 
         if (descriptor == S3D_DESC_SIFT) {
             // msResampleFeaturesGradientOrientationHistogram (reference MultiScale.cpp:583-710)
-            patch_gradients(S.patch, S.dx, S.dy, S.dz);
+            patch_gradients(patch, S.dx, S.dy, S.dz);
             for (int i = threadIdx.x; i < PV; i += blockDim.x) {
                 float e[3] = { S.dx[i], S.dy[i], S.dz[i] };
                 float fEdgeMag = vec_mag(e);
@@ -1262,7 +1303,7 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ P
             __syncthreads();
         } else {
             // msResampleFeaturesBRIEF (reference MultiScale.cpp:989-1049), blur with CPU semantics
-            blur_patch(S.patch, S.dy, S.dx, S.taps, c_tab.n_brief_taps);
+            blur_patch(patch, S.dy, S.dx, S.taps, c_tab.n_brief_taps);
             if (threadIdx.x < 64) {
                 float d = S.dx[c_tab.brief_a[threadIdx.x]] - S.dx[c_tab.brief_b[threadIdx.x]];
                 float v;
@@ -1297,10 +1338,11 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ P
             f->flag = (kp.is_max ? 0x10u : 0u) | (r > 0 ? 0x20u : 0u);
             f->x = x * size_factor; f->y = y * size_factor; f->z = z * size_factor; f->scale = sc * size_factor;
             for (int q = 0; q < 3; q++) f->eigs[q] = kp_eigs[kpi * 3 + q];
-            for (int q = 0; q < 9; q++) f->ori[q] = S.ori[q];
+            for (int q = 0; q < 9; q++) f->ori[q] = S.ori[g][q];
         }
         if (threadIdx.x < 64) f->pc[threadIdx.x] = S.pc2[threadIdx.x];
         PHASE(21);
+      }
     }
 }
 
