@@ -158,8 +158,8 @@ struct Plan {
     int n_lists = 0;
     s3d_keypoint *kps = nullptr;
     int *nrows = nullptr, *row_off = nullptr;
-    float *kp_eigs = nullptr, *kp_ori0 = nullptr, *kp_rots = nullptr, *kp_patch0 = nullptr, *kp_p1 = nullptr;
-    int *kp_nprim = nullptr, *kp_nsec = nullptr, *work_b = nullptr, *row_map = nullptr;
+    float *kp_eigs = nullptr, *kp_ori0 = nullptr, *kp_rots = nullptr, *kp_patch0 = nullptr, *kp_p1 = nullptr, *kp_fmat = nullptr;
+    int *kp_nprim = nullptr, *kp_nsec = nullptr, *work_a = nullptr, *work_b = nullptr, *row_map = nullptr;
     s3d_feature *feats = nullptr;
     float *dbg_patches = nullptr, *dbg_prerank = nullptr;
     PyramidDesc pyr;
@@ -332,8 +332,10 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
     }
     KpTables t;
     build_tables(t);
+    if (t.n_sphere != kSph) return fail(ctx, S3D_ERR_INVALID, "sphere table size");   // the keypoint kernels size their shared memory for it
     CK(cudaMemcpyToSymbol(c_tab, &t, sizeof(t)));
-    CK(cudaFuncSetAttribute(orient_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HistSmem)));
+    CK(cudaFuncSetAttribute(orient_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PatchSmem)));
+    CK(cudaFuncSetAttribute(orient_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HistSmem)));
     CK(cudaFuncSetAttribute(orient_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HistSmem)));
     CK(cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DescribeSmem)));
     CK(cudaMallocHost((void **)&ctx->h_counts, 4 * sizeof(int)));
@@ -877,6 +879,8 @@ static s3d_status plan_fill(s3d_ctx *ctx, Plan *p, int X, int Y, int Z, const s3
     PA(&p->row_off, kp_cap);
     PA(&p->kp_eigs, (size_t)kp_cap * 3);
     PA(&p->kp_ori0, (size_t)kp_cap * 9);
+    PA(&p->kp_fmat, (size_t)kp_cap * 9);
+    PA(&p->work_a, kp_cap);
     PA(&p->kp_rots, (size_t)kp_cap * PD * PD * 9);
     PA(&p->kp_p1, (size_t)kp_cap * PD * 3);
     PA(&p->kp_nprim, kp_cap);
@@ -1030,12 +1034,17 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     mark(ctx, "compact");
     // orientation: per keypoint, then per (keypoint, primary direction)
     float eig = prm->eig_thres;
-    int *work_b_count = kp_count + 3;
-    orient_a_kernel<<<ctx->sm_count * ctx->tune.tail_a, 256, sizeof(HistSmem), st>>>(p->pyr, p->kps, kp_count, eig, p->kp_nprim, p->kp_eigs,
-                                                                     p->kp_ori0, p->kp_p1, p->kp_patch0, p->work_b, work_b_count);
-    mark(ctx, "orient_a");
+    int *work_b_count = kp_count + 3, *work_a_count = kp_count + 4;
+    orient_patch_kernel<<<ctx->sm_count * ctx->tune.tail_a, 256, sizeof(PatchSmem), st>>>(p->pyr, p->kps, kp_count, p->kp_patch0, p->kp_fmat);
+    int grid_svd = (p->kp_cap + 31) / 32;
+    if (grid_svd > ctx->sm_count * 32) grid_svd = ctx->sm_count * 32;
+    orient_svd_kernel<<<grid_svd, 32, 0, st>>>(p->kp_fmat, kp_count, eig, p->kp_eigs, p->kp_ori0, p->kp_nprim, p->work_a, work_a_count);
+    orient_hist_kernel<<<ctx->sm_count * ctx->tune.tail_a, kHistThreads, sizeof(HistSmem), st>>>(p->work_a, work_a_count, p->kp_patch0, p->kp_nprim,
+                                                                                                  p->kp_p1, p->work_b, work_b_count);
+    ctx->launches += 2;
+    mark(ctx, "orient_patch+svd+hist");
     if (ctx->tune.prof_skip & 8) { CK(cudaGetLastError()); return S3D_OK; }
-    orient_b_kernel<<<ctx->sm_count * ctx->tune.tail_b, 256, sizeof(HistSmem), st>>>(p->work_b, work_b_count, p->kp_p1, p->kp_patch0, p->kp_nsec, p->kp_rots);
+    orient_b_kernel<<<ctx->sm_count * ctx->tune.tail_b, kHistThreads, sizeof(HistSmem), st>>>(p->work_b, work_b_count, p->kp_p1, p->kp_patch0, p->kp_nsec, p->kp_rots);
     mark(ctx, "orient_b");
     row_offsets_kernel<<<1, 1024, 0, st>>>(p->kp_nprim, p->kp_nsec, kp_count, p->nrows, p->row_off, p->row_map, n_features, p->row_cap, err);
     float size_factor = 1.0f;

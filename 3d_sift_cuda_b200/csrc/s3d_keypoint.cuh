@@ -186,8 +186,9 @@ __device__ __forceinline__ float vec_dot(const float *a, const float *b) { retur
 constexpr int PVP = 1332;   // patch arrays are padded to a multiple of 4 floats so each starts 16-byte aligned
 
 // sampleImage3D (reference MultiScale.cpp:2614-2714): inv = inverse orientation, already in smem.
-// Each thread owns up to 6 samples; the loop is fully unrolled and branch-light so the 8 corner loads of
-// all of a thread's samples are in flight together (the gather is pure latency otherwise).
+// A thread takes U samples per round; the round is fully unrolled and branch-light so the 8 corner loads of all U
+// samples are in flight together (the gather is pure latency otherwise).
+template <int U = 4>
 __device__ void gather_patch(const float *__restrict__ img, int X, int Y, int Zg, int z_off, int pitch,
                              float fx, float fy, float fz, float scale, const float *inv, float *patch)
 {
@@ -195,11 +196,11 @@ __device__ void gather_patch(const float *__restrict__ img, int X, int Y, int Zg
     const float fScale = fImageRad / (float)(PD / 2);
     const float m00 = inv[0], m01 = inv[1], m02 = inv[2], m10 = inv[3], m11 = inv[4], m12 = inv[5], m20 = inv[6], m21 = inv[7], m22 = inv[8];
     const long long plane = (long long)pitch * Y;
-    for (int i0 = threadIdx.x; i0 < PV; i0 += 2 * blockDim.x) {
-        float v[2][8], w[2][3];
-        bool inside[2], live[2];
+    for (int i0 = threadIdx.x; i0 < PV; i0 += U * blockDim.x) {
+        float v[U][8], w[U][3];
+        bool inside[U], live[U];
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
+        for (int u = 0; u < U; u++) {
             int i = i0 + u * blockDim.x;
             live[u] = i < PV;
             int ii = live[u] ? i : 0;
@@ -221,7 +222,7 @@ __device__ void gather_patch(const float *__restrict__ img, int X, int Y, int Zg
             v[u][4] = __ldg(p + plane); v[u][5] = __ldg(p + plane + 1); v[u][6] = __ldg(p + plane + pitch); v[u][7] = __ldg(p + plane + pitch + 1);
         }
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
+        for (int u = 0; u < U; u++) {
             float wx = w[u][0], wy = w[u][1], wz = w[u][2];
             float fn00 = wx * v[u][0] + (1.0f - wx) * v[u][1];
             float fn01 = wx * v[u][4] + (1.0f - wx) * v[u][5];
@@ -310,6 +311,47 @@ __device__ void blur_patch(const float *src, float *tmp, float *dst, const float
         float s = 0.0f;
         for (int j = 0; j < ntaps; j++) { int p = z + j - r; float v = (p >= 0 && p < PD) ? tmp[i + (j - r) * PD * PD] : 0.0f; s = s + taps[j] * v; }
         dst[i] = s;
+    }
+    __syncthreads();
+}
+
+// The same blur for 3 taps (the orientation histograms: sigma 0.5) in ONE pass without scratch: an output voxel
+// recomputes the x sums of its 9 (y,z) neighbours and the y sums of its 3 z neighbours in registers.  Every sum is the
+// expression of the three-pass form (0.0f first, taps left to right, out-of-range inputs contribute taps[j] * 0.0f,
+// which leaves a sum that started at +0.0 unchanged), so the bits are the same; two block barriers and two
+// shared-memory round trips are gone.
+__device__ void blur_patch3(const float *src, float *dst, const float *taps)
+{
+    const float t0 = taps[0], t1 = taps[1], t2 = taps[2];
+    __syncthreads();
+    for (int i = threadIdx.x; i < PV; i += blockDim.x) {
+        const int x = i % PD, y = (i / PD) % PD, z = i / (PD * PD);
+        float zs = 0.0f;
+#pragma unroll
+        for (int jz = 0; jz < 3; jz++) {
+            const int pz = z + jz - 1;
+            float vz = 0.0f;
+            if (pz >= 0 && pz < PD) {
+                float ys = 0.0f;
+#pragma unroll
+                for (int jy = 0; jy < 3; jy++) {
+                    const int py = y + jy - 1;
+                    float vy = 0.0f;
+                    if (py >= 0 && py < PD) {
+                        const float *row = src + (pz * PD + py) * PD;
+                        float xs = 0.0f;
+                        xs = xs + t0 * (x >= 1 ? row[x - 1] : 0.0f);
+                        xs = xs + t1 * row[x];
+                        xs = xs + t2 * (x + 1 < PD ? row[x + 1] : 0.0f);
+                        vy = xs;
+                    }
+                    ys = ys + (jy == 0 ? t0 : jy == 1 ? t1 : t2) * vy;
+                }
+                vz = ys;
+            }
+            zs = zs + (jz == 0 ? t0 : jz == 1 ? t1 : t2) * vz;
+        }
+        dst[i] = zs;
     }
     __syncthreads();
 }
@@ -701,67 +743,199 @@ __global__ void __launch_bounds__(1024) compact_kernel(ListDesc L, const s3d_key
 
 // ------------------------------------------------------------------------------------------------
 // Orientation assignment (reference generateFeature3D MultiScale.cpp:1705-1862, determineOrientation3D
-// :2541-2607, determineCanonicalOrientation3D :2722-3037), split in two kernels so that the secondary
-// histograms of different primary peaks run as separate CTAs:
-//   orient_a_kernel  one CTA per keypoint: identity patch, normalise, gradients, structure tensor + SVD,
-//                    eigenvalue test, primary direction histogram, its peaks -> up to 11 primary directions
-//   orient_b_kernel  one CTA per (keypoint, primary direction): secondary histogram, peaks -> rotations
+// :2541-2607, determineCanonicalOrientation3D :2722-3037), split BY PHASE so that work which parity forces onto
+// one thread never parks a whole CTA and its shared memory (round 1: one 256-thread CTA with 60 KB per keypoint,
+// 100 K cycles of which 50 K waited for one warp's sequential histogram splat and one thread's SVD):
+//   orient_patch_kernel  one CTA per keypoint: identity patch, NormalizeData, sphere gradients, structure tensor
+//   orient_svd_kernel    one THREAD per keypoint: NR SVD in double + eigenvalue test -> kept keypoints
+//   orient_hist_kernel   one CTA per kept keypoint: primary direction histogram, peaks -> up to 11 primary directions
+//   orient_b_kernel      one CTA per (keypoint, primary direction): secondary histogram, peaks -> rotations
 // The reference caps the total at 11 rotations per keypoint, taken in (primary, secondary) order; that
 // truncation is applied when rows are counted (row_offsets_kernel).
 // ------------------------------------------------------------------------------------------------
-struct HistSmem {
-    float patch[PVP];
-    float dx[PVP], dy[PVP], dz[PVP];
-    float h0[PVP], h1[PVP], h2[PVP];
-    float contrib[kMaxSphere * 8];
-    int cbase[kMaxSphere];
-    float ex[kMaxSphere], ey[kMaxSphere], ez[kMaxSphere];
-    s3d_cand peaks[128], psort[128];
-    unsigned char pflag[736];
-    float svd_mat[3][3], svd_v[3][3], svd_w[4];
-    double svd_rv1[4];
-    float taps[12];
-    float oriData[PD * 3];
+constexpr int kSph = 485;            // voxels of the 11^3 patch with dx^2+dy^2+dz^2 < 25 (the host checks c_tab.n_sphere)
+constexpr int kSphP = 488;           // padded to a multiple of 4 and of the 8 splat warps' ranges
+constexpr int kBinsP = 1332;         // 11^3 histogram bins, padded
+constexpr int kHistThreads = 256, kHistWarps = kHistThreads / 32;
+static_assert(kSphP <= kMaxSphere, "sphere table too small");
+
+struct PatchSmem {                   // orient_patch_kernel
+    float patch[PVP], scratch[PVP];
+    float ex[kSphP], ey[kSphP], ez[kSphP];
     float inv[9];
-    float fmat[9];
     float red[2];
-    float eigs[3];
-    float ori0[9];
-    int np, keep, nprim;
 };
 
-// Sequential splat of the per-voxel contributions into a zeroed 11^3 histogram, in sphere (raster)
-// order: 8 lanes own the 8 corners of a voxel's 2x2x2 footprint (distinct bins), __syncwarp orders
-// successive voxels (fioIncPixelTrilinearInterp, reference FeatureIO.cpp:853-889).  Runs on warp
-// `warp`; the caller synchronises the block afterwards.
-// (A bin-owner variant that merges per-(z,y) bucket lists was measured 10x SLOWER on real patches:
-// orientation histograms are peaked by construction, so a few bins receive most of the ~485 voxels
-// and their owner threads serialise; the in-order warp walk costs ~40 cycles per voxel regardless.)
-__device__ void splat_histogram_warp(float *hist, const float *contrib, const int *cbase, int n_sphere, int warp)
+struct HistSmem {                    // orient_hist_kernel, orient_b_kernel
+    union {                          // lifetimes: patch (until the contributions exist) -> sorted (splat) -> h1, h2 (blur, peaks)
+        struct { float patch[PVP], h1[PVP], h2[PVP]; } p;
+        float sorted[kSphP * 8];
+    } a;
+    union {                          // contrib (until the splat has sorted it) -> peak lists
+        float contrib[kSphP * 8];
+        struct { s3d_cand peaks[128], psort[128]; unsigned char pflag[736]; } k;
+    } b;
+    float h0[PVP];
+    int cbase[kSphP];
+    unsigned char cnt[kHistWarps][kBinsP];   // entries per (warp range, bin), then (low byte of) their exclusive prefix over the ranges
+    unsigned char lrank[kSphP * 8];          // rank of an entry among the entries of its warp range that hit the same bin
+    unsigned short start[kBinsP + 4];        // first sorted slot of every bin
+    unsigned short hi[kBinsP + 4];           // bits 8-9 of the prefixes, 2 bits per warp range
+    int warp_tot[kHistWarps];
+    float taps[12];
+    int np, nprim;
+};
+
+// Histogram splat (fioIncPixelTrilinearInterp, reference FeatureIO.cpp:853-889, called voxel after voxel in sphere
+// order).  Every bin must receive its terms in voxel order (fp32 sums do not commute), but different bins are
+// independent: the 8 x n_sphere (bin, value) entries are sorted by bin with a STABLE counting sort -- warp w ranks the
+// entries of its contiguous voxel range with match.any, the per-range counts are prefix-summed over ranges and bins --
+// and every bin is then summed left to right by one thread, 0.0f first like the zeroed histogram of the reference.
+// Round 1 walked the voxels on one warp, one shared-memory read-modify-write round trip per voxel (20-45 K cycles per
+// histogram); orientation histograms are peaked, so bin-owner schemes without the sort serialise on a few bins.
+// All kHistThreads threads must call; hist is complete (and the block synchronised) on return.
+#ifdef S3D_PHASE_TIMERS
+#define SPLAT_ARGS , long long &ph_t_
+#define SPLAT_PASS , ph_t_
+#else
+#define SPLAT_ARGS
+#define SPLAT_PASS
+#endif
+__device__ __forceinline__ int splat_corner_offset(int c) { return (c & 1) + ((c >> 1) & 1) * PD + ((c >> 2) & 1) * PD * PD; }
+// does the 2x2x2 footprint that starts at bin `base` cover bin `bin`?  (offsets 0, 1, 11, 12 and the same + 121)
+__device__ __forceinline__ int splat_covers(int bin, int base)
 {
-    if ((int)(threadIdx.x >> 5) == warp) {
-        int lane = threadIdx.x & 31;
-        int off = (lane & 1) + ((lane >> 1) & 1) * PD + ((lane >> 2) & 1) * PD * PD;
-        int n = 0;
-        for (; n + 4 <= n_sphere; n += 4) {
-            int b0 = cbase[n], b1 = cbase[n + 1], b2 = cbase[n + 2], b3 = cbase[n + 3];
-            float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
-            if (lane < 8) { c0 = contrib[n * 8 + lane]; c1 = contrib[n * 8 + 8 + lane]; c2 = contrib[n * 8 + 16 + lane]; c3 = contrib[n * 8 + 24 + lane]; }
-            if (b0 >= 0 && lane < 8) hist[b0 + off] = hist[b0 + off] + c0;
-            __syncwarp();
-            if (b1 >= 0 && lane < 8) hist[b1 + off] = hist[b1 + off] + c1;
-            __syncwarp();
-            if (b2 >= 0 && lane < 8) hist[b2 + off] = hist[b2 + off] + c2;
-            __syncwarp();
-            if (b3 >= 0 && lane < 8) hist[b3 + off] = hist[b3 + off] + c3;
-            __syncwarp();
+    const int q = bin - base;
+    const int r = q >= PD * PD ? q - PD * PD : q;
+    return ((unsigned)r <= 12u) ? ((0x1803 >> r) & 1) : 0;
+}
+
+__device__ void splat_histogram_sorted(HistSmem &S, float *hist, int nsph SPLAT_ARGS)
+{
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < kHistWarps * kBinsP / 4; i += kHistThreads) reinterpret_cast<unsigned int *>(&S.cnt[0][0])[i] = 0u;
+    __syncthreads();
+    // pass 1: 4 voxels x 8 corners per step, lanes in entry order.  A bin is hit at most once per voxel, so the rank
+    // of an entry among the entries of its step is the number of EARLIER voxels of the step whose footprint covers
+    // its bin (match.any would do, but its latency grows with the number of distinct values: 500+ cycles here).
+    const int vr = (nsph + kHistWarps - 1) / kHistWarps;
+    const int n0 = warp * vr, n1 = min(nsph, n0 + vr);
+    const int j = lane >> 3;
+    const int off = splat_corner_offset(lane & 7);
+    unsigned char *cnt = S.cnt[warp];
+    // (software pipelined: the footprint tests of the next step are done before the counter round trip of this one)
+    int bin, rank, later;
+    bool valid;
+    auto prepare = [&](int nb) {
+        const int n = nb + j;
+        int base = n < n1 ? S.cbase[n] : -1;
+        valid = base >= 0;
+        if (!valid) base = -100000;                    // covers nothing
+        bin = base + off;
+        rank = 0; later = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int hit = splat_covers(bin, __shfl_sync(0xffffffffu, base, q * 8));
+            if (q < j) rank += hit;
+            if (q > j) later += hit;
         }
-        for (; n < n_sphere; n++) {
-            int b = cbase[n];
-            if (b >= 0 && lane < 8) hist[b + off] = hist[b + off] + contrib[n * 8 + lane];
-            __syncwarp();
+    };
+    prepare(n0);
+    for (int nb = n0; nb < n1; nb += 4) {
+        const int c_bin = bin, c_rank = rank, c_later = later;
+        const bool c_valid = valid;
+        prepare(nb + 4);
+        int old = 0;
+        if (c_valid) old = cnt[c_bin];
+        __syncwarp();
+        if (c_valid) {
+            S.lrank[(nb + j) * 8 + (lane & 7)] = (unsigned char)(old + c_rank);
+            if (c_later == 0) cnt[c_bin] = (unsigned char)(old + c_rank + 1);     // last entry of its bin in this step
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    PHASE(22);
+    // per bin: exclusive prefix of the counts over the warp ranges (low byte in place, bits 8-9 packed in hi[]),
+    // totals -> exclusive scan over the bins
+    int tot[6], tsum = 0;
+    const int b0 = t * 6;
+    if (b0 < kBinsP) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            int run = 0, hi = 0;
+#pragma unroll
+            for (int w = 0; w < kHistWarps; w++) {
+                const int c = S.cnt[w][b0 + k];
+                S.cnt[w][b0 + k] = (unsigned char)run;
+                hi |= (run >> 8) << (2 * w);
+                run += c;
+            }
+            S.hi[b0 + k] = (unsigned short)hi;
+            tot[k] = run;
+            tsum += run;
         }
     }
+    int inc = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+    if (lane == 31) S.warp_tot[warp] = inc;
+    __syncthreads();
+    int run = inc - tsum;
+    for (int w = 0; w < warp; w++) run += S.warp_tot[w];
+    if (b0 < kBinsP) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) { S.start[b0 + k] = (unsigned short)run; run += tot[k]; }
+    }
+    __syncthreads();
+    PHASE(23);
+    // pass 2: a thread moves the 8 entries of a voxel to their slots = first slot of the bin + entries of the earlier
+    // warp ranges + rank inside the range
+    for (int n = t; n < nsph; n += kHistThreads) {
+        const int base = S.cbase[n];
+        if (base >= 0) {
+            const int w = n / vr;
+            const float4 c0 = *reinterpret_cast<const float4 *>(&S.b.contrib[n * 8]), c1 = *reinterpret_cast<const float4 *>(&S.b.contrib[n * 8 + 4]);
+            const float cv[8] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w };
+            const uint2 lr = *reinterpret_cast<const uint2 *>(&S.lrank[n * 8]);
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const int bin = base + splat_corner_offset(c);
+                const int rk = (int)(((c < 4 ? lr.x : lr.y) >> (8 * (c & 3))) & 0xffu);
+                const int pre = (int)S.cnt[w][bin] | ((((int)S.hi[bin] >> (2 * w)) & 3) << 8);
+                S.a.sorted[(int)S.start[bin] + pre + rk] = cv[c];
+            }
+        }
+    }
+    __syncthreads();
+    PHASE(24);
+    // every bin: left-to-right sum of its terms by one thread (bin PV of the padding has none: start[PV] is the total).
+    // Orientation histograms are peaked -- a few bins receive a hundred terms and more -- so the walk is arranged to
+    // run at the latency of the dependent adds: 128-bit loads from the first aligned slot on, issued one group ahead.
+    for (int b = t; b < PV; b += kHistThreads) {
+        int i = S.start[b];
+        const int i1 = S.start[b + 1];
+        float acc = 0.0f;
+        for (; i < i1 && (i & 3); i++) acc = acc + S.a.sorted[i];
+        if (i + 8 <= i1) {
+            float4 u = *reinterpret_cast<const float4 *>(&S.a.sorted[i]), v = *reinterpret_cast<const float4 *>(&S.a.sorted[i + 4]);
+            while (true) {
+                const bool more = i + 16 <= i1;
+                float4 nu = u, nv = v;
+                if (more) { nu = *reinterpret_cast<const float4 *>(&S.a.sorted[i + 8]); nv = *reinterpret_cast<const float4 *>(&S.a.sorted[i + 12]); }
+                acc = acc + u.x; acc = acc + u.y; acc = acc + u.z; acc = acc + u.w;
+                acc = acc + v.x; acc = acc + v.y; acc = acc + v.z; acc = acc + v.w;
+                i += 8;
+                if (!more) break;
+                u = nu; v = nv;
+            }
+        }
+        for (; i < i1; i++) acc = acc + S.a.sorted[i];
+        hist[b] = acc;
+    }
+    if (t == 0) hist[PV] = 0.0f;
+    __syncthreads();
+    PHASE(25);
 }
 
 // contributions of one voxel at histogram position (px,py,pz) with value v
@@ -842,133 +1016,133 @@ __device__ __forceinline__ void interp_point_patch(const float *h, int ix, int i
     o[2] = (float)interp_quadratic(iz - 1, iz, iz + 1, h[i - PD * PD], h[i], h[i + PD * PD]);
 }
 
-// gradients of the sphere voxels, in sphere order, for contiguous sequential walks
-__device__ __forceinline__ void sphere_gradients(HistSmem &S, int nsph)
+// central differences of a sphere voxel (fioGenerateEdgeImages3D, reference FeatureIO.cpp:2284-2326; sphere voxels
+// are interior voxels of the patch: |d| <= 4)
+__device__ __forceinline__ void sphere_gradient(const float *p, int i, float *e)
 {
-    for (int n = threadIdx.x; n < nsph; n += blockDim.x) {
-        int i = c_tab.sphere[n];
-        S.ex[n] = S.dx[i]; S.ey[n] = S.dy[i]; S.ez[n] = S.dz[i];
-    }
-    __syncthreads();
+    e[0] = p[i + 1] - p[i - 1];
+    e[1] = p[i + PD] - p[i - PD];
+    e[2] = p[i + PD * PD] - p[i - PD * PD];
 }
 
-__global__ void __launch_bounds__(256) orient_a_kernel(const __grid_constant__ PyramidDesc pyr,
-                                                       const s3d_keypoint *__restrict__ kps, const int *__restrict__ kp_count,
-                                                       float eig_thres,
-                                                       int *__restrict__ kp_nprim, float *__restrict__ kp_eigs, float *__restrict__ kp_ori0,
-                                                       float *__restrict__ kp_p1, float *__restrict__ kp_patch0,
-                                                       int *__restrict__ work_b, int *work_b_count)
+// identity patch, normalised (generateFeature3D :1721-1739) + structure tensor over the sphere voxels in raster order
+// (determineOrientation3D :2575-2590)
+__global__ void __launch_bounds__(256) orient_patch_kernel(const __grid_constant__ PyramidDesc pyr,
+                                                           const s3d_keypoint *__restrict__ kps, const int *__restrict__ kp_count,
+                                                           float *__restrict__ kp_patch0, float *__restrict__ kp_fmat)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    HistSmem &S = *reinterpret_cast<HistSmem *>(smem_raw);
+    PatchSmem &S = *reinterpret_cast<PatchSmem *>(smem_raw);
     const int nkp = *kp_count;
     const int nsph = c_tab.n_sphere;
-    const float fRadius = 5.0f;
-    if (threadIdx.x < 12) S.taps[threadIdx.x] = threadIdx.x < 9 ? c_tab.hist_taps[threadIdx.x] : 0.0f;
     PHASE_INIT();
     for (int kpi = blockIdx.x; kpi < nkp; kpi += gridDim.x) {
         __syncthreads();
         const s3d_keypoint kp = kps[kpi];
         const OctaveDesc &o = pyr.oct[kp.octave];
-        const float *img = o.g[kp.level];
-        PHASE(0);
-
-        // --- identity patch, normalised (generateFeature3D :1721-1739)
         if (threadIdx.x == 0) { float id[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 }; invert3(id, S.inv); }
         __syncthreads();
-        gather_patch(img, o.X, o.Y, o.Zg, o.z_off, o.pitch, kp.x, kp.y, kp.z, kp.scale, S.inv, S.patch);
+        PHASE(0);
+        gather_patch(o.g[kp.level], o.X, o.Y, o.Zg, o.z_off, o.pitch, kp.x, kp.y, kp.z, kp.scale, S.inv, S.patch);
         __syncthreads();
         PHASE(1);
-        normalize_patch(S.patch, S.h0, S.red);
+        normalize_patch(S.patch, S.scratch, S.red);
         PHASE(2);
         for (int i = threadIdx.x; i < PV; i += blockDim.x) kp_patch0[(long long)kpi * PV + i] = S.patch[i];
-
-        // --- structure tensor over the sphere voxels, raster order (determineOrientation3D)
-        patch_gradients(S.patch, S.dx, S.dy, S.dz);
-        sphere_gradients(S, nsph);
-        PHASE(3);
-
-        // --- warp 0: structure tensor over the sphere voxels in raster order (9 lanes, one accumulator
-        //     each), then lane 0 runs the SVD + eigenvalue test (determineOrientation3D).  The other warps
-        //     meanwhile build the primary direction histogram (determineCanonicalOrientation3D :2779-2817),
-        //     whose result is simply dropped if the test fails.
-        if (threadIdx.x < 32) {
-            if (threadIdx.x < 9) {
-                const float *ea = (threadIdx.x / 3 == 0) ? S.ex : (threadIdx.x / 3 == 1) ? S.ey : S.ez;
-                const float *eb = (threadIdx.x % 3 == 0) ? S.ex : (threadIdx.x % 3 == 1) ? S.ey : S.ez;
-                float m = 0.0f;
-                int n = 0;
-                for (; n + 4 <= nsph; n += 4) {
-                    float4 a = *reinterpret_cast<const float4 *>(ea + n), b = *reinterpret_cast<const float4 *>(eb + n);
-                    m = m + a.x * b.x; m = m + a.y * b.y; m = m + a.z * b.z; m = m + a.w * b.w;
-                }
-                for (; n < nsph; n++) m = m + ea[n] * eb[n];
-                S.fmat[threadIdx.x] = m;
-            }
-            __syncwarp();
-        }
-        if (threadIdx.x == 0) {
-#ifdef S3D_PHASE_TIMERS
-            long long t_svd = clock64();
-#endif
-            // the SVD's small arrays live in shared memory (dynamic indexing would otherwise spill to local
-            // memory, whose L1 traffic also slows the histogram warp running next to it)
-            float (*mat)[3] = S.svd_mat, (*v)[3] = S.svd_v;
-            float *w = S.svd_w;
-            for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) mat[a][b] = S.fmat[a * 3 + b];
-            svd3(mat, w, v, S.svd_rv1);
-            sort_eigen(w, v);
-            for (int a = 0; a < 3; a++) { S.eigs[a] = w[a]; for (int b = 0; b < 3; b++) S.ori0[a * 3 + b] = v[a][b]; }
-            float fEigSum = w[0] + w[1] + w[2];
-            float fEigPrd = w[0] * w[1] * w[2];
-            float fEigSumProd = fEigSum * fEigSum * fEigSum;
-            S.keep = (fEigSumProd < eig_thres * fEigPrd || eig_thres < 0) ? 1 : 0;
-#ifdef S3D_PHASE_TIMERS
-            atomicAdd(&g_phase[14], (unsigned long long)(clock64() - t_svd));
-#endif
-        } else if (threadIdx.x >= 32) {
-#ifdef S3D_PHASE_TIMERS
-            long long t_spl = clock64();
-#endif
-            for (int n = threadIdx.x - 32; n < nsph; n += blockDim.x - 32) {
-                float e[3] = { S.ex[n], S.ey[n], S.ez[n] };
-                float fEdgeMagSqr = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
-                int base = -1;
-                if (fEdgeMagSqr != 0) {
-                    float fEdgeMag = sqrtf(fEdgeMagSqr);
-                    float u[3];
-                    for (int k = 0; k < 3; k++) u[k] = e[k] * fRadius / fEdgeMag;
-                    for (int k = 0; k < 3; k++) u[k] = u[k] + fRadius;
-                    make_contrib((float)((double)u[0] + 0.5), (float)((double)u[1] + 0.5), (float)((double)u[2] + 0.5),
-                                 fEdgeMag, &S.contrib[n * 8], base);
-                }
-                S.cbase[n] = base;
-            }
-            for (int i = threadIdx.x - 32; i < PVP; i += blockDim.x - 32) S.h0[i] = 0.0f;
-            asm volatile("bar.sync 1, 224;" ::: "memory");    // warps 1..7 only
-#ifdef S3D_PHASE_TIMERS
-            if (threadIdx.x == 32) atomicAdd(&g_phase[5], (unsigned long long)(clock64() - t_spl));
-#endif
-            splat_histogram_warp(S.h0, S.contrib, S.cbase, nsph, 1);
-#ifdef S3D_PHASE_TIMERS
-            if (threadIdx.x == 32) atomicAdd(&g_phase[15], (unsigned long long)(clock64() - t_spl));
-#endif
+        for (int n = threadIdx.x; n < kSphP; n += blockDim.x) {
+            float e[3] = { 0.0f, 0.0f, 0.0f };
+            if (n < nsph) sphere_gradient(S.patch, c_tab.sphere[n], e);
+            S.ex[n] = e[0]; S.ey[n] = e[1]; S.ez[n] = e[2];
         }
         __syncthreads();
-        PHASE(4);
-        if (!S.keep) {
-            if (threadIdx.x == 0) kp_nprim[kpi] = -1;
-            continue;
+        // 9 lanes, one accumulator each, every sum in sphere order
+        if (threadIdx.x < 9) {
+            const float *ea = (threadIdx.x / 3 == 0) ? S.ex : (threadIdx.x / 3 == 1) ? S.ey : S.ez;
+            const float *eb = (threadIdx.x % 3 == 0) ? S.ex : (threadIdx.x % 3 == 1) ? S.ey : S.ez;
+            float m = 0.0f;
+            int n = 0;
+            for (; n + 4 <= nsph; n += 4) {
+                float4 a = *reinterpret_cast<const float4 *>(ea + n), b = *reinterpret_cast<const float4 *>(eb + n);
+                m = m + a.x * b.x; m = m + a.y * b.y; m = m + a.z * b.z; m = m + a.w * b.w;
+            }
+            for (; n < nsph; n++) m = m + ea[n] * eb[n];
+            kp_fmat[(size_t)kpi * 9 + threadIdx.x] = m;
         }
-        blur_patch(S.h0, S.h1, S.h2, S.taps, c_tab.n_hist_taps);
+        PHASE(3);
+    }
+}
+
+// one thread per keypoint: SVD of the structure tensor, eigenvalue test (determineOrientation3D :2592-2607); kept
+// keypoints are queued for the histogram kernel (any order: its outputs are indexed by keypoint)
+__global__ void __launch_bounds__(32) orient_svd_kernel(const float *__restrict__ kp_fmat, const int *__restrict__ kp_count, float eig_thres,
+                                                        float *__restrict__ kp_eigs, float *__restrict__ kp_ori0, int *__restrict__ kp_nprim,
+                                                        int *__restrict__ work_a, int *work_a_count)
+{
+    const int nkp = *kp_count;
+    PHASE_INIT();
+    for (int kpi = blockIdx.x * blockDim.x + threadIdx.x; kpi < nkp; kpi += gridDim.x * blockDim.x) {
+        float mat[3][3], v[3][3], w[4];
+        double rv1[4];
+        for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) mat[a][b] = kp_fmat[(size_t)kpi * 9 + a * 3 + b];
+        svd3(mat, w, v, rv1);
+        sort_eigen(w, v);
+        for (int a = 0; a < 3; a++) { kp_eigs[kpi * 3 + a] = w[a]; for (int b = 0; b < 3; b++) kp_ori0[(size_t)kpi * 9 + a * 3 + b] = v[a][b]; }
+        float fEigSum = w[0] + w[1] + w[2];
+        float fEigPrd = w[0] * w[1] * w[2];
+        float fEigSumProd = fEigSum * fEigSum * fEigSum;
+        if (fEigSumProd < eig_thres * fEigPrd || eig_thres < 0) work_a[atomicAdd(work_a_count, 1)] = kpi;
+        else kp_nprim[kpi] = -1;
+    }
+    PHASE(4);
+}
+
+// one CTA per kept keypoint: primary direction histogram (determineCanonicalOrientation3D :2779-2885)
+__global__ void __launch_bounds__(kHistThreads) orient_hist_kernel(const int *__restrict__ work_a, const int *__restrict__ work_a_count,
+                                                                   const float *__restrict__ kp_patch0,
+                                                                   int *__restrict__ kp_nprim, float *__restrict__ kp_p1,
+                                                                   int *__restrict__ work_b, int *work_b_count)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HistSmem &S = *reinterpret_cast<HistSmem *>(smem_raw);
+    const int n_work = *work_a_count;
+    const int nsph = c_tab.n_sphere;
+    const float fRadius = 5.0f;
+    if (threadIdx.x < 12) S.taps[threadIdx.x] = threadIdx.x < 9 ? c_tab.hist_taps[threadIdx.x] : 0.0f;
+    PHASE_INIT();
+    for (int it = blockIdx.x; it < n_work; it += gridDim.x) {
+        const int kpi = work_a[it];
+        __syncthreads();
+        for (int i = threadIdx.x; i < PV; i += blockDim.x) S.a.p.patch[i] = kp_patch0[(long long)kpi * PV + i];
+        __syncthreads();
+        for (int n = threadIdx.x; n < nsph; n += blockDim.x) {
+            float e[3];
+            sphere_gradient(S.a.p.patch, c_tab.sphere[n], e);
+            float fEdgeMagSqr = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+            int base = -1;
+            if (fEdgeMagSqr != 0) {
+                float fEdgeMag = sqrtf(fEdgeMagSqr);
+                float u[3];
+                for (int k = 0; k < 3; k++) u[k] = e[k] * fRadius / fEdgeMag;
+                for (int k = 0; k < 3; k++) u[k] = u[k] + fRadius;
+                make_contrib((float)((double)u[0] + 0.5), (float)((double)u[1] + 0.5), (float)((double)u[2] + 0.5),
+                             fEdgeMag, &S.b.contrib[n * 8], base);
+            }
+            S.cbase[n] = base;
+        }
+        __syncthreads();
+        PHASE(5);
+        splat_histogram_sorted(S, S.h0, nsph SPLAT_PASS);
+        PHASE(6);
+        if (c_tab.n_hist_taps == 3) blur_patch3(S.h0, S.a.p.h2, S.taps);
+        else blur_patch(S.h0, S.a.p.h1, S.a.p.h2, S.taps, c_tab.n_hist_taps);
         PHASE(7);
-        find_sort_peaks(S.h2, S.pflag, S.psort, S.peaks, &S.np);
+        find_sort_peaks(S.a.p.h2, S.b.k.pflag, S.b.k.psort, S.b.k.peaks, &S.np);
         PHASE(8);
         // primary directions: peaks >= 0.8 * strongest, at most 11 (:2853-2885)
         if (threadIdx.x == 0) {
             int np = S.np, cnt = 0;
             for (int pi = 0; pi < np && pi < PD; pi++) {
-                if ((double)S.peaks[pi].value < 0.8 * (double)S.peaks[0].value) break;
+                if ((double)S.b.k.peaks[pi].value < 0.8 * (double)S.b.k.peaks[0].value) break;
                 cnt++;
             }
             S.nprim = cnt;
@@ -976,7 +1150,7 @@ __global__ void __launch_bounds__(256) orient_a_kernel(const __grid_constant__ P
         __syncthreads();
         if ((int)threadIdx.x < S.nprim) {
             float o3[3];
-            interp_point_patch(S.h2, S.peaks[threadIdx.x].x, S.peaks[threadIdx.x].y, S.peaks[threadIdx.x].z, o3);
+            interp_point_patch(S.a.p.h2, S.b.k.peaks[threadIdx.x].x, S.b.k.peaks[threadIdx.x].y, S.b.k.peaks[threadIdx.x].z, o3);
             o3[0] -= fRadius; o3[1] -= fRadius; o3[2] -= fRadius;
             vec_norm(o3);
             float *dst = kp_p1 + ((long long)kpi * PD + threadIdx.x) * 3;
@@ -988,16 +1162,14 @@ __global__ void __launch_bounds__(256) orient_a_kernel(const __grid_constant__ P
             int w0 = atomicAdd(work_b_count, S.nprim);
             for (int q = 0; q < S.nprim; q++) work_b[w0 + q] = kpi * PD + q;
         }
-        if (threadIdx.x < 3) kp_eigs[kpi * 3 + threadIdx.x] = S.eigs[threadIdx.x];
-        if (threadIdx.x < 9) kp_ori0[(size_t)kpi * 9 + threadIdx.x] = S.ori0[threadIdx.x];
         PHASE(13);
     }
 }
 
 // one CTA per (keypoint, primary direction): secondary direction histogram (:2887-3033)
-__global__ void __launch_bounds__(256) orient_b_kernel(const int *__restrict__ work_b, const int *__restrict__ work_b_count,
-                                                       const float *__restrict__ kp_p1, const float *__restrict__ kp_patch0,
-                                                       int *__restrict__ kp_nsec, float *__restrict__ kp_rots)
+__global__ void __launch_bounds__(kHistThreads) orient_b_kernel(const int *__restrict__ work_b, const int *__restrict__ work_b_count,
+                                                                const float *__restrict__ kp_p1, const float *__restrict__ kp_patch0,
+                                                                int *__restrict__ kp_nsec, float *__restrict__ kp_rots)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HistSmem &S = *reinterpret_cast<HistSmem *>(smem_raw);
@@ -1010,15 +1182,13 @@ __global__ void __launch_bounds__(256) orient_b_kernel(const int *__restrict__ w
         const long long wi = work_b[it];
         const int kpi = (int)(wi / PD), pi = (int)(wi % PD);
         __syncthreads();
-        for (int i = threadIdx.x; i < PV; i += blockDim.x) S.patch[i] = kp_patch0[(long long)kpi * PV + i];
+        for (int i = threadIdx.x; i < PV; i += blockDim.x) S.a.p.patch[i] = kp_patch0[(long long)kpi * PV + i];
         __syncthreads();
-        patch_gradients(S.patch, S.dx, S.dy, S.dz);
-        sphere_gradients(S, nsph);
         const float *pp = kp_p1 + ((long long)kpi * PD + pi) * 3;
         const float p1[3] = { pp[0], pp[1], pp[2] };
-        PHASE(9);
         for (int n = threadIdx.x; n < nsph; n += blockDim.x) {
-            float e[3] = { S.ex[n], S.ey[n], S.ez[n] };
+            float e[3];
+            sphere_gradient(S.a.p.patch, c_tab.sphere[n], e);
             float fEdgeMag = vec_mag(e);
             int base = -1;
             if (fEdgeMag != 0) {
@@ -1032,18 +1202,18 @@ __global__ void __launch_bounds__(256) orient_b_kernel(const int *__restrict__ w
                 vec_norm(perp);
                 for (int k = 0; k < 3; k++) { perp[k] = perp[k] * fRadius; perp[k] = perp[k] + fRadius; }
                 make_contrib((float)((double)perp[0] + 0.5), (float)((double)perp[1] + 0.5), (float)((double)perp[2] + 0.5),
-                             fEdgeMag, &S.contrib[n * 8], base);
+                             fEdgeMag, &S.b.contrib[n * 8], base);
             }
             S.cbase[n] = base;
         }
-        for (int i = threadIdx.x; i < PVP; i += blockDim.x) S.h0[i] = 0.0f;
         __syncthreads();
-        splat_histogram_warp(S.h0, S.contrib, S.cbase, nsph, 0);
-        __syncthreads();
+        PHASE(9);
+        splat_histogram_sorted(S, S.h0, nsph SPLAT_PASS);
         PHASE(10);
-        blur_patch(S.h0, S.h1, S.h2, S.taps, c_tab.n_hist_taps);
+        if (c_tab.n_hist_taps == 3) blur_patch3(S.h0, S.a.p.h2, S.taps);
+        else blur_patch(S.h0, S.a.p.h1, S.a.p.h2, S.taps, c_tab.n_hist_taps);
         PHASE(11);
-        find_sort_peaks(S.h2, S.pflag, S.psort, S.peaks, &S.np);
+        find_sort_peaks(S.a.p.h2, S.b.k.pflag, S.b.k.psort, S.b.k.peaks, &S.np);
         PHASE(12);
         // secondary peaks >= 0.5 * strongest, at most 11 per primary (the global cap of 11 is applied later)
         const int np2 = S.np;
@@ -1051,10 +1221,10 @@ __global__ void __launch_bounds__(256) orient_b_kernel(const int *__restrict__ w
             const int j = threadIdx.x;
             bool take = j < np2;
             for (int q = 0; q <= j && take; q++)
-                if (S.peaks[q].value < 0.5f * S.peaks[0].value) take = false;   // first failure breaks the loop
+                if (S.b.k.peaks[q].value < 0.5f * S.b.k.peaks[0].value) take = false;   // first failure breaks the loop
             if (take) {
                 float p2[3], p3[3];
-                interp_point_patch(S.h2, S.peaks[j].x, S.peaks[j].y, S.peaks[j].z, p2);
+                interp_point_patch(S.a.p.h2, S.b.k.peaks[j].x, S.b.k.peaks[j].y, S.b.k.peaks[j].z, p2);
                 p2[0] -= fRadius; p2[1] -= fRadius; p2[2] -= fRadius;
                 vec_norm(p2);
                 float fPar = vec_dot(p1, p2);
