@@ -283,6 +283,31 @@ def test_batch_matches_single_volume_extraction(pkg, engine):
         b.close()
 
 
+def test_batch_at_bench_shape_against_the_oracle(pkg, oracle):
+    """The configuration bench.py times (BASELINE config 4): 6 contexts per GPU on MNI-sized volumes, with the launch
+    shapes only batch contexts use (one x+y / one-kernel-level CTA per SM, one z segment, capped face test).  Rows of
+    every volume == the oracle's, through the host-buffer entry point and the device-resident one."""
+    import torch
+    vols = [pkg.phantom.brain_phantom((182, 218, 182), 1 + i, 400) for i in range(7)]
+    want = [oracle.extract(v)["features"] for v in vols[:3]]
+    eng = pkg.Engine(0)
+    try:
+        want += [eng.extract(v) for v in vols[3:]]      # the single-volume engine is pinned to the oracle at this size above
+    finally:
+        eng.close()
+    b = pkg.Batch(0, 6)
+    try:
+        got = b.extract(vols)
+        for g, w in zip(got, want):
+            assert len(w) > 500 and g.tobytes() == w.tobytes()
+        d = [torch.from_numpy(v).cuda() for v in vols]
+        torch.cuda.synchronize()
+        nk, nr = b.extract_device(d, (182, 218, 182))
+        assert nr == [len(w) for w in want]
+    finally:
+        b.close()
+
+
 def test_plan_cache_keeps_results_identical(pkg, engine):
     """A context keeps a few plans resident (S3D_PLAN_CACHE, default 4): alternating between shapes, and
     evicting beyond the cache size, must give the same rows as the first visit of each shape."""
