@@ -425,7 +425,7 @@ def run_ours(args):
                 rows5 = m.extract_slab(big, prm5)          # first call: plans and graphs are built
                 first_ms = 1e3 * (time.perf_counter() - t0)
                 reps = []
-                for _ in range(3):
+                for _ in range(6):
                     t0 = time.perf_counter()
                     again = m.extract_slab(big, prm5)
                     reps.append(1e3 * (time.perf_counter() - t0))
