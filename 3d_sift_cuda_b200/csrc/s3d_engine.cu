@@ -178,6 +178,7 @@ struct Tuning {
     bool serial = false;         // S3D_SERIAL=1: no octave / detection branches, every kernel on the main stream
     bool timing = false;         // S3D_STAGE_TIMING=1: no graph, events at stage boundaries of the main stream
     bool stamps = false;         // S3D_STAMPS=1: %globaltimer stamps around the graph (s3d_debug_stamps)
+    int prof_sleep_us = 0;       // S3D_PROF_SLEEP_US (with S3D_PROF_SKIP & 1): a one-thread kernel of that duration replaces the keypoint tail
     int prof_skip = 0;           // S3D_PROF_SKIP (profiling only, results invalid): 1 no keypoint tail, 2 no detection/refinement, 4 no describe, 8 no orient_b, 16 no level-5 blur
     int f4_max_r = 6;            // S3D_F4_MAXR: one-kernel level (s3d_blur4.cuh) for radii up to this; wider levels use x+y / z kernels (s3d_blur2.cuh)
     long long f4_min_voxels = 2000000;   // S3D_F4_MIN_VOXELS: smaller volumes (octaves >= 1 at MNI size) use the x+y / z kernels: the one-kernel level walks its
@@ -214,6 +215,7 @@ static Tuning tuning_from_env()
     if (t.timing) t.use_graph = false;        // event nodes inside graphs carry no timestamps
     t.stamps = env_int("S3D_STAMPS", 0) == 1;
     t.prof_skip = env_int("S3D_PROF_SKIP", 0);
+    t.prof_sleep_us = env_int("S3D_PROF_SLEEP_US", 0);
     int v = env_int("S3D_F4_MAXR", t.f4_max_r);
     if (v >= 0) t.f4_max_r = v < kF4MaxR ? v : kF4MaxR;
     if (env_int("S3D_F4_TY", 16) == 32) t.f4_ty = 32;
@@ -427,6 +429,13 @@ extern "C" int s3d_debug_phase_cycles(unsigned long long *out32)
 
 // S3D_STAMPS=1 (profiling): %globaltimer at four points of an extraction -- before / after the input
 // re-pitch (outside the graph), first and last node of the graph -- to see launch gaps without a profiler
+// profiling only (S3D_PROF_SLEEP_US): a one-thread kernel that lasts `us` microseconds and uses no shared resource --
+// put in place of the keypoint tail it tells whether the tail costs the batch its latency or its resources
+__global__ void sleep_kernel(int us)
+{
+    const long long t0 = clock64();
+    while (clock64() - t0 < (long long)us * 1900) __nanosleep(200);
+}
 __global__ void stamp_kernel(unsigned long long *slot)
 {
     unsigned long long t;
@@ -1029,7 +1038,11 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     ctx->cur = st;
     for (int o = 0; o < p->n_oct; o++) CK(cudaStreamWaitEvent(st, ctx->ev_done[o], 0));
     mark(ctx, "join (detect+refine tails)");
-    if (ctx->tune.prof_skip & 1) { CK(cudaGetLastError()); return S3D_OK; }
+    if (ctx->tune.prof_skip & 1) {
+        if (ctx->tune.prof_sleep_us > 0) sleep_kernel<<<1, 1, 0, st>>>(ctx->tune.prof_sleep_us);
+        CK(cudaGetLastError());
+        return S3D_OK;
+    }
     compact_kernel<<<1, 1024, 0, st>>>(L, p->kp_stage, p->stage_flags, p->kps, kp_count, p->kp_cap, err);
     mark(ctx, "compact");
     // orientation: per keypoint, then per (keypoint, primary direction)
