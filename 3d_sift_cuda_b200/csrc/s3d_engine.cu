@@ -19,6 +19,7 @@
 #include "s3d_voxel.cuh"
 #include "s3d_blur2.cuh"
 #include "s3d_blur4.cuh"
+#include "s3d_tiny.cuh"
 #include "s3d_keypoint.cuh"
 #include "s3d_match.cuh"
 
@@ -178,9 +179,15 @@ struct Tuning {
     bool serial = false;         // S3D_SERIAL=1: no octave / detection branches, every kernel on the main stream
     bool timing = false;         // S3D_STAGE_TIMING=1: no graph, events at stage boundaries of the main stream
     bool stamps = false;         // S3D_STAMPS=1: %globaltimer stamps around the graph (s3d_debug_stamps)
+    bool tiny = true;            // S3D_TINY=0: the last octaves as ordinary blur / subsample launches instead of tiny_octaves_kernel
     int prof_sleep_us = 0;       // S3D_PROF_SLEEP_US (with S3D_PROF_SKIP & 1): a one-thread kernel of that duration replaces the keypoint tail
     int prof_skip = 0;           // S3D_PROF_SKIP (profiling only, results invalid): 1 no keypoint tail, 2 no detection/refinement, 4 no describe, 8 no orient_b, 16 no level-5 blur
     int f4_max_r = 6;            // S3D_F4_MAXR: one-kernel level (s3d_blur4.cuh) for radii up to this; wider levels use x+y / z kernels (s3d_blur2.cuh)
+    long long f4_wide_min_voxels = 16000000;   // S3D_F4_WIDE_MIN_VOXELS: inside the pipeline radii 5 and 6 take the one-kernel level from this size on.  Their
+                                 // CTAs (setmaxnreg 64/192, 8 warps, one per SM) keep the detection branch of the SAME volume from running beside
+                                 // them: alone on the GPU an MNI volume takes 865 us with them and 726 us without (the level itself is faster:
+                                 // 43.8 against 51.2 us at 11 taps).  Batch contexts set it to f4_min_voxels: other volumes fill the SMs there.
+    bool f4_wide_forced = false;
     long long f4_min_voxels = 2000000;   // S3D_F4_MIN_VOXELS: smaller volumes (octaves >= 1 at MNI size) use the x+y / z kernels: the one-kernel level walks its
                                  // z segment plane by plane, a latency chain that a small volume cannot hide behind other CTAs (measured: 11-25 us against 4 + 6 us)
     long long bucket_min_voxels = 16000000;   // S3D_BUCKET_MIN_VOXELS: from this pyramid size on the candidate lists are grouped by plane before they are ranked
@@ -195,6 +202,7 @@ struct Tuning {
     int march_target = 0;        // S3D_MARCH_TARGET: threads wanted in flight in the z march (0 = 256 per SM)
     int detect_ctas = 0;         // S3D_DETECT_CTAS: resident detect_face blocks per SM (0 = whole grid; contexts of an s3d_batch: 4)
     bool detect_ctas_forced = false;
+    bool tail_forced = false;
     int tail_a = 3, tail_b = 6, tail_d = 10;   // S3D_TAIL_BLOCKS=a,b,d: blocks per SM of orient_a / orient_b / describe
     int desc_threads = 128;      // S3D_DESC_THREADS=64|128: threads per describe block
     int max_plans = 6;           // S3D_PLAN_CACHE: resident plans (shapes) per context
@@ -215,11 +223,13 @@ static Tuning tuning_from_env()
     if (t.timing) t.use_graph = false;        // event nodes inside graphs carry no timestamps
     t.stamps = env_int("S3D_STAMPS", 0) == 1;
     t.prof_skip = env_int("S3D_PROF_SKIP", 0);
+    t.tiny = env_int("S3D_TINY", 1) != 0;
     t.prof_sleep_us = env_int("S3D_PROF_SLEEP_US", 0);
     int v = env_int("S3D_F4_MAXR", t.f4_max_r);
     if (v >= 0) t.f4_max_r = v < kF4MaxR ? v : kF4MaxR;
     if (env_int("S3D_F4_TY", 16) == 32) t.f4_ty = 32;
     { const char *mv = getenv("S3D_F4_MIN_VOXELS"); if (mv && mv[0]) t.f4_min_voxels = atoll(mv); }
+    { const char *mv = getenv("S3D_F4_WIDE_MIN_VOXELS"); if (mv && mv[0]) { t.f4_wide_min_voxels = atoll(mv); t.f4_wide_forced = true; } }
     { const char *mv = getenv("S3D_BUCKET_MIN_VOXELS"); if (mv && mv[0]) t.bucket_min_voxels = atoll(mv); }
     { const char *mv = getenv("S3D_DETECT2_MIN_VOXELS"); if (mv && mv[0]) t.detect2_min_voxels = atoll(mv); }
     t.f4_ctas = env_int("S3D_F4_CTAS", 0);
@@ -241,7 +251,7 @@ static Tuning tuning_from_env()
     {
         const char *tb = getenv("S3D_TAIL_BLOCKS");
         int a = 0, b = 0, d = 0;
-        if (tb && sscanf(tb, "%d,%d,%d", &a, &b, &d) == 3 && a > 0 && b > 0 && d > 0) { t.tail_a = a; t.tail_b = b; t.tail_d = d; }
+        if (tb && sscanf(tb, "%d,%d,%d", &a, &b, &d) == 3 && a > 0 && b > 0 && d > 0) { t.tail_a = a; t.tail_b = b; t.tail_d = d; t.tail_forced = true; }
     }
     v = env_int("S3D_DESC_THREADS", 0);
     if (v == 64 || v == 128) t.desc_threads = v;
@@ -274,6 +284,7 @@ struct s3d_ctx {
     int spec_guess = 2048;           // rows to copy next time (tracks 1.25 x the last count)
     bool spec_valid = false;         // h_counts / h_rows belong to the current result
     cudaStream_t cur = nullptr;  // stream the stage launchers enqueue on (main stream or an octave branch)
+    bool in_pipeline = false;    // the stage launchers are called by enqueue_pipeline (concurrent branches), not through the stage-level API
     Tuning tune;                 // S3D_* environment knobs, read once in ctx_create
     unsigned long long *d_stamps = nullptr;   // S3D_STAMPS=1
     std::vector<std::pair<std::string, cudaEvent_t>> marks;
@@ -336,6 +347,7 @@ static s3d_status ctx_create(int device, void *stream, bool borrow, s3d_ctx **ou
     build_tables(t);
     if (t.n_sphere != kSph) return fail(ctx, S3D_ERR_INVALID, "sphere table size");   // the keypoint kernels size their shared memory for it
     CK(cudaMemcpyToSymbol(c_tab, &t, sizeof(t)));
+    CK(cudaFuncSetAttribute(tiny_octaves_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTinySmem));
     CK(cudaFuncSetAttribute(orient_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PatchSmem)));
     CK(cudaFuncSetAttribute(orient_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HistSmem)));
     CK(cudaFuncSetAttribute(orient_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HistSmem)));
@@ -468,7 +480,8 @@ static bool launch_blur_fast(s3d_ctx *ctx, const float *in, float *tmp, float *o
     if (plane * Z >= (1ll << 31)) return false;
     const Tuning &tn = ctx->tune;
     if constexpr (R <= kF4MaxR) {
-        if (R <= tn.f4_max_r && plane * Z >= tn.f4_min_voxels &&
+        const long long min_vox = (R >= 5 && ctx->in_pipeline && tn.f4_wide_min_voxels > tn.f4_min_voxels) ? tn.f4_wide_min_voxels : tn.f4_min_voxels;
+        if (R <= tn.f4_max_r && plane * Z >= min_vox &&
             (tn.f4_ty == 32 ? launch_blur_f4<R, 32>(ctx->cur, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, tn.f4_ctas, err)
                             : launch_blur_f4<R, 16>(ctx->cur, in, out, dog, X, Y, Z, pitch, taps, ctx->sm_count, tn.f4_ctas, err))) {
             ctx->launches += 1;
@@ -947,6 +960,34 @@ static void report_marks(s3d_ctx *ctx)
     }
 }
 
+// Detection branch of one level.  Level j completes DoG j-1, so centre level j-1 can be detected (it needs DoG j-2 and
+// j-1) and centre level j-2 can be validated / refined (it needs DoG j-1).  Enqueued on `sd`.
+static s3d_status enqueue_detection(s3d_ctx *ctx, Plan *p, const ListDesc &L, int o, int j, cudaStream_t sd, int *err)
+{
+    const OctaveDesc &od = p->pyr.oct[o];
+    ctx->cur = sd;
+    int c_det = j - 1, c_ref = j - 2;
+    if (c_det <= 3 && !(ctx->tune.prof_skip & 2)) {
+        int l0 = (o * 3 + (c_det - 1)) * 2;
+        s3d_status s = detect_two_pass(ctx, od.d[c_det - 1], od.d[c_det], od.X, od.Y, od.Z, od.pitch,
+                                       p->face[o * 3 + c_det - 1], p->face_counts + o * 3 + c_det - 1, p->face_cap[o * 3 + c_det - 1],
+                                       p->cand_raw + (size_t)l0 * p->cand_cap, p->counts + l0,
+                                       p->cand_raw + (size_t)(l0 + 1) * p->cand_cap, p->counts + l0 + 1, p->cand_cap, err, od.own0, od.own1);
+        if (s != S3D_OK) return s;
+    }
+    if (c_ref >= 1 && !(ctx->tune.prof_skip & 2)) {
+        int l0 = (o * 3 + (c_ref - 1)) * 2;
+        if (p->cand_sorted) {
+            cand_bucket_kernel<<<2, 1024, (od.Z + 2) * sizeof(int), sd>>>(L, l0, od.Z, p->cand_sorted, p->plane_off, p->plane_stride);
+            ctx->launches++;
+        }
+        cand_refine_kernel<<<dim3(2, p->cand_sorted ? 128 : 32), 256, 0, sd>>>(p->pyr, L, l0, p->kp_stage, p->stage_flags, err,
+                                                                              p->cand_sorted, p->plane_off, p->plane_stride);
+        ctx->launches++;
+    }
+    return S3D_OK;
+}
+
 static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
 {
     Plan *p = ctx->plan;
@@ -984,11 +1025,54 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     // Octave o+1 only needs level 3 of octave o, so every octave runs on its own branch (stream / graph
     // branch): the tail of an octave overlaps the whole chain of smaller octaves, which is launch-latency bound.
     ListDesc L{ p->n_lists, p->cand_cap, p->cand_raw, p->counts };
+    // The last octaves are a few thousand voxels each: from the first octave on from which all of them fit, one launch
+    // of tiny_octaves_kernel replaces their blur levels and subsamples (s3d_tiny.cuh); their detection branches follow it.
+    int tiny_first = p->n_oct;
+    if (ctx->tune.tiny) {
+        bool taps_ok = true;
+        for (int j = 0; j < 5; j++) taps_ok = taps_ok && p->n_lvl_taps[j] <= 2 * kMaxFastR + 1;
+        for (int o = p->n_oct - 1; o >= 0 && taps_ok && p->n_oct - o <= kTinyMaxOct; o--) {
+            const OctaveDesc &q = p->pyr.oct[o];
+            const bool whole = q.z_off == 0 && q.Zg == q.Z && q.own0 == 0 && q.own1 == q.Z;       // not a z slab
+            if (!whole || (long long)q.pitch * q.Y * q.Z > kTinyMaxElems) break;
+            tiny_first = o;
+        }
+    }
     for (int o = 0; o < p->n_oct; o++) {
         const OctaveDesc &od = p->pyr.oct[o];
         cudaStream_t so = (o == 0 || ctx->tune.serial) ? st : ctx->side[o];
         ctx->cur = so;
         if (o > 0) CK(cudaStreamWaitEvent(so, ctx->ev_fork[o - 1], 0));
+        if (o == tiny_first) {
+            TinyDesc td;
+            memset(&td, 0, sizeof(td));
+            td.n_oct = p->n_oct - o;
+            for (int q = o; q < p->n_oct; q++) {
+                const OctaveDesc &oq = p->pyr.oct[q];
+                TinyOct &t = td.o[q - o];
+                t.X = oq.X; t.Y = oq.Y; t.Z = oq.Z; t.pitch = oq.pitch;
+                for (int j = 0; j < 6; j++) t.g[j] = p->g[q * 6 + j].p;
+                for (int j = 0; j < 5; j++) t.d[j] = p->d[q * 5 + j].p;
+            }
+            for (int j = 0; j < 5; j++) {
+                td.ntaps[j] = p->n_lvl_taps[j];
+                for (int k = 0; k < p->n_lvl_taps[j]; k++) td.taps[j][k] = p->lvl_taps[j][k];
+            }
+            tiny_octaves_kernel<<<1, kTinyThreads, kTinySmem, so>>>(td);
+            ctx->launches++;
+            CK(cudaEventRecord(ctx->ev_lvl[o][0], so));
+            for (int q = o; q < p->n_oct; q++) {
+                cudaStream_t sd = ctx->tune.serial ? st : ctx->det[q];
+                CK(cudaStreamWaitEvent(sd, ctx->ev_lvl[o][0], 0));
+                for (int j = 2; j < 6; j++) {
+                    s3d_status s = enqueue_detection(ctx, p, L, q, j, sd, err);
+                    if (s != S3D_OK) { ctx->cur = st; return s; }
+                }
+                CK(cudaEventRecord(ctx->ev_done[q], sd));
+            }
+            ctx->cur = so;
+            break;
+        }
         for (int j = 1; j < 6; j++) {
             Vol &a = p->g[o * 6 + j - 1], &b = p->g[o * 6 + j], &dd = p->d[o * 5 + j - 1];
             s3d_status s = S3D_OK;
@@ -1010,26 +1094,8 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
                 CK(cudaEventRecord(ctx->ev_lvl[o][j - 2], so));
                 cudaStream_t sd = ctx->tune.serial ? st : ctx->det[o];
                 CK(cudaStreamWaitEvent(sd, ctx->ev_lvl[o][j - 2], 0));
-                ctx->cur = sd;
-                int c_det = j - 1, c_ref = j - 2;
-                if (c_det <= 3 && !(ctx->tune.prof_skip & 2)) {
-                    int l0 = (o * 3 + (c_det - 1)) * 2;
-                    s = detect_two_pass(ctx, od.d[c_det - 1], od.d[c_det], od.X, od.Y, od.Z, od.pitch,
-                                        p->face[o * 3 + c_det - 1], p->face_counts + o * 3 + c_det - 1, p->face_cap[o * 3 + c_det - 1],
-                                        p->cand_raw + (size_t)l0 * p->cand_cap, p->counts + l0,
-                                        p->cand_raw + (size_t)(l0 + 1) * p->cand_cap, p->counts + l0 + 1, p->cand_cap, err, od.own0, od.own1);
-                    if (s != S3D_OK) { ctx->cur = st; return s; }
-                }
-                if (c_ref >= 1 && !(ctx->tune.prof_skip & 2)) {
-                    int l0 = (o * 3 + (c_ref - 1)) * 2;
-                    if (p->cand_sorted) {
-                        cand_bucket_kernel<<<2, 1024, (od.Z + 2) * sizeof(int), sd>>>(L, l0, od.Z, p->cand_sorted, p->plane_off, p->plane_stride);
-                        ctx->launches++;
-                    }
-                    cand_refine_kernel<<<dim3(2, p->cand_sorted ? 128 : 32), 256, 0, sd>>>(p->pyr, L, l0, p->kp_stage, p->stage_flags, err,
-                                                                                          p->cand_sorted, p->plane_off, p->plane_stride);
-                    ctx->launches++;
-                }
+                s = enqueue_detection(ctx, p, L, o, j, sd, err);
+                if (s != S3D_OK) { ctx->cur = st; return s; }
                 if (j == 5) CK(cudaEventRecord(ctx->ev_done[o], sd));
                 ctx->cur = so;
             }
@@ -1104,7 +1170,9 @@ static s3d_status run_pipeline(s3d_ctx *ctx, const s3d_params *prm)
     ctx->has_result = false;
     if (!ctx->tune.use_graph) {
         ctx->launches = 0;
+        ctx->in_pipeline = true;
         s3d_status s = enqueue_pipeline(ctx, prm);
+        ctx->in_pipeline = false;
         ctx->last_launches = ctx->launches;
         if (s == S3D_OK) ctx->has_result = true;
         return s;
@@ -1116,7 +1184,9 @@ static s3d_status run_pipeline(s3d_ctx *ctx, const s3d_params *prm)
         ctx->marks.clear();
         CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
         ctx->launches = 0;
+        ctx->in_pipeline = true;
         s3d_status s = enqueue_pipeline(ctx, prm);
+        ctx->in_pipeline = false;
         cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
         if (s != S3D_OK) { if (g) cudaGraphDestroy(g); return s; }
         if (e != cudaSuccess) { ctx->err = std::string("graph capture failed: ") + cudaGetErrorString(e); return S3D_ERR_CUDA; }
@@ -1396,6 +1466,10 @@ extern "C" s3d_status s3d_batch_create(int device, int n_contexts, s3d_batch **o
         if (!c->tune.detect_ctas_forced && n_contexts > 1) c->tune.detect_ctas = 4;
         // the one-kernel blur level: one resident CTA per SM instead of two (measured 529 -> 509 us per volume with 6 contexts)
         if (!c->tune.f4_ctas_forced && n_contexts > 1) c->tune.f4_ctas = c->sm_count;
+        if (!c->tune.f4_wide_forced && n_contexts > 1) c->tune.f4_wide_min_voxels = 0;
+        // describe: few CTAs, so that each walks full groups of rows (their NormalizeData sums side by side); a context
+        // alone on the GPU spreads one row per CTA instead (shortest chain)
+        if (!c->tune.tail_forced && n_contexts > 1) c->tune.tail_d = 2;
         b->ctx.push_back(c);
     }
     *out = b;

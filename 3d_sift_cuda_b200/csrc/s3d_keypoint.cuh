@@ -1332,8 +1332,11 @@ __global__ void __launch_bounds__(128) describe_kernel(const __grid_constant__ P
     }
     PHASE_INIT();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-    for (int row0 = blockIdx.x * kDescGroup; row0 < n_rows; row0 += gridDim.x * kDescGroup) {
-      const int ng = min(kDescGroup, n_rows - row0);
+    // group size: as many rows per CTA as it takes to cover the rows with this grid, at most kDescGroup -- with fewer rows
+    // than CTAs every CTA takes one row (shortest latency: one volume alone), large row counts are walked in full groups
+    const int G = max(1, min(kDescGroup, (n_rows + (int)gridDim.x - 1) / (int)gridDim.x));
+    for (int row0 = blockIdx.x * G; row0 < n_rows; row0 += gridDim.x * G) {
+      const int ng = min(G, n_rows - row0);
       // ---- phase A: orientation + patch of every row of the group
       for (int g = 0; g < ng; g++) {
         const int row = row0 + g;
