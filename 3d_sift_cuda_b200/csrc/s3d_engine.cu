@@ -962,7 +962,7 @@ static void report_marks(s3d_ctx *ctx)
 
 // Detection branch of one level.  Level j completes DoG j-1, so centre level j-1 can be detected (it needs DoG j-2 and
 // j-1) and centre level j-2 can be validated / refined (it needs DoG j-1).  Enqueued on `sd`.
-static s3d_status enqueue_detection(s3d_ctx *ctx, Plan *p, const ListDesc &L, int o, int j, cudaStream_t sd, int *err)
+static s3d_status enqueue_detection(s3d_ctx *ctx, Plan *p, const ListDesc &L, int o, int j, cudaStream_t sd, int *err, int refine_octaves = 1)
 {
     const OctaveDesc &od = p->pyr.oct[o];
     ctx->cur = sd;
@@ -974,6 +974,18 @@ static s3d_status enqueue_detection(s3d_ctx *ctx, Plan *p, const ListDesc &L, in
                                        p->cand_raw + (size_t)l0 * p->cand_cap, p->counts + l0,
                                        p->cand_raw + (size_t)(l0 + 1) * p->cand_cap, p->counts + l0 + 1, p->cand_cap, err, od.own0, od.own1);
         if (s != S3D_OK) return s;
+    }
+    // octaves >= 1 of volumes without bucketed ranking: the three centre levels are validated / refined by ONE launch
+    // after level 5 (lists 6o .. 6o+5) -- two launches less on a chain that is launch-latency bound; `refine_octaves`
+    // > 1: the lists of that many consecutive octaves (the tiny tail of the pyramid)
+    if (o >= 1 && !p->cand_sorted && !(ctx->tune.prof_skip & 2)) {
+        if (j == 5 && refine_octaves != 0) {      // < 0: that many octaves ENDING with this one
+            const int n_ref = refine_octaves > 0 ? refine_octaves : -refine_octaves;
+            const int o_first = refine_octaves > 0 ? o : o - n_ref + 1;
+            cand_refine_kernel<<<dim3(6 * n_ref, 32), 256, 0, sd>>>(p->pyr, L, o_first * 6, p->kp_stage, p->stage_flags, err, nullptr, nullptr, 0);
+            ctx->launches++;
+        }
+        return S3D_OK;
     }
     if (c_ref >= 1 && !(ctx->tune.prof_skip & 2)) {
         int l0 = (o * 3 + (c_ref - 1)) * 2;
@@ -1061,14 +1073,26 @@ static s3d_status enqueue_pipeline(s3d_ctx *ctx, const s3d_params *prm)
             tiny_octaves_kernel<<<1, kTinyThreads, kTinySmem, so>>>(td);
             ctx->launches++;
             CK(cudaEventRecord(ctx->ev_lvl[o][0], so));
-            for (int q = o; q < p->n_oct; q++) {
-                cudaStream_t sd = ctx->tune.serial ? st : ctx->det[q];
+            if (o >= 1 && !p->cand_sorted) {
+                // every detection of every tiny octave on one stream, then one refinement launch for all their lists
+                cudaStream_t sd = ctx->tune.serial ? st : ctx->det[o];
                 CK(cudaStreamWaitEvent(sd, ctx->ev_lvl[o][0], 0));
-                for (int j = 2; j < 6; j++) {
-                    s3d_status s = enqueue_detection(ctx, p, L, q, j, sd, err);
-                    if (s != S3D_OK) { ctx->cur = st; return s; }
+                for (int q = o; q < p->n_oct; q++)
+                    for (int j = 2; j < 6; j++) {
+                        s3d_status s = enqueue_detection(ctx, p, L, q, j, sd, err, (q == p->n_oct - 1 && j == 5) ? -(p->n_oct - o) : 0);
+                        if (s != S3D_OK) { ctx->cur = st; return s; }
+                    }
+                for (int q = o; q < p->n_oct; q++) CK(cudaEventRecord(ctx->ev_done[q], sd));
+            } else {
+                for (int q = o; q < p->n_oct; q++) {
+                    cudaStream_t sd = ctx->tune.serial ? st : ctx->det[q];
+                    CK(cudaStreamWaitEvent(sd, ctx->ev_lvl[o][0], 0));
+                    for (int j = 2; j < 6; j++) {
+                        s3d_status s = enqueue_detection(ctx, p, L, q, j, sd, err);
+                        if (s != S3D_OK) { ctx->cur = st; return s; }
+                    }
+                    CK(cudaEventRecord(ctx->ev_done[q], sd));
                 }
-                CK(cudaEventRecord(ctx->ev_done[q], sd));
             }
             ctx->cur = so;
             break;
