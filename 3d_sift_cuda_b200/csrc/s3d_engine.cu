@@ -967,6 +967,58 @@ static s3d_status enqueue_detection(s3d_ctx *ctx, Plan *p, const ListDesc &L, in
     const OctaveDesc &od = p->pyr.oct[o];
     ctx->cur = sd;
     int c_det = j - 1, c_ref = j - 2;
+    // Octaves >= 1 of volumes without bucketed ranking: their chains are launch-latency bound, so the three centre levels
+    // are detected by ONE launch (detect_multi_kernel; small octaves only: larger ones keep the two-pass detection per
+    // level) and validated / refined by ONE launch (lists 6o .. 6o+5), both after level 5.  `refine_octaves` < 0: that
+    // many consecutive octaves ENDING with this one (the tiny tail of the pyramid) share the two launches.
+    if (o >= 1 && !p->cand_sorted) {
+        if (ctx->tune.prof_skip & 2) return S3D_OK;
+        const bool small = (long long)od.pitch * od.Y * od.Z < ctx->tune.detect2_min_voxels;
+        if (!small && c_det <= 3) {
+            int l0 = (o * 3 + (c_det - 1)) * 2;
+            s3d_status s = detect_two_pass(ctx, od.d[c_det - 1], od.d[c_det], od.X, od.Y, od.Z, od.pitch,
+                                           p->face[o * 3 + c_det - 1], p->face_counts + o * 3 + c_det - 1, p->face_cap[o * 3 + c_det - 1],
+                                           p->cand_raw + (size_t)l0 * p->cand_cap, p->counts + l0,
+                                           p->cand_raw + (size_t)(l0 + 1) * p->cand_cap, p->counts + l0 + 1, p->cand_cap, err, od.own0, od.own1);
+            if (s != S3D_OK) return s;
+        }
+        if (j == 5 && refine_octaves != 0) {
+            const int n_ref = refine_octaves > 0 ? refine_octaves : -refine_octaves;
+            const int o_first = refine_octaves > 0 ? o : o - n_ref + 1;
+            if (small) {
+                for (int q0 = o_first; q0 <= o; q0 += kMaxDetectJobs / 3) {
+                    DetectJobs J;
+                    memset(&J, 0, sizeof(J));
+                    J.cap = p->cand_cap;
+                    int blocks = 0;
+                    for (int q = q0; q <= o && q < q0 + kMaxDetectJobs / 3; q++) {
+                        const OctaveDesc &oq = p->pyr.oct[q];
+                        if (oq.X < 3 || oq.Y < 3 || oq.Z < 3) continue;      // no interior voxel
+                        for (int c = 1; c <= 3; c++) {
+                            DetectJob &t = J.job[J.n++];
+                            const int l0 = (q * 3 + (c - 1)) * 2;
+                            t.finer = oq.d[c - 1]; t.centre = oq.d[c];
+                            t.X = oq.X; t.Y = oq.Y; t.Z = oq.Z; t.pitch = oq.pitch;
+                            t.mins = CandList{ p->cand_raw + (size_t)l0 * p->cand_cap, p->counts + l0 };
+                            t.maxs = CandList{ p->cand_raw + (size_t)(l0 + 1) * p->cand_cap, p->counts + l0 + 1 };
+                            t.own0 = oq.own0; t.own1 = oq.own1;
+                            t.nbx = (oq.X - 2 + 31) / 32; t.nby = (oq.Y - 2 + 7) / 8;
+                            t.first_block = blocks;
+                            blocks += t.nbx * t.nby * ((oq.Z - 2 + kDetectZ - 1) / kDetectZ);
+                        }
+                    }
+                    if (J.n > 0) {
+                        detect_multi_kernel<<<blocks, dim3(32, 8), 0, sd>>>(J);
+                        ctx->launches++;
+                    }
+                }
+            }
+            cand_refine_kernel<<<dim3(6 * n_ref, 32), 256, 0, sd>>>(p->pyr, L, o_first * 6, p->kp_stage, p->stage_flags, err, nullptr, nullptr, 0);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+        return S3D_OK;
+    }
     if (c_det <= 3 && !(ctx->tune.prof_skip & 2)) {
         int l0 = (o * 3 + (c_det - 1)) * 2;
         s3d_status s = detect_two_pass(ctx, od.d[c_det - 1], od.d[c_det], od.X, od.Y, od.Z, od.pitch,
@@ -974,18 +1026,6 @@ static s3d_status enqueue_detection(s3d_ctx *ctx, Plan *p, const ListDesc &L, in
                                        p->cand_raw + (size_t)l0 * p->cand_cap, p->counts + l0,
                                        p->cand_raw + (size_t)(l0 + 1) * p->cand_cap, p->counts + l0 + 1, p->cand_cap, err, od.own0, od.own1);
         if (s != S3D_OK) return s;
-    }
-    // octaves >= 1 of volumes without bucketed ranking: the three centre levels are validated / refined by ONE launch
-    // after level 5 (lists 6o .. 6o+5) -- two launches less on a chain that is launch-latency bound; `refine_octaves`
-    // > 1: the lists of that many consecutive octaves (the tiny tail of the pyramid)
-    if (o >= 1 && !p->cand_sorted && !(ctx->tune.prof_skip & 2)) {
-        if (j == 5 && refine_octaves != 0) {      // < 0: that many octaves ENDING with this one
-            const int n_ref = refine_octaves > 0 ? refine_octaves : -refine_octaves;
-            const int o_first = refine_octaves > 0 ? o : o - n_ref + 1;
-            cand_refine_kernel<<<dim3(6 * n_ref, 32), 256, 0, sd>>>(p->pyr, L, o_first * 6, p->kp_stage, p->stage_flags, err, nullptr, nullptr, 0);
-            ctx->launches++;
-        }
-        return S3D_OK;
     }
     if (c_ref >= 1 && !(ctx->tune.prof_skip & 2)) {
         int l0 = (o * 3 + (c_ref - 1)) * 2;

@@ -358,13 +358,14 @@ __global__ void __launch_bounds__(256) detect_full_kernel(const float *__restric
 }
 
 // single-kernel variant (kept for volumes too large for 32-bit voxel offsets)
-__global__ void __launch_bounds__(256) detect_kernel(const float *__restrict__ finer, const float *__restrict__ centre,
-                                                     int X, int Y, int Z, int pitch,
-                                                     CandList mins, CandList maxs, int cap, int own0, int own1)
+// one block of the single-kernel detection: block (bx, by, bz) of a (32, 8) x kDetectZ tiling of the interior voxels
+__device__ __forceinline__ void detect_block(const float *__restrict__ finer, const float *__restrict__ centre,
+                                             int X, int Y, int Z, int pitch,
+                                             CandList mins, CandList maxs, int cap, int own0, int own1, int bx, int by, int bz)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    int y = blockIdx.y * blockDim.y + threadIdx.y + 1;
-    int z0 = blockIdx.z * kDetectZ + 1;
+    int x = bx * blockDim.x + threadIdx.x + 1;
+    int y = by * blockDim.y + threadIdx.y + 1;
+    int z0 = bz * kDetectZ + 1;
     if (x > X - 2 || y > Y - 2 || z0 > Z - 2) return;
     long long plane = (long long)pitch * Y;
     long long base = (long long)y * pitch + x;
@@ -421,6 +422,35 @@ __global__ void __launch_bounds__(256) detect_kernel(const float *__restrict__ f
             if (kk < cap) mins.items[kk] = s3d_cand{ x, y, z, c };
         }
     }
+}
+
+__global__ void __launch_bounds__(256) detect_kernel(const float *__restrict__ finer, const float *__restrict__ centre,
+                                                     int X, int Y, int Z, int pitch,
+                                                     CandList mins, CandList maxs, int cap, int own0, int own1)
+{
+    detect_block(finer, centre, X, Y, Z, pitch, mins, maxs, cap, own0, own1, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Several detections in one launch: the three centre levels of a small octave (after its last level), or every
+// (octave, level) pair of the tiny tail of the pyramid.  Block b belongs to the job whose block range holds it.
+constexpr int kMaxDetectJobs = 12;
+struct DetectJob {
+    const float *finer, *centre;
+    int X, Y, Z, pitch;
+    CandList mins, maxs;
+    int own0, own1;
+    int nbx, nby, first_block;     // block grid (nbx, nby, nbz) of the job starts at linear block `first_block`
+};
+struct DetectJobs { int n; int cap; DetectJob job[kMaxDetectJobs]; };
+
+__global__ void __launch_bounds__(256) detect_multi_kernel(const __grid_constant__ DetectJobs J)
+{
+    int k = 0;
+    while (k + 1 < J.n && (int)blockIdx.x >= J.job[k + 1].first_block) k++;
+    const DetectJob &q = J.job[k];
+    const int b = blockIdx.x - q.first_block;
+    const int bx = b % q.nbx, by = (b / q.nbx) % q.nby, bz = b / (q.nbx * q.nby);
+    detect_block(q.finer, q.centre, q.X, q.Y, q.Z, q.pitch, q.mins, q.maxs, J.cap, q.own0, q.own1, bx, by, bz);
 }
 
 // Rank-by-counting sort of a candidate list into raster order (keys are unique voxel indices).
