@@ -17,17 +17,29 @@
 // Kept host code: argument parsing, NIfTI/raw loading, isotropic resampling, the world-coordinate
 // transform and the text feature file.  Output is byte-identical to the reference's CPU path.
 #include <math.h>
+#include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <chrono>
+#include <atomic>
+#include <functional>
+#include <future>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "nifti_min.h"
 #include "s3d.h"
 
 using niftimin::Mat44;
+
+static double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 static int print_options()
 {
@@ -120,50 +132,77 @@ struct Job {
     niftimin::Image im;
     std::vector<float> vol;          // float volume at extraction input resolution (empty while `typed`)
     bool typed = false;              // voxels go to the device in their file datatype (single-device path only)
+    bool need_iso = false;           // anisotropic voxels under -w: resampled on the device before the extraction
+    std::string log;                 // what the loader has to say (printed in job order: lists are loaded in parallel)
     int X = 0, Y = 0, Z = 0;         // input of the extraction (after isotropic resampling)
     int eX = 0, eY = 0, eZ = 0;      // extraction resolution (after -2+/-2-)
 };
 
-// read + (isotropic resampling on the device when needed); allow_typed: keep integer voxels for s3d_extract_typed
-static int load_job(Job &j, const Options &o, s3d_ctx *ctx, bool allow_typed)
+static void logf(Job &j, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+static void logf(Job &j, const char *fmt, ...)
+{
+    char buf[4400];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    j.log += buf;
+}
+
+// Host half of the loader: read the file (zlib inflate for .gz), datatype conversion.  Touches nothing but the job, so
+// the jobs of a list are loaded on several host threads (section 8(f) N1: file decoding off the critical path).
+// allow_typed: keep integer voxels for s3d_extract_typed.
+static int load_job_host(Job &j, const Options &o, bool allow_typed)
 {
     niftimin::Image &im = j.im;
     const char *inPath = j.in.c_str();
     if (o.raw) {
         FILE *f = fopen(inPath, "rb");
-        if (!f) { printf("Error: could not read input file: %s\n", inPath); return -1; }
+        if (!f) { logf(j, "Error: could not read input file: %s\n", inPath); return -1; }
         fseek(f, 0, SEEK_END);
         const long bytes = ftell(f);
         fseek(f, 0, SEEK_SET);
         im.data.resize((size_t)(bytes > 0 ? bytes : 0) / sizeof(float));
         const bool ok = !im.data.empty() && fread(im.data.data(), sizeof(float), im.data.size(), f) == im.data.size();
         fclose(f);
-        if (!ok) { printf("Error: could not read input file: %s\n", inPath); return -1; }
+        if (!ok) { logf(j, "Error: could not read input file: %s\n", inPath); return -1; }
         int rx = o.rawX, ry = o.rawY, rz = o.rawZ;
         if (rx <= 0) {
-            if (!guess_raw_dims(im.data.data(), im.data.size(), rx, ry, rz)) { printf("Error: could not determine raw dimensions: %s\n", inPath); return -1; }
-            printf("Raw dimensions (guessed): %d %d %d\n", rx, ry, rz);
+            if (!guess_raw_dims(im.data.data(), im.data.size(), rx, ry, rz)) { logf(j, "Error: could not determine raw dimensions: %s\n", inPath); return -1; }
+            logf(j, "Raw dimensions (guessed): %d %d %d\n", rx, ry, rz);
         }
-        if (ry <= 0 || rz <= 0 || (size_t)rx * ry * rz > im.data.size()) { printf("Error: bad raw dimensions\n"); return -1; }
+        if (ry <= 0 || rz <= 0 || (size_t)rx * ry * rz > im.data.size()) { logf(j, "Error: bad raw dimensions\n"); return -1; }
         im.nx = rx; im.ny = ry; im.nz = rz;
         memset(&im.qto_xyz, 0, sizeof(Mat44));
         im.qto_xyz.m[0][0] = im.qto_xyz.m[1][1] = im.qto_xyz.m[2][2] = im.qto_xyz.m[3][3] = 1.0f;
         im.sto_xyz = im.qto_xyz;
     } else if (niftimin::read(inPath, im, /*keep_raw=*/true) < 0) {
-        printf("Error: could not read input file: %s\n", inPath);
+        logf(j, "Error: could not read input file: %s\n", inPath);
         return -1;
     }
     // NIfTI voxels stay in their file datatype when they can go to the device as they are (the cast to float
     // then runs there, s3d_extract_typed); the isotropic resampling needs floats
-    const bool need_iso = o.bIso && (im.dx != im.dy || im.dy != im.dz || im.dx != im.dz);
-    j.typed = allow_typed && !im.raw.empty() && !need_iso && im.datatype != 16;
+    j.need_iso = o.bIso && (im.dx != im.dy || im.dy != im.dz || im.dx != im.dz);
+    j.typed = allow_typed && !im.raw.empty() && !j.need_iso && im.datatype != 16;
     if (!im.raw.empty() && !j.typed) {
         im.data.resize((size_t)im.nx * im.ny * im.nz * im.nt);
         niftimin::cast_to_float(im.raw.data(), im.datatype, im.data.size(), im.data.data());
         im.raw.clear();
     }
     j.X = im.nx; j.Y = im.ny; j.Z = im.nz;
-    if (need_iso) {
+    if (!j.need_iso && !j.typed) {
+        j.vol.assign(im.data.begin(), im.data.begin() + (size_t)j.X * j.Y * j.Z);
+        im.data.clear(); im.data.shrink_to_fit();
+    }
+    return 0;
+}
+
+// Device half: isotropic resampling when needed, extraction resolution
+static int load_job_device(Job &j, const Options &o, s3d_ctx *ctx)
+{
+    niftimin::Image &im = j.im;
+    const char *inPath = j.in.c_str();
+    if (j.need_iso) {
         // isotropic resampling (reference featExtract.cpp:118-204): matrices on the host, voxels on the device
         float fMin = im.dx;
         if (im.dy < fMin) fMin = im.dy;
@@ -183,16 +222,34 @@ static int load_job(Job &j, const Options &o, s3d_ctx *ctx, bool allow_typed)
         }
         j.X = nX; j.Y = nY; j.Z = nZ;
         im.dx = im.dy = im.dz = fMin;
-    } else if (!j.typed) {
-        j.vol.assign(im.data.begin(), im.data.begin() + (size_t)j.X * j.Y * j.Z);
+        im.data.clear(); im.data.shrink_to_fit();
     }
-    im.data.clear(); im.data.shrink_to_fit();
     j.eX = j.X; j.eY = j.Y; j.eZ = j.Z;
     if (o.bDouble == 1) { j.eX *= 2; j.eY *= 2; j.eZ *= 2; }
     else if (o.bDouble == -1) { j.eX /= 2; j.eY /= 2; j.eZ /= 2; }
     if (j.eZ <= 1) { printf("Could not read volume: %s\n", inPath); return -1; }
     printf("Input image: i=%d j=%d k=%d\n", j.eX, j.eY, j.eZ);
     return 0;
+}
+
+static int load_job(Job &j, const Options &o, s3d_ctx *ctx, bool allow_typed)
+{
+    const int rc = load_job_host(j, o, allow_typed);
+    fputs(j.log.c_str(), stdout);
+    j.log.clear();
+    return rc < 0 ? rc : load_job_device(j, o, ctx);
+}
+
+// fn(i) for i in [0, n) on up to `threads` host threads
+static void parallel_for(size_t n, int threads, const std::function<void(size_t)> &fn)
+{
+    if (threads > (int)n) threads = (int)n;
+    if (threads <= 1) { for (size_t i = 0; i < n; i++) fn(i); return; }
+    std::atomic<size_t> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([&]() { for (size_t i = next++; i < n; i = next++) fn(i); });
+    for (auto &th : pool) th.join();
 }
 
 // world coordinates (reference featExtract.cpp:436-473, 507-538) + the text feature file
@@ -369,6 +426,9 @@ int main(int argc, char **argv)
     }
 
     // ---- several devices and / or a list of volumes
+    const bool timing = getenv("S3D_CLI_TIMING") != nullptr;     // phase times of the list mode on stderr
+    const double t_start = now_s();
+    double t_load = 0, t_dev = 0, t_extract = 0, t_write = 0;
     s3d_multi *m = nullptr;
     if (s3d_multi_create((int)o.devices.size(), o.devices.data(), 4, &m) != S3D_OK) {
         printf("Error: could not initialise CUDA devices: %s\n", m ? s3d_multi_last_error(m) : "no device");
@@ -376,15 +436,13 @@ int main(int argc, char **argv)
     }
     s3d_ctx *ctx0 = nullptr;       // for the device-side resampling of the loader
     if (s3d_ctx_create(o.devices[0], &ctx0) != S3D_OK) { printf("Error: could not initialise CUDA device %d\n", o.devices[0]); return -1; }
-    for (Job &j : jobs) {
-        printf("Extracting features: %s\n", j.in.c_str());
-        if (load_job(j, o, ctx0, /*allow_typed=*/false) < 0) return -1;
-    }
-    s3d_ctx_destroy(ctx0);
     int rc = 0;
+    const double t_created_global = now_s();
     if (!listPath) {
         // one volume over several devices: z slabs
         Job &j = jobs[0];
+        printf("Extracting features: %s\n", j.in.c_str());
+        if (load_job(j, o, ctx0, /*allow_typed=*/false) < 0) return -1;
         s3d_feature *feats = nullptr;
         int n = 0;
         s3d_status st = s3d_multi_extract_slab(m, j.vol.data(), j.X, j.Y, j.Z, &prm, &feats, &n);
@@ -392,25 +450,66 @@ int main(int argc, char **argv)
         rc = finish_job(j, o, feats, n);
         s3d_free(feats);
     } else {
-        // a list: runs of equal-shaped volumes are sharded over the devices
-        size_t i0 = 0;
-        while (i0 < jobs.size() && rc == 0) {
-            size_t i1 = i0 + 1;
-            while (i1 < jobs.size() && jobs[i1].X == jobs[i0].X && jobs[i1].Y == jobs[i0].Y && jobs[i1].Z == jobs[i0].Z) i1++;
-            const int nb = (int)(i1 - i0);
-            std::vector<const float *> vols(nb);
-            std::vector<s3d_feature *> rows(nb, nullptr);
-            std::vector<int> n_rows(nb, 0);
-            for (int k = 0; k < nb; k++) vols[k] = jobs[i0 + k].vol.data();
-            s3d_status st = s3d_multi_batch_extract(m, vols.data(), nb, jobs[i0].X, jobs[i0].Y, jobs[i0].Z, &prm, rows.data(), n_rows.data());
-            if (st != S3D_OK) { printf("Error: could not extract features, %s.\n", s3d_multi_last_error(m)); rc = -1; }
-            for (int k = 0; k < nb; k++) {
-                if (rc == 0 && finish_job(jobs[i0 + k], o, rows[k], n_rows[k]) < 0) rc = -1;
-                if (rows[k]) s3d_free(rows[k]);
+        // A list, in windows of kWindow jobs: the files of window k+1 are read, inflated and converted on the host
+        // threads while window k is extracted (runs of equal-shaped volumes are sharded over the devices) and its
+        // feature files are written, also on the host threads.  File decoding and text formatting cost two orders of
+        // magnitude more host time per volume than the extraction takes on the GPU.
+        const size_t kWindow = 64;
+        int host_threads = (int)std::thread::hardware_concurrency();
+        if (host_threads < 1) host_threads = 1;
+        if (host_threads > 32) host_threads = 32;
+        std::vector<int> load_rc(jobs.size(), 0);
+        auto load_window = [&](size_t a, size_t b) {
+            parallel_for(b - a, host_threads, [&](size_t k) { load_rc[a + k] = load_job_host(jobs[a + k], o, /*allow_typed=*/false); });
+        };
+        const double t_created = now_s();
+        load_window(0, std::min(kWindow, jobs.size()));
+        t_load += now_s() - t_created;
+        for (size_t a = 0; a < jobs.size() && rc == 0; a += kWindow) {
+            const size_t b = std::min(a + kWindow, jobs.size());
+            std::future<void> next;
+            if (b < jobs.size()) next = std::async(std::launch::async, load_window, b, std::min(b + kWindow, jobs.size()));
+            double t0 = now_s();
+            for (size_t k = a; k < b && rc == 0; k++) {
+                printf("Extracting features: %s\n", jobs[k].in.c_str());
+                fputs(jobs[k].log.c_str(), stdout);
+                if (load_rc[k] < 0 || load_job_device(jobs[k], o, ctx0) < 0) rc = -1;
             }
-            i0 = i1;
+            t_dev += now_s() - t0; t0 = now_s();
+            std::vector<s3d_feature *> rows(b - a, nullptr);
+            std::vector<int> n_rows(b - a, 0);
+            size_t i0 = a;
+            while (i0 < b && rc == 0) {
+                size_t i1 = i0 + 1;
+                while (i1 < b && jobs[i1].X == jobs[i0].X && jobs[i1].Y == jobs[i0].Y && jobs[i1].Z == jobs[i0].Z) i1++;
+                const int nb = (int)(i1 - i0);
+                std::vector<const float *> vols(nb);
+                for (int k = 0; k < nb; k++) vols[k] = jobs[i0 + k].vol.data();
+                s3d_status st = s3d_multi_batch_extract(m, vols.data(), nb, jobs[i0].X, jobs[i0].Y, jobs[i0].Z, &prm, rows.data() + (i0 - a), n_rows.data() + (i0 - a));
+                if (st != S3D_OK) { printf("Error: could not extract features, %s.\n", s3d_multi_last_error(m)); rc = -1; }
+                i0 = i1;
+            }
+            t_extract += now_s() - t0; t0 = now_s();
+            std::atomic<int> write_rc(0);
+            if (rc == 0)
+                parallel_for(b - a, host_threads, [&](size_t k) {
+                    if (finish_job(jobs[a + k], o, rows[k], n_rows[k]) < 0) write_rc = -1;
+                });
+            if (write_rc < 0) rc = -1;
+            for (size_t k = a; k < b; k++) {
+                if (rows[k - a]) s3d_free(rows[k - a]);
+                std::vector<float>().swap(jobs[k].vol);
+            }
+            t_write += now_s() - t0; t0 = now_s();
+            if (next.valid()) next.get();
+            t_load += now_s() - t0;
         }
     }
+    s3d_ctx_destroy(ctx0);
+    if (timing && listPath)
+        fprintf(stderr, "featExtract -l: %zu volumes, %d host threads; startup %.3f s, waiting for file decoding %.3f s, device-side loader %.3f s, "
+                "extraction %.3f s, world transform + feature files %.3f s, total %.3f s\n", jobs.size(), (int)std::thread::hardware_concurrency(),
+                t_created_global - t_start, t_load, t_dev, t_extract, t_write, now_s() - t_start);
     s3d_multi_destroy(m);
     if (rc < 0) return -1;
     printf("\nDone.\n");
