@@ -406,6 +406,43 @@ def run_ours(args):
                              "frac": algorithmic_bytes(SHAPE) / (ms_per_volume * 1e-3) / 1e9 / peak,
                              "note": "whole step incl. keypoint stages vs SURVEY 8(d) algorithmic bytes"}}
 
+    # ---- exact kNN descriptor matching of this volume's rows against a 256-volume database ------
+    match = None
+    if rank == 0:
+        try:
+            import ctypes as C
+            import numpy as np
+            rng = np.random.default_rng(3)
+            n_a, n_b, k = nf, 256 * nf, 2
+            def rank_features(n):
+                f = np.zeros(n, pkg.api.FEATURE_DTYPE)
+                f["pc"] = np.argsort(rng.random((n, 64)), axis=1).astype(np.float32)
+                return f
+            fa, fb = rank_features(n_a), rank_features(n_b)
+            d_a = torch.from_numpy(fa.view(np.uint8)).to(dev); d_b = torch.from_numpy(fb.view(np.uint8)).to(dev)
+            d_i = torch.empty((n_a, k), dtype=torch.int32, device=dev); d_d = torch.empty((n_a, k), dtype=torch.float32, device=dev)
+            def run_match():
+                st_ = eng.L.s3d_match_device(eng.ctx, C.c_void_p(d_a.data_ptr()), n_a, C.c_void_p(d_b.data_ptr()), n_b, k,
+                                             C.c_void_p(d_i.data_ptr()), C.c_void_p(d_d.data_ptr()))
+                assert st_ == 0, st_
+            for _ in range(2): run_match()
+            eng.sync()
+            es = torch.cuda.ExternalStream(eng.stream)
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(es):
+                m0.record(es)
+                for _ in range(5): run_match()
+                m1.record(es)
+            eng.sync()
+            mms = m0.elapsed_time(m1) / 5
+            match = {"workload": "exact %d nearest neighbours of %d SIFT-Rank descriptors among %d (256 volumes), s3d_match_device" % (k, n_a, n_b),
+                     "ms": mms, "pairs_per_s": n_a * n_b / (mms * 1e-3), "fp32_tops": n_a * n_b * 192 / (mms * 1e-3) / 1e12,
+                     "frac_of_fp32_issue_peak": n_a * n_b * 192 / (mms * 1e-3) / 1e12 / 37.2,
+                     "note": "192 separately rounded FP32 operations per descriptor pair (the reference's DistSqrPCs); peak = 148 SMs x 128 lanes x 1.965 GHz"}
+            del d_a, d_b, d_i, d_d
+        except Exception as exc:      # noqa: BLE001
+            match = {"error": repr(exc)[:200]}
+
     # ---- BASELINE config 5 (N > 1): one 512^3 volume with -2+ split into z slabs over the N GPUs ------------
     slab = None
     if world > 1 and not args.no_slab:
@@ -467,6 +504,8 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "e2e_int16": e2e_i16, "pcie": pcie, "gpu_launches": launches_per_volume * nvol,
             "launches_per_volume": launches_per_volume, "roofline": roof, "cpu_baseline": cpu, "ref_cuda_baseline": ref_cuda,
         }
+        if match is not None:
+            line["match"] = match
         if slab is not None:
             line["slab"] = slab
         print(json.dumps(line))
