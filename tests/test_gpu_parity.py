@@ -233,6 +233,27 @@ def test_every_blur_path_bit_exact(pkg, oracle, monkeypatch, env):
         eng.close()
 
 
+@pytest.mark.parametrize("env", [{"S3D_TINY": "0"}, {"S3D_F4_WIDE_MIN_VOXELS": "0", "S3D_F4_MIN_VOXELS": "0"}, {"S3D_SERIAL": "1"},
+                                 {"S3D_NO_GRAPH": "1"}, {"S3D_DETECT2_MIN_VOXELS": "0"}, {"S3D_TAIL_BLOCKS": "1,1,1"}])
+def test_every_pipeline_shape_bit_exact(pkg, oracle, monkeypatch, env):
+    """The launch-count and scheduling choices of the pipeline are not allowed to change a bit: the last octaves as one
+    launch (tiny_octaves_kernel) or as ordinary levels, merged or per-level detection / refinement launches, the wide
+    one-kernel levels inside the pipeline, serial and graph-less execution, grouped describe rows -- rows, keypoints and
+    every pyramid level against the oracle on volumes whose octave chain reaches the tiny tail."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    eng = pkg.Engine(0)
+    try:
+        for shape, seed, nblobs in [((96, 80, 88), 7, 90), ((45, 52, 47), 3, 40)]:
+            vol = pkg.phantom.blob_phantom(shape, seed, nblobs)
+            want = oracle.extract(vol, 0, 0, want_keypoints=True)
+            got = eng.extract(vol)
+            assert len(want["features"]) > 20 and got.tobytes() == want["features"].tobytes(), (env, shape)
+            assert eng.keypoints().tobytes() == want["keypoints"].tobytes(), (env, shape)
+    finally:
+        eng.close()
+
+
 def test_asymmetric_taps_take_the_general_path(pkg, engine):
     """Product sharing needs w[j] == w[2R-j]; taps that are not symmetric must fall back and still follow
     the left-to-right sum (checked against a numpy restatement of filter_1d)."""
