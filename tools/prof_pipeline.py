@@ -4,6 +4,8 @@ import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 pkg = importlib.import_module("3d_sift_cuda_b200")
+if os.environ.get("PROF_LIB"):      # A/B runs of two builds on the same box
+    pkg.api.library_path = lambda: os.path.join(os.path.dirname(pkg.api.__file__), os.environ["PROF_LIB"])
 vol = pkg.phantom.brain_phantom()
 Z, Y, X = vol.shape
 e = pkg.Engine(0)
