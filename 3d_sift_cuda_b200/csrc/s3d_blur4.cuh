@@ -244,7 +244,10 @@ blur_f4_kernel(const __grid_constant__ CUtensorMap in_map, const float *__restri
 // instances: 64 x TY tiles (TY = 16: two CTAs of 7-8 warps per SM; TY = 32: one CTA of 11-12 warps), 2 columns per
 // consumer thread, 16-output x segments
 template <int R, int TY> struct F4Pick {
-    static constexpr int VX = 2, KX = 16, XW = TY == 16 ? (R <= 4 ? 3 : 4) : 4;
+    // producer warps: the three x-pass items of a 64 x 16 tile plane on TWO warps for radii <= 4 (a producer item is
+    // ~130 instructions, a consumer warp issues ~250 per plane: with three producers they idled at xb_empty half of the time;
+    // measured 39.2 -> 37.2 us at 9 taps, 33.2 -> 32.0 us at 7); radii 5, 6 need two full warpgroups for setmaxnreg
+    static constexpr int VX = 2, KX = 16, XW = TY == 16 ? (R <= 4 ? 2 : 4) : 4;
     static constexpr bool MRING = R <= 4;      // else the ring would not leave room for the resident CTAs
     using Cfg = F4Cfg<R, VX, KX, TY, XW, MRING>;
     template <bool DOG> static auto kernel() { return blur_f4_kernel<R, VX, KX, TY, XW, MRING, DOG>; }

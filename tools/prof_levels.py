@@ -5,6 +5,8 @@ import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 pkg = importlib.import_module("3d_sift_cuda_b200")
+if os.environ.get("PROF_LIB"):      # A/B runs of two builds on the same box
+    pkg.api.library_path = lambda: os.path.join(os.path.dirname(pkg.api.__file__), os.environ["PROF_LIB"])
 X, Y, Z = [int(v) for v in os.environ.get("PROF_SHAPE", "182,218,182").split(",")]
 pitch = (X + 7) // 8 * 8
 rng = np.random.default_rng(0)
