@@ -263,7 +263,11 @@ template <int R, int TY> struct F4Pick {
     // ~130 instructions, a consumer warp issues ~250 per plane: with three producers they idled at xb_empty half of the time;
     // measured 39.2 -> 37.2 us at 9 taps, 33.2 -> 32.0 us at 7); radii 5, 6 need two full warpgroups for setmaxnreg
     static constexpr int VX = 2, KX = 16, XW = TY == 16 ? (R <= 4 ? 2 : 4) : 4;
-    static constexpr bool MRING = R <= 4;      // else the ring would not leave room for the resident CTAs
+    // The DoG minuend from the ring costs R + 1 more stages.  At 9 taps that is 115 KB per CTA instead of 82 KB: the level
+    // itself runs the same (37.0 us either way) but a batch loses 2 % (475 -> 465 us per volume with the minuend read
+    // from L2): what shares the SM with a level CTA there are other volumes' kernels and their shared memory.  At 7
+    // taps the ring is kept (99 KB; without it the warm level is 5 % slower and the batch the same)
+    static constexpr bool MRING = R <= 3;
     using Cfg = F4Cfg<R, VX, KX, TY, XW, MRING>;
     template <bool DOG> static auto kernel() { return blur_f4_kernel<R, VX, KX, TY, XW, MRING, DOG>; }
 };
