@@ -27,7 +27,10 @@
 
 namespace s3d {
 
-constexpr int kF4TX = 64, kF4KY = 4, kF4Ahead = 3, kF4NXB = 4;      // kF4NXB: depth of the x-pass -> y-pass hand-over ring
+// kF4NXB: depth of the x-pass -> y-pass hand-over ring.  The level runs the same with 2, 3 or 4 slots (257.9 / 259.0 / 259.0 us for the
+// six levels of octave 0), but every slot is 6.5-8.7 KB of shared memory per CTA and a batch pays for the footprint of
+// the level CTAs (other volumes' kernels share their SMs): 464 us per volume with 4 slots, 452 with 3, 449 with 2
+constexpr int kF4TX = 64, kF4KY = 4, kF4Ahead = 3, kF4NXB = 3;
 
 // R: radius, VX: columns per consumer thread (2 | 4), KX: outputs per x-pass segment (8 | 16), TY: tile rows, XW: producer warps,
 // MRING: the DoG minuend is read from the ring (R + 1 more stages) instead of from global memory (L2)
