@@ -8,16 +8,16 @@
 // as FMUL/FADD (tools/mb/f32x2_bench.cu: 124 lane-ops/clk/SM either way), which halves the issue slots of the
 // arithmetic and leaves room for the shared-memory traffic of a tiled kernel.
 //
-//   * a CTA owns a 64x32 (x,y) tile and a z segment, and walks the segment plane by plane;
+//   * a CTA owns a 64 x 16 (or 64 x 32) (x,y) tile and a z segment, and walks the segment plane by plane;
 //   * TMA (cp.async.bulk.tensor.3d + mbarrier) stages every input plane's tile + halo into a ring, kF4Ahead planes
 //     ahead; elements outside the volume are zero-filled = the reference's zero padding (GaussBlur3D.cpp:329-479);
-//   * producer warps (x pass): ring stage -> shared buffer XB (double buffered), segments of KX outputs on packed
+//   * producer warps (x pass): ring stage -> shared buffer XB (a hand-over ring of kF4NXB slots), segments of KX outputs on packed
 //     pairs (even/odd pair alignment costs one MOV per input), 8 lanes = 8 rows, 128-bit shared accesses, row
 //     pitch / 4 odd -> conflict free;
 //   * consumer warps (y and z passes): a thread owns VX adjacent columns (float2 / float4 = packed operands) and
 //     4 rows.  y pass: XB -> registers.  z pass: scatter march in registers, 2R+1 packed partial sums per output,
 //     rotating slot picked by a switch on (plane mod 2R+1) so every accumulator index is static.  The DoG minuend
-//     (input level at the output position) is still in the ring R planes later;
+//     (input level at the output position) is still in the ring R planes later (radii <= 3), or read back from L2;
 //   * no CTA-wide barrier in the plane loop: producers and consumers hand XB over through two mbarrier pairs
 //     (full / empty), and a ring stage is refilled as soon as the consumers' `empty` arrival proves that its
 //     plane has been read as a minuend (one ncu capture of the barrier-per-plane predecessor: 40 % issue
@@ -267,9 +267,9 @@ template <int R, int TY> struct F4Pick {
     // measured 39.2 -> 37.2 us at 9 taps, 33.2 -> 32.0 us at 7); radii 5, 6 need two full warpgroups for setmaxnreg
     static constexpr int VX = 2, KX = 16, XW = TY == 16 ? (R <= 4 ? 2 : 4) : 4;
     // The DoG minuend from the ring costs R + 1 more stages.  At 9 taps that is 115 KB per CTA instead of 82 KB: the level
-    // itself runs the same (37.0 us either way) but a batch loses 2 % (475 -> 465 us per volume with the minuend read
+    // (measured with a 4-slot hand-over ring; 68 KB now) itself runs the same (37.0 us either way) but a batch loses 2 % (475 -> 465 us per volume with the minuend read
     // from L2): what shares the SM with a level CTA there are other volumes' kernels and their shared memory.  At 7
-    // taps the ring is kept (99 KB; without it the warm level is 5 % slower and the batch the same)
+    // taps the ring is kept (85 KB with the 3-slot hand-over ring; without it the warm level is 5 % slower and the batch the same)
     static constexpr bool MRING = R <= 3;
     using Cfg = F4Cfg<R, VX, KX, TY, XW, MRING>;
     template <bool DOG> static auto kernel() { return blur_f4_kernel<R, VX, KX, TY, XW, MRING, DOG>; }
