@@ -771,11 +771,11 @@ struct HistSmem {                    // orient_hist_kernel, orient_b_kernel
         struct { float patch[PVP], h1[PVP], h2[PVP]; } p;
         float sorted[kSphP * 8];
     } a;
-    union {                          // contrib (until the splat has sorted it) -> peak lists
-        float contrib[kSphP * 8];
+    union {                          // splat terms of a voxel (until the splat has sorted them) -> the histogram -> peak lists
+        float4 cw[kSphP];            // value and the three lower-corner weights: its 8 contributions are formed when they are scattered
+        float h0[PVP];
         struct { s3d_cand peaks[128], psort[128]; unsigned char pflag[736]; } k;
     } b;
-    float h0[PVP];
     int cbase[kSphP];
     unsigned char cnt[kHistWarps][kBinsP];   // entries per (warp range, bin), then (low byte of) their exclusive prefix over the ranges
     unsigned char lrank[kSphP * 8];          // rank of an entry among the entries of its warp range that hit the same bin
@@ -801,6 +801,33 @@ struct HistSmem {                    // orient_hist_kernel, orient_b_kernel
 #define SPLAT_ARGS
 #define SPLAT_PASS
 #endif
+// Splat terms of one voxel at histogram position (px,py,pz) with value v (fioIncPixelTrilinearInterp, reference
+// FeatureIO.cpp:853-889): bin of the lower corner and (v, wx, wy, wz); its 8 contributions are the products below, formed
+// when the splat scatters them (8 floats per voxel would be 15.6 KB of shared memory per CTA, and a batch pays for every
+// kilobyte the tail CTAs hold: +16 KB here = -6 % throughput, profiles/README.md).
+__device__ __forceinline__ void make_contrib(float px, float py, float pz, float v, float4 &cw, int &base)
+{
+    int iX, iY, iZ;
+    float wx, wy, wz;
+    interp_coord(px, (float)PD, iX, wx);
+    interp_coord(py, (float)PD, iY, wy);
+    interp_coord(pz, (float)PD, iZ, wz);
+    base = (iZ * PD + iY) * PD + iX;
+    cw = make_float4(v, wx, wy, wz);
+}
+__device__ __forceinline__ void contrib_values(const float4 cw, float *c8)
+{
+    const float v = cw.x, wx = cw.y, wy = cw.z, wz = cw.w;
+    c8[0] = v * wx * wy * wz;
+    c8[1] = v * (1.0f - wx) * wy * wz;
+    c8[2] = v * wx * (1.0f - wy) * wz;
+    c8[3] = v * (1.0f - wx) * (1.0f - wy) * wz;
+    c8[4] = v * wx * wy * (1.0f - wz);
+    c8[5] = v * (1.0f - wx) * wy * (1.0f - wz);
+    c8[6] = v * wx * (1.0f - wy) * (1.0f - wz);
+    c8[7] = v * (1.0f - wx) * (1.0f - wy) * (1.0f - wz);
+}
+
 __device__ __forceinline__ int splat_corner_offset(int c) { return (c & 1) + ((c >> 1) & 1) * PD + ((c >> 2) & 1) * PD * PD; }
 // does the 2x2x2 footprint that starts at bin `base` cover bin `bin`?  (offsets 0, 1, 11, 12 and the same + 121)
 __device__ __forceinline__ int splat_covers(int bin, int base)
@@ -895,8 +922,8 @@ __device__ void splat_histogram_sorted(HistSmem &S, float *hist, int nsph SPLAT_
         const int base = S.cbase[n];
         if (base >= 0) {
             const int w = n / vr;
-            const float4 c0 = *reinterpret_cast<const float4 *>(&S.b.contrib[n * 8]), c1 = *reinterpret_cast<const float4 *>(&S.b.contrib[n * 8 + 4]);
-            const float cv[8] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w };
+            float cv[8];
+            contrib_values(S.b.cw[n], cv);
             const uint2 lr = *reinterpret_cast<const uint2 *>(&S.lrank[n * 8]);
 #pragma unroll
             for (int c = 0; c < 8; c++) {
@@ -936,25 +963,6 @@ __device__ void splat_histogram_sorted(HistSmem &S, float *hist, int nsph SPLAT_
     if (t == 0) hist[PV] = 0.0f;
     __syncthreads();
     PHASE(25);
-}
-
-// contributions of one voxel at histogram position (px,py,pz) with value v
-__device__ __forceinline__ void make_contrib(float px, float py, float pz, float v, float *c8, int &base)
-{
-    int iX, iY, iZ;
-    float wx, wy, wz;
-    interp_coord(px, (float)PD, iX, wx);
-    interp_coord(py, (float)PD, iY, wy);
-    interp_coord(pz, (float)PD, iZ, wz);
-    base = (iZ * PD + iY) * PD + iX;
-    c8[0] = v * wx * wy * wz;
-    c8[1] = v * (1.0f - wx) * wy * wz;
-    c8[2] = v * wx * (1.0f - wy) * wz;
-    c8[3] = v * (1.0f - wx) * (1.0f - wy) * wz;
-    c8[4] = v * wx * wy * (1.0f - wz);
-    c8[5] = v * (1.0f - wx) * wy * (1.0f - wz);
-    c8[6] = v * wx * (1.0f - wy) * (1.0f - wz);
-    c8[7] = v * (1.0f - wx) * (1.0f - wy) * (1.0f - wz);
 }
 
 // regFindFEATUREIOPeaks + lvSortHighLow on an 11^3 histogram (reference MultiScale.cpp:1987-2121,
@@ -1125,16 +1133,16 @@ __global__ void __launch_bounds__(kHistThreads) orient_hist_kernel(const int *__
                 for (int k = 0; k < 3; k++) u[k] = e[k] * fRadius / fEdgeMag;
                 for (int k = 0; k < 3; k++) u[k] = u[k] + fRadius;
                 make_contrib((float)((double)u[0] + 0.5), (float)((double)u[1] + 0.5), (float)((double)u[2] + 0.5),
-                             fEdgeMag, &S.b.contrib[n * 8], base);
+                             fEdgeMag, S.b.cw[n], base);
             }
             S.cbase[n] = base;
         }
         __syncthreads();
         PHASE(5);
-        splat_histogram_sorted(S, S.h0, nsph SPLAT_PASS);
+        splat_histogram_sorted(S, S.b.h0, nsph SPLAT_PASS);
         PHASE(6);
-        if (c_tab.n_hist_taps == 3) blur_patch3(S.h0, S.a.p.h2, S.taps);
-        else blur_patch(S.h0, S.a.p.h1, S.a.p.h2, S.taps, c_tab.n_hist_taps);
+        if (c_tab.n_hist_taps == 3) blur_patch3(S.b.h0, S.a.p.h2, S.taps);
+        else blur_patch(S.b.h0, S.a.p.h1, S.a.p.h2, S.taps, c_tab.n_hist_taps);
         PHASE(7);
         find_sort_peaks(S.a.p.h2, S.b.k.pflag, S.b.k.psort, S.b.k.peaks, &S.np);
         PHASE(8);
@@ -1202,16 +1210,16 @@ __global__ void __launch_bounds__(kHistThreads) orient_b_kernel(const int *__res
                 vec_norm(perp);
                 for (int k = 0; k < 3; k++) { perp[k] = perp[k] * fRadius; perp[k] = perp[k] + fRadius; }
                 make_contrib((float)((double)perp[0] + 0.5), (float)((double)perp[1] + 0.5), (float)((double)perp[2] + 0.5),
-                             fEdgeMag, &S.b.contrib[n * 8], base);
+                             fEdgeMag, S.b.cw[n], base);
             }
             S.cbase[n] = base;
         }
         __syncthreads();
         PHASE(9);
-        splat_histogram_sorted(S, S.h0, nsph SPLAT_PASS);
+        splat_histogram_sorted(S, S.b.h0, nsph SPLAT_PASS);
         PHASE(10);
-        if (c_tab.n_hist_taps == 3) blur_patch3(S.h0, S.a.p.h2, S.taps);
-        else blur_patch(S.h0, S.a.p.h1, S.a.p.h2, S.taps, c_tab.n_hist_taps);
+        if (c_tab.n_hist_taps == 3) blur_patch3(S.b.h0, S.a.p.h2, S.taps);
+        else blur_patch(S.b.h0, S.a.p.h1, S.a.p.h2, S.taps, c_tab.n_hist_taps);
         PHASE(11);
         find_sort_peaks(S.a.p.h2, S.b.k.pflag, S.b.k.psort, S.b.k.peaks, &S.np);
         PHASE(12);
