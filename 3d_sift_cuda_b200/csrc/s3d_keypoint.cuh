@@ -187,8 +187,10 @@ constexpr int PVP = 1332;   // patch arrays are padded to a multiple of 4 floats
 
 // sampleImage3D (reference MultiScale.cpp:2614-2714): inv = inverse orientation, already in smem.
 // A thread takes U samples per round; the round is fully unrolled and branch-light so the 8 corner loads of all U
-// samples are in flight together (the gather is pure latency otherwise).
-template <int U = 4>
+// samples are in flight together (the gather is pure latency otherwise).  U = 2: with 4 the gather of one keypoint is
+// 6 % shorter but orient_patch_kernel needs 108 registers instead of 63, and a batch pays for the registers the tail
+// CTAs hold (444.8 against 432.5 us per volume, same box; U = 1: 48 registers, 432.8 us).
+template <int U = 2>
 __device__ void gather_patch(const float *__restrict__ img, int X, int Y, int Zg, int z_off, int pitch,
                              float fx, float fy, float fz, float scale, const float *inv, float *patch)
 {
