@@ -196,7 +196,7 @@ struct Tuning {
     bool f4_ctas_forced = false;
     int f4_ctas = 0;             // S3D_F4_CTAS: CTAs the one-kernel level aims for (0 = resident CTAs per SM x SMs)
     int xy2_ctas = 2;            // S3D_XY2_CTAS_PER_SM: persistent x+y CTAs per SM (contexts of an s3d_batch use 1)
-    bool xy2_ctas_forced = false;
+    bool xy2_ctas_forced = false, xy2_threads_forced = false;
     XY2Tune xy2;                 // S3D_XY2_SMEM_KB, S3D_XY2_TX / S3D_XY2_TY, S3D_XY2_KY, S3D_XY2_THREADS: tile choice of the x+y kernel
     int z2_vec = 0;              // S3D_Z2_VEC=2|4: columns per thread of the z march (0 = by radius)
     int march_target = 0;        // S3D_MARCH_TARGET: threads wanted in flight in the z march (0 = 256 per SM)
@@ -242,7 +242,7 @@ static Tuning tuning_from_env()
     t.xy2.force_ty = env_int("S3D_XY2_TY", 0);
     v = env_int("S3D_XY2_KY", 0);
     if (v == 8 || v == 16) t.xy2.ky = v;
-    if (env_int("S3D_XY2_THREADS", 0) == 128) t.xy2.threads = 128;
+    { const int v2 = env_int("S3D_XY2_THREADS", 0); if (v2 == 128 || v2 == 256) { t.xy2.threads = v2; t.xy2_threads_forced = true; } }
     v = env_int("S3D_Z2_VEC", 0);
     if (v == 2 || v == 4) t.z2_vec = v;
     t.march_target = env_int("S3D_MARCH_TARGET", 0);
@@ -1524,6 +1524,9 @@ extern "C" s3d_status s3d_batch_create(int device, int n_contexts, s3d_batch **o
             return st;
         }
         if (!c->tune.xy2_ctas_forced && n_contexts > 1) c->tune.xy2_ctas = 1;      // throughput mode, see launch_blur_xy2
+        // ... of 128 threads: half the registers and warps of the x+y CTA for the kernels of the other volumes on the SM
+        // (432.6 -> 426.4 us per volume; alone on the GPU 256 threads are faster)
+        if (!c->tune.xy2_threads_forced && n_contexts > 1) c->tune.xy2.threads = 128;
         // ... and the z march runs as one segment: the threads it lacks to cover the memory latency alone are
         // provided by the other volumes in flight, and no halo planes are read twice (S3D_MARCH_TARGET overrides)
         if (c->tune.march_target == 0 && n_contexts > 1) c->tune.march_target = 1;
